@@ -1,0 +1,149 @@
+/*
+ * wdb200.h -- C ABI of libwdb200.so, the B200-native (sm_100a) rollout kernels that
+ * replace WarpDrive's JIT-compiled CUDA module.
+ *
+ * Boundary being replaced (reference = salesforce/warp-drive v2.7.1): the reference
+ * looks kernels up BY NAME in a pycuda module and launches them with positional
+ * arguments (warp_drive/managers/pycuda_managers/pycuda_function_manager.py:319-388,
+ * `get_function(name)(*args, block=, grid=)`).  Each entry point below takes the same
+ * arguments, in the same order, as the reference kernel it replaces, with three
+ * changes: (1) a leading `stream` (cudaStream_t as void*; NULL = legacy default
+ * stream), (2) the compile-time constants wkNumberEnvs / wkNumberAgents /
+ * wkBlocksPerEnv (warp_drive/cuda_includes/template_env_config.h:19-21) become run-time
+ * arguments, (3) `bool` kernel parameters become int32 (the reference passes np.int32
+ * into `bool` params, SURVEY.md section 8 "Python-side arg passing").
+ *
+ * Conventions
+ *   - every function returns a cudaError_t as int (0 == cudaSuccess) and never throws;
+ *     wdb_error_string() turns it into text.  Launches are asynchronous on `stream`.
+ *   - all buffers are caller-owned device memory (torch CUDA tensors), row-major,
+ *     C-contiguous, 32-bit elements.  State arrays are updated in place
+ *     (warp_drive/env_wrapper.py:347-352).
+ *   - the library allocates nothing; RNG state is a caller-provided blob of
+ *     wdb_rng_state_bytes(n_streams) bytes.
+ *   - one host thread per process, one process per GPU.
+ */
+#ifndef WDB200_H_
+#define WDB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WDB_ABI_VERSION 1
+
+int wdb_abi_version(void);
+const char *wdb_error_string(int err);
+/* number of kernel launches issued through this library since load (bench.py's
+ * `gpu_launches` evidence) */
+long long wdb_launch_count(void);
+
+/* ------------------------------------------------------------------ RNG ------ */
+/* Replaces init_random / free_random (warp_drive/cuda_includes/core/random.cu:14-31):
+ * the reference heap-allocates one XORWOW curandState per (env, agent) thread; here the
+ * state is a flat caller-owned blob: {u64 seed, u64 n_streams, u64 offset[n_streams]}
+ * driving a counter-based Philox4x32-10 (key = seed, counter = {offset, stream}). */
+long long wdb_rng_state_bytes(long long n_streams);
+int wdb_rng_init(void *stream, void *rng_state, long long n_streams,
+                 unsigned long long seed);
+
+/* Replaces sample_actions (random.cu:51-85; launched from PyCUDASampler.sample,
+ * pycuda_function_manager.py:532-572).  probs [n_envs, n_agents, n_actions] f32.
+ * actions [n_envs, n_agents, 1] i32.  cum_distr [n_envs, n_agents, n_actions] f32 or
+ * NULL (the reference always materialises it; it is scratch).  actions_combined
+ * (optional) receives the same index at [pos * combined_stride + combined_offset] --
+ * the reference does that with a separate torch copy (trainer_base.py:507-512).
+ * uniforms (optional, test hook): if non-NULL the draw p is read from uniforms[pos]
+ * instead of the RNG, which makes the index selection parity-testable. */
+int wdb_sample_actions(void *stream, void *rng_state, const float *probs, int *actions,
+                       float *cum_distr, int n_envs, int n_agents, int n_actions,
+                       int use_argmax, int *actions_combined, int combined_stride,
+                       int combined_offset, const float *uniforms);
+
+/* Replaces the numba-only sample_ou_process (warp_drive/numba_includes/core/random.py:
+ * 74-105): ou = (1-damping)*ou + stddev*N(0,1); action = mean + scale*ou.
+ * normals (optional, test hook) replaces the N(0,1) draw. */
+int wdb_sample_ou_process(void *stream, void *rng_state, const float *mean,
+                          float *actions, float *ou_state, int n_envs, int n_agents,
+                          float damping, float stddev, float scale,
+                          const float *normals);
+
+/* ------------------------------------------------------------------ reset ---- */
+/* Replaces reset_in_{float,int}_when_done_{2d,3d} + undo_done_flag_and_reset_timestep
+ * (warp_drive/cuda_includes/core/reset.cu:9-75; one launch per registered array in
+ * PyCUDAEnvironmentReset.reset_when_done_deterministic, pycuda_function_manager.py:
+ * 668-753) and the numba-only reset_when_done_{1,2,3}d_from_pool
+ * (numba_includes/core/pool_reset.py:15-52) with ONE launch over a device-resident
+ * descriptor table. */
+typedef struct wdb_reset_desc {
+  void *dst;                /* data[env]            */
+  const void *ref;          /* data_at_reset[env] or pool[row]                      */
+  long long bytes_per_env;  /* multiple of 4                                        */
+  long long pool_rows;      /* 0: deterministic (ref indexed by env); >0: pool size */
+} wdb_reset_desc;
+
+int wdb_reset_when_done(void *stream, const wdb_reset_desc *table_dev, int n_arrays,
+                        int *done, int *timestep, int n_envs, int force_reset,
+                        int undo_done_and_timestep, void *pool_rng_state);
+
+/* ------------------------------------------------------------------ log ------ */
+/* Replace reset_log_mask / update_log_mask / log_one_step_in_{float,int}
+ * (warp_drive/cuda_includes/core/log.cu:11-62). */
+int wdb_reset_log_mask(void *stream, int *log_mask, int episode_length);
+int wdb_update_log_mask(void *stream, int *log_mask, int timestep, int episode_length);
+int wdb_log_one_step(void *stream, void *log, const void *data, int n_agents,
+                     int feature_dim, int timestep, int episode_length, int env_id);
+
+/* ------------------------------------------------------------------ envs ----- */
+/* Replaces testkernel (example_envs/dummy_env/test_step.cu:9-45). */
+int wdb_testkernel(void *stream, int n_envs, int n_agents, float *x, int *y, int *done,
+                   int *actions, float multiplier, int target, int step,
+                   int episode_length);
+
+/* Replaces CudaTagGridWorldStep (example_envs/tag_gridworld/
+ * tag_gridworld_step_pycuda.cu:112-251; argument order of tag_gridworld.py:353-368).
+ * index_to_action: device int[10], the reference's __constant__ kIndexToActionArr. */
+int wdb_tag_gridworld_step(void *stream, int n_envs, int n_agents, int *loc_x,
+                           int *loc_y, const int *actions, int *done, float *rewards,
+                           float *obs, float wall_hit_penalty,
+                           float tag_reward_for_tagger, float tag_penalty_for_runner,
+                           float step_cost_for_tagger, int use_full_observation,
+                           int world_boundary, int *env_timestep, int episode_length,
+                           const int *index_to_action);
+
+/* Replaces CudaTagContinuousStep (example_envs/tag_continuous/
+ * tag_continuous_step_pycuda.cu:351-520; argument order of tag_continuous.py:806-840).
+ * neighbor_distances / neighbor_ids_sorted_by_distance are the reference's O(N^2)
+ * global scratch; they may be NULL (the B200 kernel keeps the sweep on chip).
+ * stats (optional, device int[4]): [0] += agents that took the exact tie-resolution
+ * path, [1] += tags. */
+int wdb_tag_continuous_step(
+    void *stream, int n_envs, int n_agents, int blocks_per_env, float *loc_x,
+    float *loc_y, float *speed, float *direction, float *acceleration,
+    const int *agent_types, float *edge_hit_reward_penalty, float edge_hit_penalty,
+    float grid_length, const float *acceleration_actions, const float *turn_actions,
+    float max_speed, int num_other_agents_observed, const float *skill_levels,
+    int runner_exits_game_after_tagged, int *still_in_the_game,
+    int use_full_observation, float *obs, const int *action_indices,
+    float *neighbor_distances, int *neighbor_ids_sorted_by_distance,
+    int *nearest_neighbor_ids, float *rewards, const float *step_rewards,
+    int *num_runners, float distance_margin_for_reward, float tag_reward_for_tagger,
+    float tag_penalty_for_runner, float end_of_game_reward_for_runner, int *done,
+    int *env_timestep, int episode_length, int *stats);
+
+/* Replaces NumbaClassicControlCartPoleEnvStep (example_envs/single_agent/
+ * classic_control/cartpole/cartpole_step_numba.py:6-83; argument order of
+ * cartpole.py:105-122). */
+int wdb_cartpole_step(void *stream, int n_envs, float *state, const int *action,
+                      int *done, float *reward, float *obs, float gravity,
+                      float masspole, float total_mass, float length,
+                      float polemass_length, float force_mag, float tau,
+                      float theta_threshold_radians, float x_threshold,
+                      int *env_timestep, int episode_length);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WDB200_H_ */

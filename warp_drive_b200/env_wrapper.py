@@ -1,0 +1,168 @@
+"""EnvWrapper: runs an environment on the CPU (`env_backend="cpu"`, NumPy step) or as
+`num_envs` device-resident replicas stepped by libwdb200 kernels.
+
+Same constructor and methods as the reference wrapper (warp_drive/env_wrapper.py:28-408):
+`reset_all_envs / reset_only_done_envs / step_all_envs / init_reset_pool /
+custom_reset_all_envs / obs_at_reset / reset / step`.  `env_backend` accepts the
+reference's "pycuda" and "numba" (both mean "the native B200 backend" here), "b200", and
+"cpu".  The first reset runs on the host and pushes the (replicated) initial state to
+HBM once; every later reset and every step is device-only.
+"""
+import logging
+
+import numpy as np
+
+from warp_drive_b200.utils.gpu_environment_context import CUDAEnvironmentContext
+from warp_drive_b200.utils.spaces import obs_dict_to_spaces
+
+_DEVICE_BACKENDS = ("pycuda", "numba", "b200")
+
+
+class EnvWrapper:
+    def __init__(self, env_obj=None, env_name=None, env_config=None, num_envs=1,
+                 blocks_per_env=None, env_backend="cpu", testing_mode=False,
+                 testing_bin_filename=None, env_registrar=None, event_messenger=None,
+                 process_id=0, use_cuda=None):
+        if use_cuda is not None:  # pre-1.8 argument (reference Argfix, env_wrapper.py:45)
+            logging.warning("EnvWrapper(use_cuda=...) is deprecated, use env_backend")
+            env_backend = use_cuda
+        if isinstance(env_backend, bool):
+            env_backend = "pycuda" if env_backend else "cpu"
+
+        if env_obj is not None:
+            self.env = env_obj
+        else:
+            assert env_name is not None and env_config is not None and env_registrar is not None
+            self.env = env_registrar.get(env_name, env_backend)(**env_config)
+
+        self.n_agents = self.env.num_agents
+        self.episode_length = self.env.episode_length
+        assert self.env.name
+        self.name = self.env.name
+
+        obs = self.obs_at_reset()
+        self.env.observation_space = obs_dict_to_spaces(obs)
+        assert set(self.env.observation_space.keys()) == set(self.env.action_space.keys())
+
+        if env_backend not in _DEVICE_BACKENDS + ("cpu",):
+            logging.warning("Environment backend not recognized, defaulting to cpu")
+            env_backend = "cpu"
+        self.env_backend = env_backend
+        if hasattr(self.env, "env_backend"):
+            self.env.env_backend = env_backend
+
+        # first reset on the host, later resets on the device
+        self.reset_on_host = True
+
+        if self.env_backend == "cpu":
+            return
+
+        from warp_drive_b200.managers.data_manager import CUDADataManager
+        from warp_drive_b200.managers.function_manager import (
+            CUDAEnvironmentReset, CUDAFunctionFeed, CUDAFunctionManager,
+        )
+
+        assert isinstance(self.env, CUDAEnvironmentContext), (
+            f"{self.env_backend} backend requires the environment to be an instance of "
+            "CUDAEnvironmentContext")
+        assert num_envs >= 1
+        self.n_envs = num_envs
+        # the library picks its own launch geometry; blocks_per_env is recorded only
+        # because env classes read it back from the managers
+        self.blocks_per_env = 1 if blocks_per_env is None else int(blocks_per_env)
+
+        self.cuda_data_manager = CUDADataManager(
+            num_agents=self.n_agents, episode_length=self.episode_length,
+            num_envs=self.n_envs, blocks_per_env=self.blocks_per_env)
+        self.cuda_function_manager = CUDAFunctionManager(
+            num_agents=int(self.cuda_data_manager.meta_info("n_agents")),
+            num_envs=int(self.cuda_data_manager.meta_info("n_envs")),
+            blocks_per_env=int(self.cuda_data_manager.meta_info("blocks_per_env")),
+            process_id=process_id)
+        # no nvcc / numba JIT: the kernels are prebuilt in libwdb200.so
+        self.cuda_function_manager.initialize_default_functions()
+        self.cuda_function_feed = CUDAFunctionFeed(self.cuda_data_manager)
+
+        prefix = "Numba" if self.env_backend == "numba" else "Cuda"
+        step_function = f"{prefix}{self.name}Step"
+        context_ready = self.env.initialize_step_function_context(
+            cuda_data_manager=self.cuda_data_manager,
+            cuda_function_manager=self.cuda_function_manager,
+            cuda_step_function_feed=self.cuda_function_feed,
+            step_function_name=step_function)
+        assert context_ready, "The environment class failed to initialize the CUDA step function"
+        self.env_resetter = CUDAEnvironmentReset(function_manager=self.cuda_function_manager)
+        self.env_resetter.register_custom_reset_function(
+            self.cuda_data_manager, reset_function_name=f"Cuda{self.name}Reset")
+
+    # ------------------------------------------------------------------ reset / step
+    def reset_all_envs(self):
+        self.env.timestep = 0
+        obs = self.obs_at_reset() if self.reset_on_host else None
+        if self.env_backend == "cpu":
+            return obs
+        if not self.reset_on_host:
+            self.env_resetter.reset_when_done(self.cuda_data_manager, mode="force_reset")
+            return {}
+
+        def replicate(array):
+            array = np.asarray(array)
+            return np.broadcast_to(array, (self.n_envs,) + array.shape).copy()
+
+        data = self.env.get_data_dictionary()
+        tensors = self.env.get_tensor_dictionary()
+        pools = self.env.get_reset_pool_dictionary()
+        for feed in (data, tensors):
+            for key in feed:
+                if feed[key]["attributes"]["save_copy_and_apply_at_reset"]:
+                    feed[key]["data"] = replicate(feed[key]["data"])
+        for key in pools:
+            attrs = pools[key]["attributes"]
+            if not attrs.get("is_reset_pool", False):
+                continue
+            target = attrs["reset_target"]
+            for feed in (data, tensors):
+                if target in feed:
+                    assert not feed[target]["attributes"]["save_copy_and_apply_at_reset"]
+                    feed[target]["data"] = replicate(feed[target]["data"])
+                    break
+            else:
+                raise Exception(
+                    f"Fail to locate the target data {target} for the reset pool in "
+                    "neither data_dictionary nor tensor_dictionary")
+        self.cuda_data_manager.push_data_to_device(data)
+        self.cuda_data_manager.push_data_to_device(tensors, torch_accessible=True)
+        self.cuda_data_manager.push_data_to_device(pools)
+        self.reset_on_host = False
+        return obs
+
+    def init_reset_pool(self, seed=None):
+        self.env_resetter.init_reset_pool(self.cuda_data_manager, seed)
+
+    def reset_only_done_envs(self, undo_done_after_reset=True):
+        assert self.env_backend != "cpu" and not self.reset_on_host, (
+            "reset_only_done_envs() only works for device backends after the first reset")
+        self.env_resetter.reset_when_done(
+            self.cuda_data_manager, mode="if_done",
+            undo_done_after_reset=undo_done_after_reset)
+        return {}
+
+    def custom_reset_all_envs(self, args=None, block=None, grid=None):
+        self.env_resetter.custom_reset(args=args, block=block, grid=grid)
+        return {}
+
+    def step_all_envs(self, actions=None):
+        if self.env_backend != "cpu":
+            self.env.step()
+            return None
+        assert actions is not None, "Please provide actions to step with."
+        return self.env.step(actions)
+
+    def obs_at_reset(self):
+        return self.env.reset()
+
+    def reset(self):
+        return self.reset_all_envs()
+
+    def step(self, actions=None):
+        return self.step_all_envs(actions)
