@@ -49,6 +49,11 @@ long long wdb_rng_state_bytes(long long n_streams);
 int wdb_rng_init(void *stream, void *rng_state, long long n_streams,
                  unsigned long long seed);
 
+/* Test hook: out[4*i .. 4*i+3] = the next Philox block of stream i (advances every
+ * stream's offset by one) -- lets tests pin the device RNG against the scalar oracle. */
+int wdb_rng_draw_u32x4(void *stream, void *rng_state, unsigned int *out,
+                       long long n_streams);
+
 /* Replaces sample_actions (random.cu:51-85; launched from PyCUDASampler.sample,
  * pycuda_function_manager.py:532-572).  probs [n_envs, n_agents, n_actions] f32.
  * actions [n_envs, n_agents, 1] i32.  cum_distr [n_envs, n_agents, n_actions] f32 or

@@ -39,6 +39,25 @@ WDB_API int wdb_rng_init(void *stream, void *rng_state, long long n_streams,
   return finish_launch();
 }
 
+__global__ void rng_draw_kernel(void *state, uint4 *out, long long n_streams) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_streams) return;
+  const RngHeader h = *reinterpret_cast<const RngHeader *>(state);
+  unsigned long long *off = rng_offsets(state);
+  const unsigned long long o = off[i];
+  out[i] = rng_draw4(h, (unsigned long long)i, o);
+  off[i] = o + 1;
+}
+
+WDB_API int wdb_rng_draw_u32x4(void *stream, void *rng_state, unsigned int *out,
+                               long long n_streams) {
+  if (!rng_state || !out || n_streams <= 0) return (int)cudaErrorInvalidValue;
+  const int block = 256;
+  rng_draw_kernel<<<(int)((n_streams + block - 1) / block), block, 0, as_stream(stream)>>>(
+      rng_state, reinterpret_cast<uint4 *>(out), n_streams);
+  return finish_launch();
+}
+
 // ======================================================================== sampler
 // replaces sample_actions (core/random.cu:51-85).  One thread per (env, agent) row, but
 // the rows of a CTA are staged through shared memory so that the global reads of probs

@@ -30,6 +30,7 @@ _SIGNATURES = {
     "wdb_launch_count": (_ll, []),
     "wdb_rng_state_bytes": (_ll, [_ll]),
     "wdb_rng_init": (_i, [_vp, _vp, _ll, _ull]),
+    "wdb_rng_draw_u32x4": (_i, [_vp, _vp, _vp, _ll]),
     "wdb_sample_actions": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "wdb_sample_ou_process": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _f, _vp]),
     "wdb_reset_when_done": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp]),
