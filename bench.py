@@ -1,0 +1,427 @@
+#!/usr/bin/env python
+"""bench.py -- rollout throughput of the B200-native engine on BASELINE.json config 2
+(tag_continuous, 2000 envs x (5 taggers + 100 runners), discrete actions, K = 10 partial
+observations), one process per GPU.
+
+    python bench.py --gpus 1 --steps 200 --warmup 50
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...     # the reference's NumPy CPU step (oracle port)
+
+One "step" = one rollout timestep of every env replica on this rank:
+policy forward (2 policies) -> sample 2 action heads -> env.step -> bookkeeping ->
+done-masked reset -> push to the training batch.  Rank 0 prints ONE JSON line.
+
+  value     agent-steps/s (envs x agents x steps / s) of the whole device-resident
+            rollout, all ranks, CUDA-event timed, max over ranks
+  e2e       the same metric through the public EnvWrapper API with HOST buffers: every
+            step copies the actions host->device from pinned memory and the step's
+            observations/rewards/done device->host
+  roofline  the dominant kernel (the fused sample+step+reset kernel) timed alone with
+            CUDA events and an L2 flush between launches, against MEASURED_PEAKS.json
+  cpu_baseline  oracle/numpy_ref.py (NumPy restatement of the reference CPU step) on the
+            host cores, bounded sample
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# BASELINE.json config 2 == warp_drive/training/run_configs/tag_continuous.yaml:10-34 of
+# the reference with num_taggers = 5
+ENV_CONFIG = dict(
+    num_taggers=5, num_runners=100, grid_length=20.0, episode_length=500,
+    max_acceleration=0.1, min_acceleration=-0.1, max_turn=2.356, min_turn=-2.356,
+    num_acceleration_levels=20, num_turn_levels=20, skill_level_runner=1.0,
+    skill_level_tagger=1.0, max_speed=1.0, seed=274880, use_full_observation=False,
+    runner_exits_game_after_tagged=True, num_other_agents_observed=10,
+    tag_reward_for_tagger=10.0, tag_penalty_for_runner=-10.0, step_penalty_for_tagger=0.0,
+    step_reward_for_runner=0.0, edge_hit_penalty=0.0, end_of_game_reward_for_runner=1.0,
+    tagging_distance=0.02)
+MODEL_CONFIG = {"type": "fully_connected", "fc_dims": [256, 256], "model_ckpt_filepath": ""}
+
+# algorithmic bytes per agent-step (SURVEY.md section 8d / BASELINE.md section 3)
+BYTES_FUSED = 516      # sample (2 x 21 probs) + step: reads 192, writes 324
+BYTES_STEP_ONLY = 348  # step with actions in
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fp:
+            return json.load(fp), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._thread = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                     "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._thread.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names)
+                   if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]),
+                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(sm),
+                "reasons": reasons}
+
+
+def build_engine(n_envs, seed, graph_steps, use_graph=True):
+    import torch
+
+    from warp_drive_b200.env_wrapper import EnvWrapper
+    from warp_drive_b200.envs.tag_continuous import TagContinuous
+    from warp_drive_b200.managers.function_manager import CUDASampler
+    from warp_drive_b200.training.models.fully_connected import FullyConnected
+    from warp_drive_b200.training.rollout import RolloutEngine
+    from warp_drive_b200.training.utils.data_loader import create_and_push_data_placeholders
+
+    env = TagContinuous(**ENV_CONFIG)
+    wrapper = EnvWrapper(env, num_envs=n_envs, env_backend="b200")
+    wrapper.reset_all_envs()
+    policy_map = {"runner": sorted(env.runners), "tagger": sorted(env.taggers)}
+    sampler = CUDASampler(wrapper.cuda_function_manager)
+    create_and_push_data_placeholders(
+        env_wrapper=wrapper, action_sampler=sampler, policy_tag_to_agent_id_map=policy_map,
+        training_batch_size_per_env=graph_steps)
+    sampler.init_random(seed)
+    torch.manual_seed(seed)
+    models = {p: FullyConnected(wrapper, MODEL_CONFIG, p, policy_map).cuda().eval()
+              for p in policy_map}
+    wrapper.reset_all_envs()
+    engine = RolloutEngine(wrapper, models, policy_map, sampler, graph_steps,
+                           use_cuda_graph=use_graph)
+    return wrapper, engine, sampler, policy_map
+
+
+def flush_l2(buf):
+    buf.add_(1)   # read+write 512 MiB > 126 MB L2
+
+
+def time_dominant_kernel(wrapper, engine, iters=30):
+    """CUDA-event time of the dominant kernel alone, L2 flushed before every launch."""
+    import torch
+
+    flush = torch.zeros(128 * 1024 * 1024, dtype=torch.float32, device="cuda")
+    probs = engine.evaluate_policies(-1)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(iters)]
+    for i in range(iters + 3):
+        engine.sample_actions(probs, -1)
+        flush_l2(flush)
+        if i >= 3:
+            ev[i - 3][0].record()
+        wrapper.step_all_envs()
+        if i >= 3:
+            ev[i - 3][1].record()
+        wrapper.reset_only_done_envs()
+    torch.cuda.synchronize()
+    ms = sorted(a.elapsed_time(b) for a, b in ev)
+    return {"kernel": "tag_continuous_step_kernel", "ms_median": ms[len(ms) // 2],
+            "ms_min": ms[0], "bytes_per_agent_step": BYTES_STEP_ONLY}
+
+
+def time_e2e_host_buffers(wrapper, n_steps, warmup=3):
+    """Public-API env.step() with host buffers: H2D actions, step, D2H obs/rewards/done."""
+    import torch
+
+    dm = wrapper.cuda_data_manager
+    actions_d = dm.data_on_device_via_torch("sampled_actions")
+    obs_d = dm.data_on_device_via_torch("observations")
+    rew_d = dm.data_on_device_via_torch("rewards")
+    done_d = dm.data_on_device_via_torch("_done_")
+    rs = np.random.RandomState(0)
+    host_actions = [torch.from_numpy(rs.randint(0, 21, tuple(actions_d.shape)).astype(np.int32)
+                                     ).pin_memory() for _ in range(4)]
+    obs_h = torch.empty(obs_d.shape, dtype=obs_d.dtype).pin_memory()
+    rew_h = torch.empty(rew_d.shape, dtype=rew_d.dtype).pin_memory()
+    done_h = torch.empty(done_d.shape, dtype=done_d.dtype).pin_memory()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for i in range(warmup + n_steps):
+        if i == warmup:
+            torch.cuda.synchronize()
+            start.record()
+        actions_d.copy_(host_actions[i % 4], non_blocking=True)
+        wrapper.step_all_envs()
+        obs_h.copy_(obs_d, non_blocking=True)
+        rew_h.copy_(rew_d, non_blocking=True)
+        done_h.copy_(done_d, non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the host consumes this step's result
+        wrapper.reset_only_done_envs()
+    end.record()
+    torch.cuda.synchronize()
+    ms = start.elapsed_time(end) / n_steps
+    h2d = actions_d.numel() * 4
+    d2h = obs_d.numel() * 4 + rew_d.numel() * 4 + done_d.numel() * 4
+    return ms, h2d, d2h
+
+
+def cpu_baseline(sample_steps, n_procs=None):
+    """oracle/numpy_ref.py on the host cores (bounded sample of config 2)."""
+    from oracle.numpy_ref import timed_agent_steps_per_sec
+    from warp_drive_b200.envs.tag_continuous import TagContinuous
+
+    env = TagContinuous(**ENV_CONFIG)
+    env.reset()
+    dd = env.get_data_dictionary()
+    cfg = {k: dd[k]["data"] for k in (
+        "agent_types", "acceleration_actions", "turn_actions", "skill_levels", "step_rewards",
+        "grid_length", "edge_hit_penalty", "max_speed", "distance_margin_for_reward",
+        "tag_reward_for_tagger", "tag_penalty_for_runner", "end_of_game_reward_for_runner",
+        "num_other_agents_observed", "use_full_observation", "runner_exits_game_after_tagged")}
+    cfg["episode_length"] = env.episode_length
+    init = {k: np.array(dd[k]["data"]) for k in
+            ("loc_x", "loc_y", "speed", "direction", "acceleration")}
+    return timed_agent_steps_per_sec(cfg, init, sample_steps, warmup=2, n_procs=n_procs)
+
+
+def c_oracle_rate(n_envs=64, n_steps=10):
+    """The C restatement of the CUDA kernel (OpenMP, all cores): extra context only."""
+    import oracle
+    from warp_drive_b200.envs.tag_continuous import TagContinuous
+
+    env = TagContinuous(**ENV_CONFIG)
+    env.reset()
+    dd = env.get_data_dictionary()
+    N, K = env.num_agents, env.num_other_agents_observed
+    rep = lambda a, dt: np.ascontiguousarray(np.broadcast_to(np.asarray(a, dt), (n_envs, N))).copy()  # noqa: E731
+    st = {k: rep(dd[k]["data"], np.float32) for k in
+          ("loc_x", "loc_y", "speed", "direction", "acceleration", "edge_hit_reward_penalty")}
+    st["still_in_the_game"] = rep(dd["still_in_the_game"]["data"], np.int32)
+    st["num_runners"] = np.full(n_envs, env.num_runners, np.int32)
+    st["nearest_neighbor_ids"] = np.zeros((n_envs, N, K), np.int32)
+    st["_done_"] = np.zeros(n_envs, np.int32)
+    st["_timestep_"] = np.zeros(n_envs, np.int32)
+    cfg = {"agent_types": np.asarray(dd["agent_types"]["data"], np.int32)}
+    for k in ("acceleration_actions", "turn_actions", "skill_levels", "step_rewards"):
+        cfg[k] = np.asarray(dd[k]["data"], np.float32)
+    for k in ("grid_length", "edge_hit_penalty", "max_speed", "distance_margin_for_reward",
+              "tag_reward_for_tagger", "tag_penalty_for_runner",
+              "end_of_game_reward_for_runner", "num_other_agents_observed",
+              "use_full_observation", "runner_exits_game_after_tagged"):
+        cfg[k] = dd[k]["data"]
+    cfg["episode_length"] = env.episode_length
+    rs = np.random.RandomState(0)
+    acts = rs.randint(0, 21, (n_steps + 1, n_envs, N, 2)).astype(np.int32)
+    obs = np.zeros((n_envs, N, 7 * K + 1), np.float32)
+    rew = np.zeros((n_envs, N), np.float32)
+    oracle.tag_continuous_step(st, cfg, acts[0], obs, rew)
+    t0 = time.perf_counter()
+    for t in range(n_steps):
+        oracle.tag_continuous_step(st, cfg, acts[t + 1], obs, rew)
+    dt = time.perf_counter() - t0
+    return n_envs * N * n_steps / dt, oracle.lib().wd_oracle_num_threads()
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's own CPU implementation of the path = its NumPy
+    step(), restated in oracle/numpy_ref.py, on all host cores.  Each 'step' is one env
+    step of one replica per core (a bounded sample of the workload)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    steps = max(1, min(args.steps, 400))
+    res = cpu_baseline(steps, n_procs=cores)
+    value = res["agent_steps_per_sec"]
+    line = {
+        "impl": "reference", "metric": "agent_steps_per_sec", "value": value,
+        "unit": "agent-steps/s", "n_gpus": args.gpus, "steps": steps, "warmup": 2,
+        "ms_per_step": 1000.0 * cores * res["n_agents"] / value, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "tag_continuous 5 taggers + 100 runners, K=10 partial obs, "
+                               "one env replica per host core (bounded sample of config 2)"},
+        "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": cores,
+                         "kind": "port",
+                         "sample": f"{steps} env-steps x {cores} processes x 105 agents, "
+                                   "oracle/numpy_ref.py"},
+        "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs", type=int, default=2000, help="env replicas per GPU")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    from warp_drive_b200 import lib as wlib
+
+    K = args.steps
+    W = max(3, args.warmup)
+    # the rollout is captured as CUDA graphs of T timesteps; T divides K
+    T = max(d for d in range(1, min(K, 50) + 1) if K % d == 0)
+    wrapper, engine, sampler, policy_map = build_engine(
+        args.envs, seed=1234 + rank, graph_steps=T, use_graph=not args.no_graph)
+    E, N = wrapper.n_envs, wrapper.n_agents
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also captures the graph)
+    launches0 = wlib.launch_count()
+    engine.rollout()
+    torch.cuda.synchronize()
+    launches_per_rollout = None
+    for _ in range(max(0, math.ceil(W / T) - 1)):
+        engine.rollout()
+    # my kernels per T-step rollout (graph replays do not pass through the library, so
+    # count one eager rollout)
+    if not args.no_graph:
+        c0 = wlib.launch_count()
+        engine._rollout_eager()
+        launches_per_rollout = wlib.launch_count() - c0
+    torch.cuda.synchronize()
+
+    # ---- timed region: exactly K steps
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with ClockSampler(local_rank) as clocks:
+        c0 = wlib.launch_count()
+        start.record()
+        for _ in range(K // T):
+            engine.rollout()
+        end.record()
+        barrier()
+    elapsed_ms = start.elapsed_time(end)
+    my_launches = (wlib.launch_count() - c0) if args.no_graph else launches_per_rollout * (K // T)
+    t = torch.tensor([elapsed_ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    value = world * E * N * K / (elapsed_ms / 1000.0)
+
+    # ---- e2e through the public API with host buffers (max over ranks)
+    e2e_ms, h2d, d2h = time_e2e_host_buffers(wrapper, n_steps=min(K, 50))
+    t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * E * N / (float(t.item()) / 1000.0)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (rank 0 only)
+    peaks, peak_src = measured_peaks()
+    dk = time_dominant_kernel(wrapper, engine)
+    achieved = dk["bytes_per_agent_step"] * E * N / (dk["ms_median"] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                "kernel": dk["kernel"], "kernel_ms": dk["ms_median"],
+                "algorithmic_bytes_per_agent_step": dk["bytes_per_agent_step"],
+                "peak_source": peak_src, "l2": "flushed before every launch"}
+
+    line = {
+        "metric": "agent_steps_per_sec", "value": value, "unit": "agent-steps/s",
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": elapsed_ms / K,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"tag_continuous {E} envs/GPU x (5 taggers + 100 runners), "
+                               "discrete 21x21 actions, K=10 partial obs, 2 policies "
+                               "fully_connected [256,256], rollout step = forward + sample "
+                               "+ step + reset + push-to-batch",
+                   "envs_per_gpu": E, "agents": N, "graph_steps": T,
+                   "cuda_graph": not args.no_graph,
+                   "l2": "working set per step (~110 MB obs+probs+batch slots, batch slot "
+                         "changes every step) exceeds what stays L2-resident; dominant "
+                         "kernel additionally timed with an explicit L2 flush"},
+        "clocks": clocks.summary(),
+        "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
+                "path": "EnvWrapper.step_all_envs with pinned host actions in and "
+                        "observations/rewards/done out every step"},
+        "gpu_launches": int(my_launches),
+        "roofline": roofline,
+    }
+    if not args.skip_cpu_baseline:
+        cores = os.cpu_count() or 1
+        res = cpu_baseline(sample_steps=150, n_procs=cores)
+        line["cpu_baseline"] = {
+            "value": res["agent_steps_per_sec"], "unit": "agent-steps/s", "cores": cores,
+            "kind": "port",
+            "sample": f"150 env-steps x {cores} processes x 105 agents of the same env "
+                      "config (oracle/numpy_ref.py = reference NumPy step restated)"}
+        try:
+            rate, threads = c_oracle_rate()
+            line["cpu_c_oracle"] = {"value": rate, "unit": "agent-steps/s", "threads": threads,
+                                    "note": "C/OpenMP restatement of the CUDA kernel "
+                                            "(oracle/wd_oracle.c), context only"}
+        except Exception as err:  # noqa: BLE001
+            line["cpu_c_oracle"] = {"error": str(err)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -144,3 +144,24 @@ def test_sampler_index_selection(oracle_lib):
     o = np.zeros(2, np.int32)
     oracle_lib.wd_oracle_sample_actions(am, o, 1, None, np.zeros(2, np.float32), 2, 3, 1)
     assert o.tolist() == [0, 1]
+
+
+@pytest.mark.parametrize("name", ["test1", "test2", "test3", "test4", "partial_mid"])
+def test_numpy_port_matches_reference(name):
+    """oracle/numpy_ref.py (the reported CPU baseline) reproduces trajectories recorded
+    from the real reference NumPy env, including rewards on the final step."""
+    from oracle.numpy_ref import TagContinuousNumpyRef
+
+    fx = load_golden(f"tag_continuous_numpy_{name}.npz")
+    cfg = tc_cfg_from_fixture(fx)
+    init = {k: fx[f"init__{k}"] for k in ("loc_x", "loc_y", "speed", "direction", "acceleration")}
+    env = TagContinuousNumpyRef(cfg, init)
+    N = env.N
+    o0 = env.generate_observation()
+    assert close(np.stack([o0[a] for a in range(N)]), fx["obs0"], 1e-6).all()
+    for t in range(fx["actions"].shape[0]):
+        obs, rew, done = env.step(fx["actions"][t])
+        assert close(np.stack([obs[a] for a in range(N)]), fx["obs"][t], 1e-6).all(), t
+        assert close(np.array([rew[a] for a in range(N)]), fx["rewards"][t], 1e-6).all(), t
+        assert bool(done) == bool(fx["done"][t])
+        assert (env.still_in_the_game == fx["still_in_the_game"][t]).all()

@@ -1,0 +1,157 @@
+"""RolloutEngine: the device-resident rollout loop
+`policy forward -> sample -> env.step -> bookkeeping -> done-masked reset -> push to batch`.
+
+This is the B200 re-design of TrainerBase._generate_rollout_batch and its helpers
+(warp_drive/training/trainers/trainer_base.py:383-601, trainer_a2c.py:159-216): the
+reference issues ~55 kernel launches and >= 5 host synchronisations per timestep
+(SURVEY.md section 3.2); here one timestep has NO host synchronisation (done handling is
+a device-side mask), and the whole T-step rollout is captured once in a CUDA graph and
+replayed.
+"""
+import torch
+
+from warp_drive_b200.utils.constants import Constants
+
+_OBSERVATIONS = Constants.OBSERVATIONS
+_ACTIONS = Constants.ACTIONS
+_REWARDS = Constants.REWARDS
+_DONE_FLAGS = Constants.DONE_FLAGS
+_PROCESSED_OBSERVATIONS = Constants.PROCESSED_OBSERVATIONS
+
+
+class RolloutEngine:
+    def __init__(self, env_wrapper, models, policy_tag_to_agent_id_map, sampler,
+                 batch_size_per_env, use_cuda_graph=True, forward_dtype=None):
+        self.env_wrapper = env_wrapper
+        self.dm = env_wrapper.cuda_data_manager
+        self.models = models
+        self.policy_map = policy_tag_to_agent_id_map
+        self.policies = list(policy_tag_to_agent_id_map.keys())
+        self.sampler = sampler
+        self.T = int(batch_size_per_env)
+        self.use_cuda_graph = use_cuda_graph
+        self.forward_dtype = forward_dtype
+        dev = self.dm.device
+        self.E = env_wrapper.n_envs
+        self.N = env_wrapper.n_agents
+        self.ids = {p: torch.as_tensor(ids, dtype=torch.long, device=dev)
+                    for p, ids in self.policy_map.items()}
+        self.covers_all = {p: len(ids) == self.N and list(ids) == list(range(self.N))
+                           for p, ids in self.policy_map.items()}
+        first = self.policy_map[self.policies[0]][0]
+        from warp_drive_b200.training.utils.data_loader import action_head_sizes
+
+        self.heads, self.continuous = action_head_sizes(env_wrapper.env.action_space[first])
+        self.n_heads = len(self.heads)
+        self.combined = None
+        if len(self.policies) > 1:
+            self.combined = [torch.zeros((self.E, self.N, h), device=dev) for h in self.heads]
+        # episodic statistics (device scalars: no host sync while rolling out)
+        self.reward_running_sum = {p: torch.zeros((self.E, len(ids)), device=dev)
+                                   for p, ids in self.policy_map.items()}
+        self.step_running_sum = torch.zeros(self.E, dtype=torch.int64, device=dev)
+        self.episodic_reward_sum = {p: torch.zeros((), device=dev) for p in self.policies}
+        self.episodic_step_sum = torch.zeros((), dtype=torch.int64, device=dev)
+        self.num_completed_episodes = torch.zeros((), dtype=torch.int64, device=dev)
+        self._graph = None
+        self._graph_stream = None
+
+    # ------------------------------------------------------------------ one timestep
+    def _tensor(self, name):
+        return self.dm.data_on_device_via_torch(name)
+
+    def evaluate_policies(self, t):
+        """obs -> per-head probabilities [E, N, A_k] (trainer_a2c.py:159-216)."""
+        obs = self._tensor(_OBSERVATIONS).view(self.E, self.N, -1)
+        out = None
+        for p in self.policies:
+            model = self.models[p]
+            obs_p = obs if self.covers_all[p] else obs.index_select(1, self.ids[p])
+            if t >= 0:
+                self._tensor(f"{_PROCESSED_OBSERVATIONS}_batch_{p}")[t].copy_(obs_p)
+            if self.forward_dtype is not None:
+                with torch.autocast("cuda", dtype=self.forward_dtype):
+                    probs, _ = model(obs_p)
+                probs = [q.float() for q in probs]
+            else:
+                probs, _ = model(obs_p)
+            if self.combined is None:
+                out = probs
+            else:
+                for k in range(self.n_heads):
+                    self.combined[k].index_copy_(1, self.ids[p], probs[k])
+                out = self.combined
+        return out
+
+    def sample_actions(self, probs, t, **sample_params):
+        """probs -> sampled_actions (+ per-policy batch push), trainer_base.py:437-512."""
+        dm = self.dm
+        if self.n_heads == 1:
+            self.sampler.sample(dm, probs[0], _ACTIONS, write_cum_distr=False, **sample_params)
+        else:
+            actions = self._tensor(_ACTIONS)
+            for k in range(self.n_heads):
+                self.sampler.sample(dm, probs[k], f"{_ACTIONS}_{k}", write_cum_distr=False,
+                                    combined=(actions, self.n_heads, k), **sample_params)
+        if t >= 0:
+            actions = self._tensor(_ACTIONS)
+            for p in self.policies:
+                batch = self._tensor(f"{_ACTIONS}_batch_{p}")[t]
+                batch.copy_(actions if self.covers_all[p]
+                            else actions.index_select(1, self.ids[p]))
+
+    def bookkeep(self, t):
+        """done / rewards -> batches, running episodic sums without host syncs
+        (trainer_base.py:514-601 uses nonzero()/len())."""
+        done = self._tensor("_done_")
+        rewards = self._tensor(_REWARDS)
+        if t >= 0:
+            self._tensor(f"{_DONE_FLAGS}_batch")[t].copy_(done)
+        donef = done.to(torch.float32)
+        for p in self.policies:
+            r_p = rewards if self.covers_all[p] else rewards.index_select(1, self.ids[p])
+            if t >= 0:
+                self._tensor(f"{_REWARDS}_batch_{p}")[t].copy_(r_p)
+            run = self.reward_running_sum[p]
+            run.add_(r_p)
+            self.episodic_reward_sum[p].add_((run * donef[:, None]).sum())
+            run.mul_(1.0 - donef[:, None])
+        self.step_running_sum.add_(1)
+        done64 = done.to(torch.int64)
+        self.episodic_step_sum.add_((self.step_running_sum * done64).sum())
+        self.step_running_sum.mul_(1 - done64)
+        self.num_completed_episodes.add_(done64.sum())
+
+    def step(self, t, **sample_params):
+        with torch.no_grad():
+            probs = self.evaluate_policies(t)
+            self.sample_actions(probs, t, **sample_params)
+            self.env_wrapper.step_all_envs()
+            self.bookkeep(t)
+            # done-masked reset: a no-op for envs that are not done, so no host-side
+            # `if done_flags.any()` (trainer_base.py:421-422) is needed
+            self.env_wrapper.reset_only_done_envs()
+
+    # ------------------------------------------------------------------ T-step rollout
+    def _rollout_eager(self, **sample_params):
+        for t in range(self.T):
+            self.step(t, **sample_params)
+
+    def rollout(self, **sample_params):
+        """Generate one training batch (T timesteps for every env replica)."""
+        if not self.use_cuda_graph or sample_params:
+            self._rollout_eager(**sample_params)
+            return
+        if self._graph is None:
+            # warm-up on a side stream (cuBLAS workspaces, lazy inits), then capture
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self.step(0)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._rollout_eager()
+            self._graph = graph
+        self._graph.replay()
