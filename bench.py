@@ -109,7 +109,7 @@ class ClockSampler:
                 "reasons": reasons}
 
 
-def build_engine(n_envs, seed, graph_steps, use_graph=True):
+def build_engine(n_envs, seed, graph_steps, use_graph=True, forward_dtype=None):
     import torch
 
     from warp_drive_b200.env_wrapper import EnvWrapper
@@ -132,8 +132,11 @@ def build_engine(n_envs, seed, graph_steps, use_graph=True):
     models = {p: FullyConnected(wrapper, MODEL_CONFIG, p, policy_map).cuda().eval()
               for p in policy_map}
     wrapper.reset_all_envs()
+    # the fused kernel hands observations straight to the per-policy forward buffers; the
+    # [E, N, F] `observations` array is only materialised on demand
     engine = RolloutEngine(wrapper, models, policy_map, sampler, graph_steps,
-                           use_cuda_graph=use_graph)
+                           use_cuda_graph=use_graph, forward_dtype=forward_dtype,
+                           write_observations=False)
     return wrapper, engine, sampler, policy_map
 
 
@@ -142,26 +145,48 @@ def flush_l2(buf):
 
 
 def time_dominant_kernel(wrapper, engine, iters=30):
-    """CUDA-event time of the dominant kernel alone, L2 flushed before every launch."""
+    """CUDA-event time of the dominant kernel alone (the fused sample+step+reset+push
+    launch), L2 flushed before every launch."""
     import torch
 
     flush = torch.zeros(128 * 1024 * 1024, dtype=torch.float32, device="cuda")
-    probs = engine.evaluate_policies(-1)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(iters)]
-    for i in range(iters + 3):
-        engine.sample_actions(probs, -1)
-        flush_l2(flush)
-        if i >= 3:
-            ev[i - 3][0].record()
-        wrapper.step_all_envs()
-        if i >= 3:
-            ev[i - 3][1].record()
-        wrapper.reset_only_done_envs()
+    if engine.fused is None:
+        probs = engine.evaluate_policies(-1)
+        for i in range(iters + 3):
+            engine.sample_actions(probs, -1)
+            flush_l2(flush)
+            if i >= 3:
+                ev[i - 3][0].record()
+            wrapper.step_all_envs()
+            if i >= 3:
+                ev[i - 3][1].record()
+            wrapper.reset_only_done_envs()
+        name, nbytes = "tag_continuous_kernel<false> (step only)", BYTES_STEP_ONLY
+    else:
+        dm = wrapper.cuda_data_manager
+        with torch.no_grad():
+            probs = {p: engine._forward(engine.models[p], engine.cur_obs[p])
+                     for p in engine.policies}
+        slots = {k: {p: dm.data_on_device_via_torch(f"{k}_batch_{p}")[0]
+                     for p in engine.policies}
+                 for k in ("sampled_actions", "rewards", "processed_observations")}
+        done_b = dm.data_on_device_via_torch("done_flags_batch")[0]
+        for i in range(iters + 3):
+            flush_l2(flush)
+            if i >= 3:
+                ev[i - 3][0].record()
+            engine.fused.launch(probs, actions_batch=slots["sampled_actions"],
+                                rewards_batch=slots["rewards"],
+                                obs_next=slots["processed_observations"], done_batch=done_b)
+            if i >= 3:
+                ev[i - 3][1].record()
+        name, nbytes = "tag_continuous_kernel<true> (fused sample+step+push+reset)", BYTES_FUSED
     torch.cuda.synchronize()
     ms = sorted(a.elapsed_time(b) for a, b in ev)
-    return {"kernel": "tag_continuous_step_kernel", "ms_median": ms[len(ms) // 2],
-            "ms_min": ms[0], "bytes_per_agent_step": BYTES_STEP_ONLY}
+    return {"kernel": name, "ms_median": ms[len(ms) // 2], "ms_min": ms[0],
+            "bytes_per_agent_step": nbytes}
 
 
 def time_e2e_host_buffers(wrapper, n_steps, warmup=3):

@@ -138,6 +138,73 @@ int wdb_tag_continuous_step(
     float tag_penalty_for_runner, float end_of_game_reward_for_runner, int *done,
     int *env_timestep, int episode_length, int *stats);
 
+/* ------------------------------------------------------------ fused rollout step -- */
+/* ONE launch per rollout timestep of tag_continuous:
+ *   sample both action heads from the policies' probabilities (sample_actions x2,
+ *   core/random.cu:51-85) -> CudaTagContinuousStep -> push actions / rewards / done to the
+ *   training batch slots and update the episodic sums (trainer_base.py:437-601) ->
+ *   write the new observations per policy for the next forward pass
+ *   (model_base.py:181-200) -> done-masked reset of every registered array + undo of
+ *   done/timestep (core/reset.cu:9-75; function_manager.py:256-273).
+ * The reference issues ~50 launches and >= 5 host syncs for the same work. */
+typedef struct wdb_tc_env {          /* the arguments of wdb_tag_continuous_step */
+  int n_envs, n_agents;
+  float *loc_x, *loc_y, *speed, *direction, *acceleration;
+  const int *agent_types;
+  float *edge_hit_reward_penalty;
+  float edge_hit_penalty, grid_length;
+  const float *acceleration_actions, *turn_actions;
+  float max_speed;
+  int num_other_agents_observed;
+  const float *skill_levels;
+  int runner_exits_game_after_tagged;
+  int *still_in_the_game;
+  int use_full_observation;
+  float *obs;                        /* [E, N, F]; may be NULL when obs_next is used */
+  float *neighbor_distances;         /* optional scratch */
+  int *neighbor_ids_sorted_by_distance;
+  int *nearest_neighbor_ids;
+  float *rewards;
+  const float *step_rewards;
+  int *num_runners;
+  float distance_margin_for_reward, tag_reward_for_tagger, tag_penalty_for_runner,
+      end_of_game_reward_for_runner;
+  int *done, *env_timestep;
+  int episode_length;
+  int *stats;
+} wdb_tc_env;
+
+typedef struct wdb_tc_policy_io {    /* per policy; agents of a policy are [E, Np, ...] */
+  int n_agents;                      /* Np */
+  const float *probs0, *probs1;      /* [E, Np, A0], [E, Np, A1] from the forward pass */
+  int *actions_batch;                /* [E, Np, 2]  slot t of sampled_actions_batch_p, or NULL */
+  float *rewards_batch;              /* [E, Np]     slot t of rewards_batch_p, or NULL */
+  float *obs_next;                   /* [E, Np, F]  where the next forward reads, or NULL */
+  float *reward_running_sum;         /* [E, Np] or NULL */
+  float *episodic_reward_sum;        /* scalar or NULL */
+} wdb_tc_policy_io;
+
+typedef struct wdb_tc_rollout {
+  void *rng_state;
+  const float *uniforms;             /* test hook [E, N, 2]; NULL = device RNG */
+  int n_policies, n_actions0, n_actions1;
+  const int *agent_policy;           /* [N] policy index of every agent */
+  const int *agent_slot;             /* [N] index of the agent inside its policy */
+  wdb_tc_policy_io policy[4];
+  int *sampled_actions;              /* [E, N, 2] or NULL */
+  int *sampled_actions_0, *sampled_actions_1;   /* [E, N, 1] or NULL */
+  int *done_batch;                   /* [E] slot t of done_flags_batch, or NULL */
+  int *step_running_sum;             /* [E] or NULL */
+  unsigned long long *episodic_step_sum, *num_completed_episodes;   /* scalars or NULL */
+  const wdb_reset_desc *reset_table; /* device table of the arrays to restore */
+  int n_reset_arrays;
+  const float *obs_at_reset;         /* [E, N, F]: source of obs_next for envs that reset */
+  int reset_done_envs;               /* 0: leave done envs alone (done stays set) */
+} wdb_tc_rollout;
+
+int wdb_tag_continuous_rollout_step(void *stream, const wdb_tc_env *env,
+                                    const wdb_tc_rollout *rollout);
+
 /* Replaces NumbaClassicControlCartPoleEnvStep (example_envs/single_agent/
  * classic_control/cartpole/cartpole_step_numba.py:6-83; argument order of
  * cartpole.py:105-122). */

@@ -1,0 +1,205 @@
+"""GPU tests of the fused rollout timestep (wdb_tag_continuous_rollout_step) and of the
+RolloutEngine: the single-launch path must produce exactly what the separate
+sample / step / bookkeeping / reset calls produce (which are themselves pinned to the
+oracle and to the reference kernels in test_gpu_envs.py / test_gpu_core.py)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ENV_KW = dict(num_taggers=3, num_runners=20, grid_length=10.0, episode_length=40,
+              max_acceleration=0.1, min_acceleration=-0.1, max_turn=2.356, min_turn=-2.356,
+              num_acceleration_levels=20, num_turn_levels=20, seed=274880,
+              use_full_observation=False, num_other_agents_observed=5,
+              tag_reward_for_tagger=10.0, tag_penalty_for_runner=-10.0,
+              edge_hit_penalty=-0.5, tagging_distance=0.08, step_reward_for_runner=0.01)
+
+
+def _setup(E, T, full_obs=False, seed=11):
+    from warp_drive_b200.env_wrapper import EnvWrapper
+    from warp_drive_b200.envs.tag_continuous import TagContinuous
+    from warp_drive_b200.managers.function_manager import CUDASampler
+    from warp_drive_b200.training.utils.data_loader import create_and_push_data_placeholders
+
+    kw = dict(ENV_KW, use_full_observation=full_obs)
+    env = TagContinuous(**kw)
+    wrapper = EnvWrapper(env, num_envs=E, env_backend="b200")
+    wrapper.reset_all_envs()
+    policy_map = {"runner": sorted(env.runners), "tagger": sorted(env.taggers)}
+    sampler = CUDASampler(wrapper.cuda_function_manager)
+    create_and_push_data_placeholders(env_wrapper=wrapper, action_sampler=sampler,
+                                      policy_tag_to_agent_id_map=policy_map,
+                                      training_batch_size_per_env=T)
+    sampler.init_random(seed)
+    return wrapper, sampler, policy_map
+
+
+STATE = ("loc_x", "loc_y", "speed", "direction", "acceleration", "edge_hit_reward_penalty",
+         "still_in_the_game", "num_runners", "nearest_neighbor_ids", "_done_", "_timestep_",
+         "observations", "rewards", "sampled_actions")
+
+
+@pytest.mark.parametrize("full_obs", [False, True])
+def test_fused_step_equals_separate_calls(full_obs):
+    from warp_drive_b200.training.fused_tag_continuous import FusedTagContinuousStep
+
+    E, T = 10, 4
+    wa, sa, pm = _setup(E, T, full_obs)
+    wb, sb, _ = _setup(E, T, full_obs)
+    dma, dmb = wa.cuda_data_manager, wb.cuda_data_manager
+    N = wa.n_agents
+    ids = {p: torch.as_tensor(v, device="cuda") for p, v in pm.items()}
+    fused = FusedTagContinuousStep(wb, pm, sb)
+    run = {p: torch.zeros((E, len(v)), device="cuda") for p, v in pm.items()}
+    ep_sum = {p: torch.zeros((), device="cuda") for p in pm}
+    steps = torch.zeros(E, dtype=torch.int32, device="cuda")
+    ep_steps = torch.zeros((), dtype=torch.int64, device="cuda")
+    n_done = torch.zeros((), dtype=torch.int64, device="cuda")
+    fused.set_bookkeeping(run, ep_sum, steps, ep_steps, n_done)
+    ref_run = {p: torch.zeros((E, len(v)), device="cuda") for p, v in pm.items()}
+    ref_ep = {p: 0.0 for p in pm}
+    ref_steps = torch.zeros(E, dtype=torch.int64, device="cuda")
+    ref_ep_steps, ref_n_done = 0, 0
+    g = torch.Generator(device="cuda").manual_seed(5)
+    F = dma.get_shape("observations")[2]
+    total_done = 0
+    for t in range(100):
+        probs = {p: [torch.softmax(2 * torch.randn((E, len(v), 21), device="cuda", generator=g), -1)
+                     for _ in range(2)] for p, v in pm.items()}
+        u = torch.rand((E, N, 2), device="cuda", generator=g).clamp_min(1e-7)
+        # ---- A: separate calls (combined probs -> sampler x2 -> step -> reset)
+        acts = dma.data_on_device_via_torch("sampled_actions")
+        for k in range(2):
+            comb = torch.zeros((E, N, 21), device="cuda")
+            for p in pm:
+                comb[:, ids[p]] = probs[p][k]
+            sa.sample(dma, comb, f"sampled_actions_{k}", combined=(acts, 2, k),
+                      uniforms=u[:, :, k].contiguous())
+        wa.step_all_envs()
+        done_a = dma.data_on_device_via_torch("_done_").clone()
+        rew_a = dma.data_on_device_via_torch("rewards").clone()
+        acts_a = acts.clone()
+        for p in pm:
+            ref_run[p] += rew_a[:, ids[p]]
+            ref_ep[p] += float((ref_run[p] * done_a[:, None]).sum())
+            ref_run[p] *= (1 - done_a[:, None])
+        ref_steps += 1
+        ref_ep_steps += int((ref_steps * done_a).sum())
+        ref_steps *= (1 - done_a)
+        ref_n_done += int(done_a.sum())
+        wa.reset_only_done_envs()
+        # ---- B: one fused launch
+        slot = t % T
+        ab = {p: dmb.data_on_device_via_torch(f"sampled_actions_batch_{p}")[slot] for p in pm}
+        rb = {p: dmb.data_on_device_via_torch(f"rewards_batch_{p}")[slot] for p in pm}
+        ob = {p: torch.full((E, len(v), F), -7.0, device="cuda") for p, v in pm.items()}
+        db = dmb.data_on_device_via_torch("done_flags_batch")[slot]
+        fused.launch(probs, actions_batch=ab, rewards_batch=rb, obs_next=ob, done_batch=db,
+                     uniforms=u)
+        torch.cuda.synchronize()
+        for k in STATE:
+            ta, tb = dma.data_on_device_via_torch(k), dmb.data_on_device_via_torch(k)
+            if k == "rewards":
+                ta = rew_a
+            if k == "nearest_neighbor_ids":
+                continue   # stale tails differ only where invalid; covered via observations
+            assert torch.equal(ta, tb), (t, k)
+        assert torch.equal(dmb.data_on_device_via_torch("sampled_actions_0")[..., 0], acts_a[..., 0])
+        assert torch.equal(dmb.data_on_device_via_torch("sampled_actions_1")[..., 0], acts_a[..., 1])
+        assert torch.equal(db, done_a)
+        obs_post = dma.data_on_device_via_torch("observations").view(E, N, -1)
+        for p in pm:
+            assert torch.equal(ab[p], acts_a[:, ids[p]]), (t, p)
+            assert torch.equal(rb[p], rew_a[:, ids[p]]), (t, p)
+            assert torch.equal(ob[p], obs_post[:, ids[p]]), (t, p)      # post-reset obs
+            assert torch.allclose(run[p], ref_run[p], atol=1e-5)
+            assert abs(float(ep_sum[p]) - ref_ep[p]) < 1e-2 + 1e-5 * abs(ref_ep[p])
+        assert torch.equal(steps.long(), ref_steps)
+        assert int(ep_steps) == ref_ep_steps and int(n_done) == ref_n_done
+        total_done += int(done_a.sum())
+    assert total_done >= 2 * E       # episodes ended and were reset on both paths
+
+
+def test_fused_step_without_reset_keeps_done_set():
+    from warp_drive_b200.training.fused_tag_continuous import FusedTagContinuousStep
+
+    E, T = 4, 2
+    w, s, pm = _setup(E, T)
+    dm = w.cuda_data_manager
+    fused = FusedTagContinuousStep(w, pm, s)
+    probs = {p: [torch.full((E, len(v), 21), 1 / 21.0, device="cuda") for _ in range(2)]
+             for p, v in pm.items()}
+    for t in range(ENV_KW["episode_length"]):
+        fused.launch(probs, reset_done_envs=False)
+    assert bool((dm.data_on_device_via_torch("_done_") == 1).all())
+    assert bool((dm.data_on_device_via_torch("_timestep_") == ENV_KW["episode_length"]).all())
+    w.reset_only_done_envs()
+    assert int(dm.data_on_device_via_torch("_done_").sum()) == 0
+    assert torch.equal(dm.data_on_device_via_torch("loc_x"),
+                       dm.data_on_device_via_torch("loc_x_at_reset"))
+
+
+def _engine(E, T, use_graph, fused, seed=3):
+    from warp_drive_b200.training.models.fully_connected import FullyConnected
+    from warp_drive_b200.training.rollout import RolloutEngine
+
+    w, s, pm = _setup(E, T, seed=seed)
+    torch.manual_seed(0)
+    cfg = {"type": "fully_connected", "fc_dims": [32, 32], "model_ckpt_filepath": ""}
+    models = {p: FullyConnected(w, cfg, p, pm).cuda().eval() for p in pm}
+    w.reset_all_envs()
+    eng = RolloutEngine(w, models, pm, s, T, use_cuda_graph=use_graph, use_fused_step=fused)
+    return w, eng, pm
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_engine_cuda_graph_matches_eager(fused):
+    """Same seeds -> the CUDA-graph replayed rollout fills the training batch exactly like
+    the eager loop (the warm-up step of the capture is replicated on the eager side)."""
+    E, T = 6, 8
+    wa, ea, pm = _engine(E, T, True, fused)
+    wb, eb, _ = _engine(E, T, False, fused)
+    ea.rollout()
+    ea.rollout()
+    eb.step(0)              # the graph path ran one eager warm-up step before capturing
+    eb.rollout()
+    eb.rollout()
+    torch.cuda.synchronize()
+    for p in pm:
+        for name in (f"processed_observations_batch_{p}", f"sampled_actions_batch_{p}",
+                     f"rewards_batch_{p}"):
+            ta = wa.cuda_data_manager.data_on_device_via_torch(name)
+            tb = wb.cuda_data_manager.data_on_device_via_torch(name)
+            assert torch.equal(ta, tb), name
+    assert torch.equal(wa.cuda_data_manager.data_on_device_via_torch("done_flags_batch"),
+                       wb.cuda_data_manager.data_on_device_via_torch("done_flags_batch"))
+    assert int(ea.num_completed_episodes) == int(eb.num_completed_episodes)
+
+
+def test_engine_fused_matches_unfused_batches():
+    """Fused single-launch timestep vs the generic multi-launch path, same models, same
+    RNG seed: identical training batches (both draw u from the same Philox streams:
+    generic = one draw per head call, fused = one draw for both heads, so compare through
+    the injected-uniform test above; here only structural equivalence of the first step,
+    where both consume draw #0.x / #0.x+#1.x differently, is NOT expected) -- instead check
+    the batch invariants of the fused engine against its own state arrays."""
+    E, T = 8, 16
+    w, e, pm = _engine(E, T, True, True)
+    dm = w.cuda_data_manager
+    for _ in range(4):
+        e.rollout()
+    torch.cuda.synchronize()
+    obs = dm.data_on_device_via_torch("observations")
+    N = w.n_agents
+    for p, ids in pm.items():
+        i = torch.as_tensor(ids, device="cuda")
+        # the observation the next forward pass will read == observations[:, ids]
+        assert torch.equal(e.cur_obs[p], obs.view(E, N, -1)[:, i])
+        acts = dm.data_on_device_via_torch(f"sampled_actions_batch_{p}")
+        assert int(acts.min()) >= 0 and int(acts.max()) <= 20
+        assert torch.equal(acts[T - 1], dm.data_on_device_via_torch("sampled_actions")[:, i])
+        assert torch.equal(dm.data_on_device_via_torch(f"rewards_batch_{p}")[T - 1],
+                           dm.data_on_device_via_torch("rewards")[:, i])
+    assert int(e.num_completed_episodes) >= E      # 64 steps > one 40-step episode
+    assert float(e.episodic_step_sum) / float(e.num_completed_episodes) <= 40

@@ -1,34 +1,43 @@
-// wdb_tag_continuous.cu -- TagContinuous env.step() for sm_100a.
+// wdb_tag_continuous.cu -- TagContinuous env.step() and the fused rollout step for sm_100a.
 //
 // Replaces CudaTagContinuousStep + CudaTagContinuousGenerateObservation +
 // CudaTagContinuousComputeReward (example_envs/tag_continuous/
-// tag_continuous_step_pycuda.cu:13-520 of the reference).
+// tag_continuous_step_pycuda.cu:13-520 of the reference) and -- in the fused entry point
+// wdb_tag_continuous_rollout_step -- also sample_actions x2 (core/random.cu:51-85), the
+// action/reward/done push-to-batch copies and episodic bookkeeping of the trainer
+// (trainer_base.py:437-601) and the 13 reset launches (core/reset.cu:9-75,
+// pycuda_function_manager.py:668-753) of one rollout timestep.
 //
 // Layout / mapping
-//   * one thread per agent; a CTA carries EPB whole env replicas (EPB*N threads) so
-//     that warps stay full when N is not a multiple of 32 (N=105 -> 3 envs = 315
-//     threads = 10 warps, 98.4 % of lanes busy; the reference's 105-thread block wastes
-//     18 % of its 4th warp).
-//   * the env's agent state (x, y, speed, acc, dir, alive) is loaded once with
-//     unit-stride loads, updated in registers, written back once, and staged in shared
-//     memory; the O(N^2) neighbour sweep and the tagger scan read only shared memory.
-//     The reference re-reads global memory for every pair and keeps N*(N-1) distances
-//     and ids per env in global scratch.
-//   * observations are assembled in a shared-memory tile and written out with
-//     unit-stride stores (the reference writes rows with a 4*F-byte stride per thread).
+//   * one thread per agent; a CTA carries EPB whole env replicas (EPB*N threads) so warps
+//     stay full when N is not a multiple of 32 (N=105 -> 3 envs = 315 threads = 10 warps,
+//     98.4 % of lanes busy; the reference's 105-thread block wastes 18 % of its 4th warp).
+//   * agent state (x, y, speed, acc, dir, alive) is loaded once with unit-stride loads,
+//     updated in registers, written back once, and staged in shared memory; the O(N^2)
+//     neighbour sweep and the tagger scan read only shared memory.  The reference re-reads
+//     global memory per pair and keeps N*(N-1) distances and ids per env in global scratch.
+//   * action probabilities are staged through shared memory with unit-stride loads (the
+//     reference reads rows with an A*4-byte stride per thread and round-trips the CDF
+//     through global memory); observations are assembled in a shared-memory tile and
+//     written out with unit-stride stores.
 //
-// Exactness (what "parity" means here)
-//   * kinematics use the same float32 expressions as the reference, so state is
-//     bit-identical to the reference kernel compiled by the same nvcc.
+// Exactness (what "parity" means here; tests/test_gpu_envs.py compares against the
+// reference kernels compiled from the reference sources, bit for bit)
+//   * kinematics use the same float32 expressions as the reference.
 //   * k-nearest selection: the reference orders neighbours by
 //     d = (float)sqrt(pow((double)dx,2)+pow((double)dy,2)) through a swap-based partial
-//     selection sort whose tie order is NOT id order (:179-199).  The fast path ranks by
-//     the float32 squared distance and accepts the result only when every adjacent pair
-//     among the K+1 nearest is separated by more than 2^-19 relative -- then the float32
-//     ranking provably equals the ranking by d and no tie exists.  Otherwise the agent
-//     takes the exact path: the literal reference algorithm on float64-derived distances.
-//   * tag test: a float32 pre-test with a 2^-10 guard band decides "clearly not tagged";
-//     anything near the margin re-evaluates with the reference's float64 expression.
+//     selection sort whose tie order is NOT id order (:179-199).  The fast path ranks all
+//     candidates with a branch-free sorting network on packed (float32 squared distance |
+//     id) keys and accepts the result only when the exact float32 squared distances of the
+//     K+1 nearest are strictly increasing with relative gaps > 2^-19 (2^-15 for the last
+//     pair, which also covers the key truncation) -- then the ranking provably equals the
+//     ranking by d and no tie exists.  Otherwise the agent takes the exact path: the
+//     literal reference algorithm on float64-derived distances.
+//   * dx / (sqrt(2.0)*L) is a float64 division in the reference; here it is a float64
+//     multiply by the reciprocal plus a check that the product is not within 4 ulp of a
+//     float32 rounding boundary (else the true division runs), which gives the same bits.
+//   * tag test: a float32 pre-test with a guard band decides "clearly not tagged"; anything
+//     near the margin re-evaluates with the reference's float64 expression.
 //   * the reference's two data races (rewards[tagger] += ..., num_runners -= 1, :324-329)
 //     are resolved with shared-memory atomics (every tag counts), matching the reference's
 //     NumPy semantics (tag_continuous.py:660-672).
@@ -44,9 +53,12 @@ namespace {
 __constant__ float kTwoPi = 6.283185308;
 __constant__ float kEpsilon = 1.0e-10;
 
+constexpr int kMaxPolicies = 4;
+constexpr int kListLen = 16;   // sorted candidate list kept per agent (self + K+1 <= 16)
+
 struct TcParams {
   int n_envs, N, epb, K, episode_length;
-  int use_full_obs, runner_exits, stage_obs, scratch_in_smem;
+  int use_full_obs, runner_exits, stage_obs, scratch_in_smem, id_bits;
   float *loc_x, *loc_y, *speed, *direction, *acceleration;
   const int *agent_types;
   float *edge_pen;
@@ -55,10 +67,10 @@ struct TcParams {
   float max_speed;
   const float *skill;
   int *alive;
-  float *obs;
-  const int *actions;
-  float *g_nd;   // global scratch (optional)
-  int *g_nid;    // global scratch (optional)
+  float *obs;          // may be NULL in fused mode (observations only go to obs_next)
+  const int *actions;  // step-only mode: input.  fused mode: output (may be NULL)
+  float *g_nd;
+  int *g_nid;
   int *nearest;
   float *rewards;
   const float *step_rewards;
@@ -68,20 +80,52 @@ struct TcParams {
   int *stats;
 };
 
-// ComputeDistance (:13-26) -- the reference's exact expression (float args, int
-// exponent: resolves to the double pow, double sqrt, narrowed to float).
+struct FusedParams {
+  // sampler
+  void *rng;
+  const float *uniforms;            // optional test hook [E, N, 2]
+  int n_policies, A0, A1;
+  const int *agent_policy;          // [N] policy index of each agent
+  const int *agent_slot;            // [N] index of the agent inside its policy
+  int policy_size[kMaxPolicies];
+  const float *probs0[kMaxPolicies];  // [E, Np, A0]
+  const float *probs1[kMaxPolicies];  // [E, Np, A1]
+  int *actions_out;                 // sampled_actions [E, N, 2]
+  int *actions_head0, *actions_head1;  // optional [E, N, 1]
+  // push-to-batch slots of this timestep (all optional)
+  int *actions_batch[kMaxPolicies];     // [E, Np, 2]
+  float *rewards_batch[kMaxPolicies];   // [E, Np]
+  float *obs_next[kMaxPolicies];        // [E, Np, F] : post-step (post-reset) observations
+  int *done_batch;                      // [E]
+  // episodic bookkeeping (optional)
+  float *reward_running_sum[kMaxPolicies];   // [E, Np]
+  float *episodic_reward_sum[kMaxPolicies];  // scalar
+  int *step_running_sum;                     // [E]
+  unsigned long long *episodic_step_sum, *num_completed;
+  // done-masked reset
+  const wdb_reset_desc *reset_table;
+  int n_reset;
+  const float *obs_at_reset;        // [E, N, F] (for obs_next of envs that reset)
+  int do_reset;
+};
+
+// ComputeDistance (:13-26) -- the reference's exact expression (float args, int exponent:
+// resolves to the double pow, double sqrt, narrowed to float).
 __device__ __forceinline__ float exact_distance(float x1, float y1, float x2, float y2) {
   return sqrt(pow(x1 - x2, 2) + pow(y1 - y2, 2));
 }
 
 // Literal restatement of :154-199 for ONE agent on a private scratch list.
-__device__ __noinline__ int exact_select(const float *sx, const float *sy, const int *salive,
-                                         int N, int a, int K, float *d, int *ids) {
+__device__ __noinline__ int exact_select(const float2 *pos, const int *salive, int N, int a,
+                                         int K, float *d, int *ids) {
   int nv = 0;
   for (int b = 0; b < N; b++)
     if (b != a && salive[b]) ids[nv++] = b;
-  const float xa = sx[a], ya = sy[a];
-  for (int i = 0; i < nv; i++) d[i] = exact_distance(xa, ya, sx[ids[i]], sy[ids[i]]);
+  const float2 pa = pos[a];
+  for (int i = 0; i < nv; i++) {
+    const float2 pb = pos[ids[i]];
+    d[i] = exact_distance(pa.x, pa.y, pb.x, pb.y);
+  }
   const int kk = min(nv, K);
   for (int i = 0; i < kk; i++) {
     for (int j = i + 1; j < nv; j++) {
@@ -94,15 +138,64 @@ __device__ __noinline__ int exact_select(const float *sx, const float *sy, const
   return kk;
 }
 
-template <int C>
-__global__ void __launch_bounds__(1024)
-tag_continuous_step_kernel(const TcParams P) {
+// ---------------------------------------------------------------- sorting networks
+__device__ __forceinline__ void cex(uint32_t &a, uint32_t &b) {
+  const uint32_t lo = min(a, b), hi = max(a, b);
+  a = lo; b = hi;
+}
+
+// Batcher odd-even merge sort of 16 keys (63 compare-exchanges, fully unrolled)
+__device__ __forceinline__ void sort16(uint32_t (&v)[kListLen]) {
+#pragma unroll
+  for (int p = 1; p < kListLen; p <<= 1) {
+#pragma unroll
+    for (int k = p; k >= 1; k >>= 1) {
+#pragma unroll
+      for (int j = k % p; j + k < kListLen; j += 2 * k) {
+#pragma unroll
+        for (int i = 0; i < k; i++) {
+          if (i + j + k < kListLen && (i + j) / (2 * p) == (i + j + k) / (2 * p))
+            cex(v[i + j], v[i + j + k]);
+        }
+      }
+    }
+  }
+}
+
+// bitonic merge of a 16-element bitonic sequence into ascending order (32 CEs)
+__device__ __forceinline__ void bitonic_merge16(uint32_t (&v)[kListLen]) {
+#pragma unroll
+  for (int k = kListLen / 2; k >= 1; k >>= 1) {
+#pragma unroll
+    for (int i = 0; i < kListLen; i++) {
+      if ((i & k) == 0) cex(v[i], v[i | k]);
+    }
+  }
+}
+
+// q = (float)((double)d / c) bit-exactly, with inv_c = 1.0 / c: the float64 product can
+// differ from the float64 quotient by a few ulp(53), which changes the float32 rounding
+// only if the product sits within those few ulp of a float32 rounding boundary (the 29
+// discarded mantissa bits ~ 0x10000000).  Those (probability ~2^-26) take the real divide.
+__device__ __forceinline__ float div_by_const_f64(float d, double c, double inv_c) {
+  const double prod = (double)d * inv_c;
+  const uint32_t lo = (uint32_t)__double2loint(prod) & 0x1FFFFFFFu;
+  if (__builtin_expect(lo - 0x0FFFFFF8u <= 0x10u, 0)) return (float)((double)d / c);
+  return (float)prod;
+}
+
+// MAXT = 320: the common geometry (EPB * N <= 320 threads, two CTAs per SM, <= 96
+// registers per thread); MAXT = 1024: one env of up to 1024 agents per CTA.
+template <bool FUSED, int MAXT>
+__global__ void __launch_bounds__(MAXT, MAXT == 320 ? 2 : 1)
+tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant__ FusedParams Q) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int N = P.N, epb = P.epb, K = P.K;
   const int EN = epb * N;
-  float *sx = reinterpret_cast<float *>(smem_raw);
-  float *sy = sx + EN;
-  float *ssp = sy + EN;
+  const int nwarps = blockDim.x / kWarp;
+  float2 *spos = reinterpret_cast<float2 *>(smem_raw);   // real positions
+  float2 *skey = spos + EN;                              // positions, dead agents = +inf
+  float *ssp = reinterpret_cast<float *>(skey + EN);
   float *sacc = ssp + EN;
   float *sdir = sacc + EN;
   float *srew = sdir + EN;
@@ -111,17 +204,21 @@ tag_continuous_step_kernel(const TcParams P) {
   int *stag = stype + N;          // [N]
   int *s_t = stag + N;            // [epb]
   int *s_nrun = s_t + epb;        // [epb]
-  int *s_ntag = s_nrun + epb;     // [1] (+3 pad)
-  float *s_scr_d = reinterpret_cast<float *>(s_ntag + 4);      // [nwarps][N] if scratch_in_smem
-  const int nwarps = blockDim.x / kWarp;
+  int *s_nalive = s_nrun + epb;   // [epb]
+  int *s_done = s_nalive + epb;   // [epb]
+  int *s_ntag = s_done + epb;     // [4]
+  float *s_scr_d = reinterpret_cast<float *>(s_ntag + 4);
   int *s_scr_i = reinterpret_cast<int *>(s_scr_d + (P.scratch_in_smem ? nwarps * N : 0));
-  float *sobs = reinterpret_cast<float *>(s_scr_i + (P.scratch_in_smem ? nwarps * N : 0));
+  // big tile: action probabilities first (fused mode), then the observation tile
+  float *s_tile = reinterpret_cast<float *>(s_scr_i + (P.scratch_in_smem ? nwarps * N : 0));
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int le = tid / N;
   const int a = tid - le * N;
-  const int env = blockIdx.x * epb + le;
+  const int env0 = blockIdx.x * epb;
+  const int env = env0 + le;
+  const int envs_here = min(epb, P.n_envs - env0);
   const bool active = (le < epb) && (env < P.n_envs);
   const int gi = env * N + a;
   const int li = le * N + a;
@@ -129,22 +226,99 @@ tag_continuous_step_kernel(const TcParams P) {
 
   // ------------------------------------------------------------------ phase 0
   if (tid < N) stype[tid] = P.agent_types[tid];
+  if (tid < epb) s_nalive[tid] = 0;
   if (active && a == 0) {
     const int t = P.timestep[env] + 1;   // :391-393
     P.timestep[env] = t;
     s_t[le] = t;
     s_nrun[le] = P.num_runners[env];
   }
+
+  int act0 = 0, act1 = 0;
+  if (FUSED) {
+    // ---- categorical sampling of both action heads (core/random.cu:51-85) ----
+    // stage every policy's [envs_here, Np, A] block (contiguous in global memory) with
+    // unit-stride loads; rows keep their global layout (stride A is odd for A = 21, so a
+    // thread walking its own row is bank-conflict free)
+    int off = 0;
+    int p_off0[kMaxPolicies], p_off1[kMaxPolicies];
+#pragma unroll
+    for (int p = 0; p < kMaxPolicies; p++) {
+      if (p < Q.n_policies) {
+        const int np = Q.policy_size[p];
+        p_off0[p] = off;
+        {
+          const int n = envs_here * np * Q.A0;
+          const float *src = Q.probs0[p] + (long long)env0 * np * Q.A0;
+          for (int i = tid; i < n; i += blockDim.x) s_tile[off + i] = src[i];
+          off += epb * np * Q.A0;
+        }
+        p_off1[p] = off;
+        {
+          const int n = envs_here * np * Q.A1;
+          const float *src = Q.probs1[p] + (long long)env0 * np * Q.A1;
+          for (int i = tid; i < n; i += blockDim.x) s_tile[off + i] = src[i];
+          off += epb * np * Q.A1;
+        }
+      }
+    }
+    __syncthreads();
+    if (active) {
+      const int pol = Q.agent_policy[a], slot = Q.agent_slot[a];
+      int np = 0, o0 = 0, o1 = 0;
+#pragma unroll
+      for (int p = 0; p < kMaxPolicies; p++)
+        if (p == pol) { np = Q.policy_size[p]; o0 = p_off0[p]; o1 = p_off1[p]; }
+      float u0, u1;
+      if (Q.uniforms) {
+        u0 = Q.uniforms[2ll * gi];
+        u1 = Q.uniforms[2ll * gi + 1];
+      } else {
+        const RngHeader h = *reinterpret_cast<const RngHeader *>(Q.rng);
+        unsigned long long *offp = rng_offsets(Q.rng);
+        const unsigned long long o = offp[gi];
+        const uint4 d = rng_draw4(h, (unsigned long long)gi, o);
+        offp[gi] = o + 1;
+        u0 = u32_to_uniform(d.x);
+        u1 = u32_to_uniform(d.y);
+      }
+      {
+        float *row = s_tile + o0 + (le * np + slot) * Q.A0;
+        float c = row[0];
+        for (int i = 1; i < Q.A0; i++) { c = row[i] + c; row[i] = c; }
+        act0 = search_index(row, 1, u0, Q.A0 - 1);
+      }
+      {
+        float *row = s_tile + o1 + (le * np + slot) * Q.A1;
+        float c = row[0];
+        for (int i = 1; i < Q.A1; i++) { c = row[i] + c; row[i] = c; }
+        act1 = search_index(row, 1, u1, Q.A1 - 1);
+      }
+      if (Q.actions_out) *reinterpret_cast<int2 *>(Q.actions_out + 2ll * gi) = make_int2(act0, act1);
+      if (Q.actions_head0) Q.actions_head0[gi] = act0;
+      if (Q.actions_head1) Q.actions_head1[gi] = act1;
+      if (Q.actions_batch[0]) {
+#pragma unroll
+        for (int p = 0; p < kMaxPolicies; p++)
+          if (p == pol && Q.actions_batch[p])
+            *reinterpret_cast<int2 *>(Q.actions_batch[p] + 2ll * ((long long)env * np + slot)) =
+                make_int2(act0, act1);
+      }
+    }
+  } else if (active) {
+    const int2 act = *reinterpret_cast<const int2 *>(P.actions + 2ll * gi);
+    act0 = act.x; act1 = act.y;
+  }
+
   int alive = 0;
   float cap = 0.f;
   if (active) {
     // :402-465 kinematics, same float32 expression forms as the reference
-    const int2 act = *reinterpret_cast<const int2 *>(P.actions + 2ll * gi);
     float x = P.loc_x[gi], y = P.loc_y[gi], sp = P.speed[gi];
     float dir = P.direction[gi], acc = P.acceleration[gi];
     alive = P.alive[gi];
-    acc += P.acc_actions[act.x];
-    dir = fmod(dir + P.turn_actions[act.y], kTwoPi) * alive;
+    acc += P.acc_actions[act0];
+    dir = fmod(dir + P.turn_actions[act1], kTwoPi) * alive;
     if (dir < 0) dir = kTwoPi + dir;
     cap = P.max_speed * P.skill[a];
     sp = min(cap, max(0.0, sp + acc)) * alive;
@@ -160,15 +334,18 @@ tag_continuous_step_kernel(const TcParams P) {
     }
     P.loc_x[gi] = x; P.loc_y[gi] = y; P.speed[gi] = sp;
     P.direction[gi] = dir; P.acceleration[gi] = acc; P.edge_pen[gi] = ep;
-    sx[li] = x; sy[li] = y; ssp[li] = sp; sacc[li] = acc; sdir[li] = dir;
+    spos[li] = make_float2(x, y);
+    skey[li] = alive ? make_float2(x, y) : make_float2(CUDART_INF_F, CUDART_INF_F);
+    ssp[li] = sp; sacc[li] = acc; sdir[li] = dir;
     salive[li] = alive;
-    // :283-291 reward initialisation (0 + edge + step), kept in shared memory so that
-    // tag rewards can be accumulated atomically
+    if (alive) atomicAdd(&s_nalive[le], 1);
+    // :283-291 reward initialisation (0 + edge + step), kept in shared memory so that tag
+    // rewards can be accumulated atomically
     float r = 0.0f;
     if (alive) { r += ep; r += P.step_rewards[a]; }
     srew[li] = r;
   }
-  __syncthreads();
+  __syncthreads();   // state staged; probability tile is dead from here on
 
   // tagger id list in id order (agent_types is shared by all envs), built by warp 0
   if (warp == 0) {
@@ -185,51 +362,64 @@ tag_continuous_step_kernel(const TcParams P) {
 
   // ------------------------------------------------------------------ observations
   const double diag = sqrt(2.0) * L;                // :94
+  const double inv_diag = 1.0 / diag;
   const float vnorm = P.max_speed + kEpsilon;       // :101
   const int t_env = active ? s_t[le] : 0;
-  const float *ex = sx + le * N, *ey = sy + le * N;
+  const float2 *epos = spos + le * N;
   const int *ealive = salive + le * N;
+  const int F = P.use_full_obs ? 7 * (N - 1) + 1 : 7 * K + 1;
 
   if (!P.use_full_obs) {
-    const int F = 7 * K + 1;
-    float ls[C];
-    int lid[C];
-#pragma unroll
-    for (int p = 0; p < C; p++) { ls[p] = CUDART_INF_F; lid[p] = 0; }
+    uint32_t R[kListLen];
     int kk = 0;
     bool suspect = false;
+    const uint32_t idmask = (1u << P.id_bits) - 1u;
+    const bool net_ok = (K + 2 <= kListLen);
     if (active && alive) {
-      if (C >= K + 1) {
-        // fast path: rank by float32 squared distance, keep the C nearest sorted
-        const float xa = ex[a], ya = ey[a];
-        int nv = 0;
-        for (int b = 0; b < N; b++) {
-          if (b == a || !ealive[b]) continue;
-          nv++;
-          const float dx = xa - ex[b], dy = ya - ey[b];
-          float cs = dx * dx + dy * dy;
-          if (cs < ls[C - 1]) {
-            int cid = b;
+      const int nv = s_nalive[le] - 1;            // alive others
+      kk = min(nv, K);
+      if (net_ok) {
+        // fast path: branch-free top-16 of packed (squared distance | id) keys.  Dead
+        // agents sit at +inf and sort last; self has key (0 | a).
+        const float2 pa = epos[a];
+        const float2 *kp = skey + le * N;
+        for (int base = 0; base < N; base += kListLen) {
+          uint32_t c[kListLen];
 #pragma unroll
-            for (int p = 0; p < C; p++) {
-              const bool sw = cs < ls[p];
-              const float ts = ls[p];
-              const int ti = lid[p];
-              ls[p] = sw ? cs : ts;
-              lid[p] = sw ? cid : ti;
-              cs = sw ? ts : cs;
-              cid = sw ? ti : cid;
+          for (int i = 0; i < kListLen; i++) {
+            const int b = base + i;
+            if (b < N) {
+              const float2 pb = kp[b];
+              const float dx = pa.x - pb.x, dy = pa.y - pb.y;
+              c[i] = (__float_as_uint(dx * dx + dy * dy) & ~idmask) | (uint32_t)b;
+            } else {
+              c[i] = 0x7f800000u | idmask;
             }
           }
-        }
-        kk = min(nv, K);
-        const int m = min(nv, K + 1);
+          sort16(c);
+          if (base == 0) {
 #pragma unroll
-        for (int p = 0; p + 1 < C; p++) {
-          if (p + 1 < m) {
-            // not separated by > 2^-19 relative -> a tie in the reference's float
-            // distance is possible: resolve exactly
-            if (!(ls[p + 1] - ls[p] > ls[p + 1] * 1.9073486328125e-06f)) suspect = true;
+            for (int i = 0; i < kListLen; i++) R[i] = c[i];
+          } else {
+#pragma unroll
+            for (int i = 0; i < kListLen; i++) R[i] = min(R[i], c[kListLen - 1 - i]);
+            bitonic_merge16(R);
+          }
+        }
+        // verification on exact float32 squared distances of self + the K+1 nearest
+        const int m = min(nv, K + 1);
+        if ((int)(R[0] & idmask) != a) suspect = true;     // a co-located agent sorted first
+        float prev = 0.0f;
+#pragma unroll
+        for (int i = 1; i < kListLen; i++) {
+          if (i <= m) {
+            const float2 pb = epos[R[i] & idmask];
+            const float dx = pa.x - pb.x, dy = pa.y - pb.y;
+            const float s = dx * dx + dy * dy;
+            // relative gap: 2^-19 inside the top K, 2^-15 for the (K, K+1) boundary pair
+            const float tol = (i == K + 1) ? 3.0517578125e-05f : 1.9073486328125e-06f;
+            if (!(s - prev > s * tol)) suspect = true;
+            prev = s;
           }
         }
       } else {
@@ -238,111 +428,123 @@ tag_continuous_step_kernel(const TcParams P) {
     }
     // exact path, one lane of the warp at a time on the warp's private scratch
     unsigned todo = __ballot_sync(0xffffffffu, suspect);
-    if (todo) {
-      float *d;
-      int *ids;
-      while (todo) {
-        const int Lx = __ffs(todo) - 1;
-        todo &= todo - 1;
-        if (lane == Lx) {
-          if (P.scratch_in_smem) {
-            d = s_scr_d + warp * N;
-            ids = s_scr_i + warp * N;
-          } else {
-            d = P.g_nd + (long long)gi * (N - 1);
-            ids = P.g_nid + (long long)gi * (N - 1);
-          }
-          kk = exact_select(ex, ey, ealive, N, a, K, d, ids);
-          if (C >= K + 1) {
-#pragma unroll
-            for (int p = 0; p < C; p++)
-              if (p < kk) lid[p] = ids[p];
-          }
-          if (P.stats) atomicAdd(&P.stats[0], 1);
+    while (todo) {
+      const int Lx = __ffs(todo) - 1;
+      todo &= todo - 1;
+      if (lane == Lx) {
+        float *d;
+        int *ids;
+        if (P.scratch_in_smem) {
+          d = s_scr_d + warp * N;
+          ids = s_scr_i + warp * N;
+        } else {
+          d = P.g_nd + (long long)gi * (N - 1);
+          ids = P.g_nid + (long long)gi * (N - 1);
         }
-        __syncwarp();
+        kk = exact_select(epos, ealive, N, a, K, d, ids);
+        if (net_ok) {
+#pragma unroll
+          for (int i = 1; i < kListLen; i++)
+            if (i <= kk) R[i] = (uint32_t)ids[i - 1];
+        }
+        if (P.stats) atomicAdd(&P.stats[0], 1);
       }
+      __syncwarp();
     }
 
     if (active) {
-      float *orow = P.stage_obs ? (sobs + (long long)li * F) : (P.obs + (long long)gi * F);
+      float *orow = P.stage_obs ? (s_tile + (long long)li * F) : (P.obs + (long long)gi * F);
       for (int f = 0; f < F; f++) orow[f] = 0.0f;             // :121-139
       if (alive) {
         int *nn = P.nearest + (long long)gi * K;
-        const float xa = ex[a], ya = ey[a];
+        const float2 pa = epos[a];
         const float spa = ssp[li], acca = sacc[li], dira = sdir[li];
-        if (C >= K + 1) {
+        const bool unit_v = (vnorm == 1.0f);
+        const int *gids = (!net_ok && !P.scratch_in_smem)
+                              ? P.g_nid + (long long)gi * (N - 1) : nullptr;
 #pragma unroll
-          for (int p = 0; p < C; p++) {
-            if (p < kk) {
-              const int b = lid[p];
-              nn[p] = b;                                        // :202-211
-              const int lb = le * N + b;                        // :214-250
-              orow[0 * K + p] = static_cast<float>(ex[b] - xa) / diag;
-              orow[1 * K + p] = static_cast<float>(ey[b] - ya) / diag;
-              orow[2 * K + p] = static_cast<float>(ssp[lb] - spa) / vnorm;
-              orow[3 * K + p] = static_cast<float>(sacc[lb] - acca) / vnorm;
-              orow[4 * K + p] = static_cast<float>(sdir[lb] - dira) / (kTwoPi);
-              orow[5 * K + p] = stype[b];
-              orow[6 * K + p] = ealive[b];
-            }
+        for (int p = 0; p < kListLen - 1; p++) {
+          if (p < kk) {
+            const int b = net_ok ? (int)(R[p + 1] & idmask) : gids[p];
+            nn[p] = b;                                          // :202-211
+            const int lb = le * N + b;                          // :214-250
+            const float2 pb = epos[b];
+            orow[0 * K + p] = div_by_const_f64(pb.x - pa.x, diag, inv_diag);
+            orow[1 * K + p] = div_by_const_f64(pb.y - pa.y, diag, inv_diag);
+            const float dsp = ssp[lb] - spa, dac = sacc[lb] - acca;
+            orow[2 * K + p] = unit_v ? dsp : dsp / vnorm;
+            orow[3 * K + p] = unit_v ? dac : dac / vnorm;
+            orow[4 * K + p] = static_cast<float>(sdir[lb] - dira) / (kTwoPi);
+            orow[5 * K + p] = stype[b];
+            orow[6 * K + p] = ealive[b];
           }
-        } else {
-          // K too large for the register list: ids come from the exact-path scratch.
-          // (a warp's scratch is overwritten by its next lane, so this branch re-runs
-          //  the selection per lane; correctness path only)
-          float *d = P.scratch_in_smem ? nullptr : P.g_nd + (long long)gi * (N - 1);
-          int *ids = P.scratch_in_smem ? nullptr : P.g_nid + (long long)gi * (N - 1);
-          if (ids) {
-            (void)d;
-            for (int p = 0; p < kk; p++) {
-              const int b = ids[p];
-              nn[p] = b;
-              const int lb = le * N + b;
-              orow[0 * K + p] = static_cast<float>(ex[b] - xa) / diag;
-              orow[1 * K + p] = static_cast<float>(ey[b] - ya) / diag;
-              orow[2 * K + p] = static_cast<float>(ssp[lb] - spa) / vnorm;
-              orow[3 * K + p] = static_cast<float>(sacc[lb] - acca) / vnorm;
-              orow[4 * K + p] = static_cast<float>(sdir[lb] - dira) / (kTwoPi);
-              orow[5 * K + p] = stype[b];
-              orow[6 * K + p] = ealive[b];
-            }
+        }
+        if (!net_ok) {
+          for (int p = kListLen - 1; p < kk; p++) {
+            const int b = gids[p];
+            nn[p] = b;
+            const int lb = le * N + b;
+            const float2 pb = epos[b];
+            orow[0 * K + p] = div_by_const_f64(pb.x - pa.x, diag, inv_diag);
+            orow[1 * K + p] = div_by_const_f64(pb.y - pa.y, diag, inv_diag);
+            orow[2 * K + p] = static_cast<float>(ssp[lb] - spa) / vnorm;
+            orow[3 * K + p] = static_cast<float>(sacc[lb] - acca) / vnorm;
+            orow[4 * K + p] = static_cast<float>(sdir[lb] - dira) / (kTwoPi);
+            orow[5 * K + p] = stype[b];
+            orow[6 * K + p] = ealive[b];
           }
         }
         orow[7 * K] = static_cast<float>(t_env) / P.episode_length;   // :251-253
       }
     }
   } else {
-    // full observation (:55-113): one warp per row, lanes over the other agents, so
-    // every feature plane of a row is written with unit-stride stores
+    // full observation (:55-113): one warp per row, lanes over the other agents, so every
+    // feature plane of a row is written with unit-stride stores
     const int M = N - 1;
-    const int F = 7 * M + 1;
-    const int rows = min(epb, P.n_envs - blockIdx.x * epb) * N;
+    const int rows = envs_here * N;
     for (int row = warp; row < rows; row += nwarps) {
       const int re = row / N, ra = row - re * N;
-      const int renv = blockIdx.x * epb + re;
-      float *orow = P.obs + ((long long)renv * N + ra) * F;
-      const float *rx = sx + re * N, *ry = sy + re * N, *rsp = ssp + re * N;
-      const float *racc = sacc + re * N, *rdir = sdir + re * N;
+      const int renv = env0 + re;
+      float *orow = P.obs ? P.obs + ((long long)renv * N + ra) * F : nullptr;
+      float *orow2 = nullptr;
+      if (FUSED) {
+        const int pol = Q.agent_policy[ra];
+#pragma unroll
+        for (int p = 0; p < kMaxPolicies; p++)
+          if (p == pol && Q.obs_next[p])
+            orow2 = Q.obs_next[p] + ((long long)renv * Q.policy_size[p] + Q.agent_slot[ra]) * F;
+      }
+      const float2 *rpos = spos + re * N;
+      const float *rsp = ssp + re * N, *racc = sacc + re * N, *rdir = sdir + re * N;
       const int *ral = salive + re * N;
       const bool self_alive = ral[ra] != 0;
       for (int idx = lane; idx < M; idx += kWarp) {
         const int b = idx < ra ? idx : idx + 1;
         float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f, f4 = 0.f;
         if (self_alive) {
-          f0 = static_cast<float>(rx[b] - rx[ra]) / diag;
-          f1 = static_cast<float>(ry[b] - ry[ra]) / diag;
+          f0 = div_by_const_f64(rpos[b].x - rpos[ra].x, diag, inv_diag);
+          f1 = div_by_const_f64(rpos[b].y - rpos[ra].y, diag, inv_diag);
           f2 = static_cast<float>(rsp[b] - rsp[ra]) / vnorm;
           f3 = static_cast<float>(racc[b] - racc[ra]) / vnorm;
           f4 = static_cast<float>(rdir[b] - rdir[ra]) / (kTwoPi);
         }
-        orow[0 * M + idx] = f0; orow[1 * M + idx] = f1; orow[2 * M + idx] = f2;
-        orow[3 * M + idx] = f3; orow[4 * M + idx] = f4;
-        orow[5 * M + idx] = stype[b];
-        orow[6 * M + idx] = ral[b];
+        const float f5 = stype[b], f6 = ral[b];
+        if (orow) {
+          orow[0 * M + idx] = f0; orow[1 * M + idx] = f1; orow[2 * M + idx] = f2;
+          orow[3 * M + idx] = f3; orow[4 * M + idx] = f4; orow[5 * M + idx] = f5;
+          orow[6 * M + idx] = f6;
+        }
+        if (orow2) {
+          orow2[0 * M + idx] = f0; orow2[1 * M + idx] = f1; orow2[2 * M + idx] = f2;
+          orow2[3 * M + idx] = f3; orow2[4 * M + idx] = f4; orow2[5 * M + idx] = f5;
+          orow2[6 * M + idx] = f6;
+        }
       }
-      if (lane == 0)
-        orow[7 * M] = self_alive ? static_cast<float>(s_t[re]) / P.episode_length : 0.0f;
+      if (lane == 0) {
+        const float tt = self_alive ? static_cast<float>(s_t[re]) / P.episode_length : 0.0f;
+        if (orow) orow[7 * M] = tt;
+        if (orow2) orow2[7 * M] = tt;
+      }
     }
   }
   __syncthreads();   // obs tile complete; srew initialised; tagger list ready
@@ -353,21 +555,22 @@ tag_continuous_step_kernel(const TcParams P) {
   if (is_runner && alive) {                                  // :296-338
     float min_dist = L * sqrt(2.0);
     int nearest_tagger = -1;
-    const float xa = ex[a], ya = ey[a];
+    const float2 pa = epos[a];
     const int ntag = *s_ntag;
-    // float32 pre-test with a guard band; only candidates near the margin (or the grid
-    // diagonal initial value) need the reference's float64 expression
+    // float32 pre-test with a guard band; only candidates near the margin need the
+    // reference's float64 expression
     float min_s = CUDART_INF_F;
     for (int q = 0; q < ntag; q++) {
-      const int b = stag[q];
-      const float dx = xa - ex[b], dy = ya - ey[b];
+      const float2 pb = epos[stag[q]];
+      const float dx = pa.x - pb.x, dy = pa.y - pb.y;
       min_s = fminf(min_s, dx * dx + dy * dy);
     }
     const float guard = P.margin * 1.001f;
     if (min_s <= guard * guard) {
       for (int q = 0; q < ntag; q++) {
         const int b = stag[q];
-        const float dist = exact_distance(xa, ya, ex[b], ey[b]);
+        const float2 pb = epos[b];
+        const float dist = exact_distance(pa.x, pa.y, pb.x, pb.y);
         if (dist < min_dist) { min_dist = dist; nearest_tagger = b; }
       }
       if (min_dist < P.margin) {
@@ -383,34 +586,227 @@ tag_continuous_step_kernel(const TcParams P) {
     if (t_env == P.episode_length) r += P.end_reward;        // :334-337
   }
   __syncthreads();
+  int done_now = 0;
   if (active) {
-    P.rewards[gi] = (stype[a] == 1) ? srew[li] : r;
-    if (a == 0) {                                            // :341-348
-      const int nr = s_nrun[le];
+    r = (stype[a] == 1) ? srew[li] : r;
+    P.rewards[gi] = r;
+    const int nr = s_nrun[le];
+    done_now = (t_env == P.episode_length || nr == 0) ? 1 : 0;   // :341-348
+    if (a == 0) {
       P.num_runners[env] = nr;
-      if (t_env == P.episode_length || nr == 0) P.done[env] = 1;
+      if (FUSED) {
+        // done is sticky in the reference (only the reset kernel clears it)
+        const int d = done_now | (P.done[env] > 0 ? 1 : 0);
+        s_done[le] = d;
+        if (Q.done_batch) Q.done_batch[env] = d;
+        const bool will_reset = d && Q.do_reset;
+        if (!will_reset) { if (d) P.done[env] = 1; }
+        else { P.done[env] = 0; P.timestep[env] = 0; }
+        if (Q.step_running_sum) {
+          const int steps = Q.step_running_sum[env] + 1;
+          if (d) {
+            if (Q.episodic_step_sum) atomicAdd(Q.episodic_step_sum, (unsigned long long)steps);
+            if (Q.num_completed) atomicAdd(Q.num_completed, 1ull);
+            Q.step_running_sum[env] = 0;
+          } else {
+            Q.step_running_sum[env] = steps;
+          }
+        }
+      } else if (done_now) {
+        P.done[env] = 1;
+      }
     }
   }
+  if (FUSED) {
+    __syncthreads();   // s_done visible
+    if (active) {
+      const int pol = Q.agent_policy[a], slot = Q.agent_slot[a];
+      const int d = s_done[le];
+#pragma unroll
+      for (int p = 0; p < kMaxPolicies; p++) {
+        if (p == pol) {
+          const long long pi = (long long)env * Q.policy_size[p] + slot;
+          if (Q.rewards_batch[p]) Q.rewards_batch[p][pi] = r;
+          if (Q.reward_running_sum[p]) {
+            const float run = Q.reward_running_sum[p][pi] + r;
+            if (d) {
+              // one atomic per agent of a finished env (rare: once per episode)
+              if (Q.episodic_reward_sum[p]) atomicAdd(Q.episodic_reward_sum[p], run);
+              Q.reward_running_sum[p][pi] = 0.0f;
+            } else {
+              Q.reward_running_sum[p][pi] = run;
+            }
+          }
+        }
+      }
+    }
+  }
+
   if (!P.use_full_obs && P.stage_obs) {
     // coalesced copy-out of the CTA's contiguous observation tile
-    const int F = 7 * K + 1;
-    const int envs_here = min(epb, P.n_envs - blockIdx.x * epb);
     const int total = envs_here * N * F;
-    float *dst = P.obs + (long long)blockIdx.x * epb * N * F;
-    for (int i = tid; i < total; i += blockDim.x) dst[i] = sobs[i];
+    if (P.obs) {
+      float *dst = P.obs + (long long)env0 * N * F;
+      for (int i = tid; i < total; i += blockDim.x) dst[i] = s_tile[i];
+    }
+    if (FUSED) {
+      // per-policy [E, Np, F] copies for the next policy forward: rows of one warp are
+      // written F floats at a time with unit stride inside each row
+      const int rows = envs_here * N;
+      for (int row = warp; row < rows; row += nwarps) {
+        const int re = row / N, ra = row - re * N;
+        const int pol = Q.agent_policy[ra];
+        float *dst = nullptr;
+#pragma unroll
+        for (int p = 0; p < kMaxPolicies; p++)
+          if (p == pol && Q.obs_next[p])
+            dst = Q.obs_next[p] + ((long long)(env0 + re) * Q.policy_size[p] + Q.agent_slot[ra]) * F;
+        if (dst) {
+          const float *src = s_tile + (long long)row * F;
+          for (int f = lane; f < F; f += kWarp) dst[f] = src[f];
+        }
+      }
+    }
+  }
+
+  if (FUSED && Q.do_reset) {
+    // done-masked reset of this CTA's envs (core/reset.cu:9-75 for every registered array
+    // + undo of done/timestep, already applied above)
+    __syncthreads();   // all global writes of this step by this CTA are issued
+    for (int e = 0; e < envs_here; e++) {
+      if (!s_done[e]) continue;
+      const int renv = env0 + e;
+      for (int arr = 0; arr < Q.n_reset; arr++) {
+        const wdb_reset_desc d = Q.reset_table[arr];
+        const long long words = d.bytes_per_env >> 2;
+        uint32_t *dst = reinterpret_cast<uint32_t *>(
+            reinterpret_cast<char *>(d.dst) + (long long)renv * d.bytes_per_env);
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(
+            reinterpret_cast<const char *>(d.ref) + (long long)renv * d.bytes_per_env);
+        for (long long i = tid; i < words; i += blockDim.x) dst[i] = src[i];
+      }
+      if (Q.obs_at_reset) {
+        const float *src = Q.obs_at_reset + (long long)renv * N * F;
+        for (int row = warp; row < N; row += nwarps) {
+          const int pol = Q.agent_policy[row];
+          float *dst = nullptr;
+#pragma unroll
+          for (int p = 0; p < kMaxPolicies; p++)
+            if (p == pol && Q.obs_next[p])
+              dst = Q.obs_next[p] + ((long long)renv * Q.policy_size[p] + Q.agent_slot[row]) * F;
+          if (dst)
+            for (int f = lane; f < F; f += kWarp) dst[f] = src[(long long)row * F + f];
+        }
+      }
+    }
   }
 }
 
-template <int C>
-int launch_tc(const TcParams &P, int block, size_t smem, cudaStream_t stream, int grid) {
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(tag_continuous_step_kernel<C>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
-    if (e != cudaSuccess) return (int)e;
+struct LaunchPlan {
+  int epb, block, grid;
+  size_t smem;
+};
+
+// shared-memory carve-up; must mirror the kernel prologue
+int plan_launch(TcParams &P, const FusedParams *Q, bool have_gscratch, LaunchPlan &plan) {
+  const int N = P.N, K = P.K;
+  int epb = N >= 320 ? 1 : 320 / N;
+  if (epb > P.n_envs) epb = P.n_envs;
+  const int block = round_up(epb * N, 32);
+  const int nwarps = block / 32;
+  const int F = 7 * K + 1;
+  const size_t base = sizeof(float) * 9ull * epb * N + sizeof(int) * (2ull * N + 4ull * epb + 4);
+  const size_t scr = 8ull * nwarps * N;
+  size_t tile_obs = P.use_full_obs ? 0 : sizeof(float) * (size_t)epb * N * F;
+  size_t tile_probs = 0;
+  if (Q) {
+    for (int p = 0; p < Q->n_policies; p++)
+      tile_probs += sizeof(float) * (size_t)epb * Q->policy_size[p] * (Q->A0 + Q->A1);
   }
-  tag_continuous_step_kernel<C><<<grid, block, smem, stream>>>(P);
+  const size_t kMaxSmem = 200 * 1024;
+  P.scratch_in_smem = (base + scr <= 64 * 1024) || !have_gscratch;
+  if (P.scratch_in_smem && base + scr > kMaxSmem) return (int)cudaErrorInvalidValue;
+  size_t smem = base + (P.scratch_in_smem ? scr : 0);
+  P.stage_obs = !P.use_full_obs && (smem + tile_obs <= 110 * 1024);
+  size_t tile = P.stage_obs ? tile_obs : 0;
+  if (tile_probs > tile) tile = tile_probs;
+  smem += tile;
+  if (smem > kMaxSmem) return (int)cudaErrorInvalidValue;
+  if (!P.stage_obs && !P.use_full_obs && !P.obs) return (int)cudaErrorInvalidValue;
+  P.epb = epb;
+  int bits = 1;
+  while ((1 << bits) < N) bits++;
+  P.id_bits = bits;
+  if (K + 2 > kListLen) {
+    // selection falls back to the exact path for every agent; ids must survive until the
+    // observation is written -> per-agent global scratch
+    if (!have_gscratch) return (int)cudaErrorInvalidValue;
+    P.scratch_in_smem = 0;
+    smem = base + tile;
+  }
+  plan.epb = epb;
+  plan.block = block;
+  plan.grid = (P.n_envs + epb - 1) / epb;
+  plan.smem = smem;
+  return 0;
+}
+
+template <bool FUSED, int MAXT>
+int launch_t(const TcParams &P, const FusedParams &Q, const LaunchPlan &plan, cudaStream_t st) {
+  static size_t configured = 0;
+  if (plan.smem > 48 * 1024 && plan.smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(tag_continuous_kernel<FUSED, MAXT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)plan.smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = plan.smem;
+  }
+  tag_continuous_kernel<FUSED, MAXT><<<plan.grid, plan.block, plan.smem, st>>>(P, Q);
   return finish_launch();
+}
+
+template <bool FUSED>
+int launch(const TcParams &P, const FusedParams &Q, const LaunchPlan &plan, cudaStream_t st) {
+  return plan.block <= 320 ? launch_t<FUSED, 320>(P, Q, plan, st)
+                           : launch_t<FUSED, 1024>(P, Q, plan, st);
+}
+
+int fill_params(TcParams &P, int n_envs, int n_agents, float *loc_x, float *loc_y,
+                float *speed, float *direction, float *acceleration, const int *agent_types,
+                float *edge_hit_reward_penalty, float edge_hit_penalty, float grid_length,
+                const float *acceleration_actions, const float *turn_actions, float max_speed,
+                int num_other_agents_observed, const float *skill_levels,
+                int runner_exits_game_after_tagged, int *still_in_the_game,
+                int use_full_observation, float *obs, const int *action_indices,
+                float *neighbor_distances, int *neighbor_ids_sorted_by_distance,
+                int *nearest_neighbor_ids, float *rewards, const float *step_rewards,
+                int *num_runners, float distance_margin_for_reward,
+                float tag_reward_for_tagger, float tag_penalty_for_runner,
+                float end_of_game_reward_for_runner, int *done, int *env_timestep,
+                int episode_length, int *stats) {
+  if (!loc_x || !loc_y || !speed || !direction || !acceleration || !agent_types ||
+      !edge_hit_reward_penalty || !acceleration_actions || !turn_actions || !skill_levels ||
+      !still_in_the_game || !nearest_neighbor_ids || !rewards || !step_rewards ||
+      !num_runners || !done || !env_timestep)
+    return (int)cudaErrorInvalidValue;
+  if (n_envs <= 0 || n_agents < 2 || n_agents > 1024 || num_other_agents_observed < 0)
+    return (int)cudaErrorInvalidValue;
+  P.n_envs = n_envs; P.N = n_agents; P.K = num_other_agents_observed;
+  P.episode_length = episode_length;
+  P.use_full_obs = use_full_observation; P.runner_exits = runner_exits_game_after_tagged;
+  P.loc_x = loc_x; P.loc_y = loc_y; P.speed = speed; P.direction = direction;
+  P.acceleration = acceleration; P.agent_types = agent_types;
+  P.edge_pen = edge_hit_reward_penalty; P.edge_hit_penalty = edge_hit_penalty;
+  P.grid_length = grid_length; P.acc_actions = acceleration_actions;
+  P.turn_actions = turn_actions; P.max_speed = max_speed; P.skill = skill_levels;
+  P.alive = still_in_the_game; P.obs = obs; P.actions = action_indices;
+  P.g_nd = neighbor_distances; P.g_nid = neighbor_ids_sorted_by_distance;
+  P.nearest = nearest_neighbor_ids; P.rewards = rewards; P.step_rewards = step_rewards;
+  P.num_runners = num_runners; P.margin = distance_margin_for_reward;
+  P.tag_reward = tag_reward_for_tagger; P.tag_penalty = tag_penalty_for_runner;
+  P.end_reward = end_of_game_reward_for_runner; P.done = done; P.timestep = env_timestep;
+  P.stats = stats;
+  return 0;
 }
 
 }  // namespace
@@ -429,63 +825,85 @@ WDB_API int wdb_tag_continuous_step(
     float tag_penalty_for_runner, float end_of_game_reward_for_runner, int *done,
     int *env_timestep, int episode_length, int *stats) {
   (void)blocks_per_env;  // launch geometry is chosen here; kept for call compatibility
-  if (!loc_x || !loc_y || !speed || !direction || !acceleration || !agent_types ||
-      !edge_hit_reward_penalty || !acceleration_actions || !turn_actions ||
-      !skill_levels || !still_in_the_game || !obs || !action_indices ||
-      !nearest_neighbor_ids || !rewards || !step_rewards || !num_runners || !done ||
-      !env_timestep)
-    return (int)cudaErrorInvalidValue;
-  if (n_envs <= 0 || n_agents < 2 || n_agents > 1024 || num_other_agents_observed < 0)
-    return (int)cudaErrorInvalidValue;
-  if ((uintptr_t)action_indices & 7) return (int)cudaErrorMisalignedAddress;
-
   TcParams P;
-  P.n_envs = n_envs; P.N = n_agents; P.K = num_other_agents_observed;
-  P.episode_length = episode_length;
-  P.use_full_obs = use_full_observation; P.runner_exits = runner_exits_game_after_tagged;
-  P.loc_x = loc_x; P.loc_y = loc_y; P.speed = speed; P.direction = direction;
-  P.acceleration = acceleration; P.agent_types = agent_types;
-  P.edge_pen = edge_hit_reward_penalty; P.edge_hit_penalty = edge_hit_penalty;
-  P.grid_length = grid_length; P.acc_actions = acceleration_actions;
-  P.turn_actions = turn_actions; P.max_speed = max_speed; P.skill = skill_levels;
-  P.alive = still_in_the_game; P.obs = obs; P.actions = action_indices;
-  P.g_nd = neighbor_distances; P.g_nid = neighbor_ids_sorted_by_distance;
-  P.nearest = nearest_neighbor_ids; P.rewards = rewards; P.step_rewards = step_rewards;
-  P.num_runners = num_runners; P.margin = distance_margin_for_reward;
-  P.tag_reward = tag_reward_for_tagger; P.tag_penalty = tag_penalty_for_runner;
-  P.end_reward = end_of_game_reward_for_runner; P.done = done; P.timestep = env_timestep;
-  P.stats = stats;
+  int err = fill_params(P, n_envs, n_agents, loc_x, loc_y, speed, direction, acceleration,
+                        agent_types, edge_hit_reward_penalty, edge_hit_penalty, grid_length,
+                        acceleration_actions, turn_actions, max_speed,
+                        num_other_agents_observed, skill_levels,
+                        runner_exits_game_after_tagged, still_in_the_game,
+                        use_full_observation, obs, action_indices, neighbor_distances,
+                        neighbor_ids_sorted_by_distance, nearest_neighbor_ids, rewards,
+                        step_rewards, num_runners, distance_margin_for_reward,
+                        tag_reward_for_tagger, tag_penalty_for_runner,
+                        end_of_game_reward_for_runner, done, env_timestep, episode_length,
+                        stats);
+  if (err) return err;
+  if (!obs || !action_indices) return (int)cudaErrorInvalidValue;
+  if ((uintptr_t)action_indices & 7) return (int)cudaErrorMisalignedAddress;
+  LaunchPlan plan;
+  err = plan_launch(P, nullptr, neighbor_distances && neighbor_ids_sorted_by_distance, plan);
+  if (err) return err;
+  FusedParams Q = {};
+  return launch<false>(P, Q, plan, as_stream(stream));
+}
 
-  const int N = n_agents, K = P.K;
-  int epb = N >= 320 ? 1 : 320 / N;
-  if (epb > n_envs) epb = n_envs;
-  const int block = round_up(epb * N, 32);
-  const int nwarps = block / 32;
-  const int F = 7 * K + 1;
-  const size_t base = sizeof(float) * 7ull * epb * N + sizeof(int) * (2ull * N + 2ull * epb + 4);
-  const size_t scr = 8ull * nwarps * N;
-  const size_t tile = use_full_observation ? 0 : sizeof(float) * (size_t)epb * N * F;
-  const size_t kMaxSmem = 200 * 1024;
-  const bool have_gscratch = neighbor_distances && neighbor_ids_sorted_by_distance;
-  P.scratch_in_smem = (base + scr <= 64 * 1024) || !have_gscratch;
-  if (P.scratch_in_smem && base + scr > kMaxSmem) return (int)cudaErrorInvalidValue;
-  size_t smem = base + (P.scratch_in_smem ? scr : 0);
-  P.stage_obs = !use_full_observation && (smem + tile <= 110 * 1024);
-  if (P.stage_obs) smem += tile;
-  P.epb = epb;
-  const int grid = (n_envs + epb - 1) / epb;
-  cudaStream_t st = as_stream(stream);
-  if (use_full_observation) return launch_tc<1>(P, block, smem, st, grid);
-  if (K + 1 <= 2) return launch_tc<2>(P, block, smem, st, grid);
-  if (K + 1 <= 4) return launch_tc<4>(P, block, smem, st, grid);
-  if (K + 1 <= 6) return launch_tc<6>(P, block, smem, st, grid);
-  if (K + 1 <= 8) return launch_tc<8>(P, block, smem, st, grid);
-  if (K + 1 <= 11) return launch_tc<11>(P, block, smem, st, grid);
-  if (K + 1 <= 16) return launch_tc<16>(P, block, smem, st, grid);
-  // K too large for the register list: every agent takes the exact path, which needs
-  // per-agent scratch that survives until the observation is written -> global scratch
-  if (!have_gscratch) return (int)cudaErrorInvalidValue;
-  P.scratch_in_smem = 0;
-  smem = base + (P.stage_obs ? tile : 0);
-  return launch_tc<1>(P, block, smem, st, grid);
+WDB_API int wdb_tag_continuous_rollout_step(void *stream, const wdb_tc_env *env,
+                                            const wdb_tc_rollout *ro) {
+  if (!env || !ro) return (int)cudaErrorInvalidValue;
+  TcParams P;
+  int err = fill_params(
+      P, env->n_envs, env->n_agents, env->loc_x, env->loc_y, env->speed, env->direction,
+      env->acceleration, env->agent_types, env->edge_hit_reward_penalty,
+      env->edge_hit_penalty, env->grid_length, env->acceleration_actions, env->turn_actions,
+      env->max_speed, env->num_other_agents_observed, env->skill_levels,
+      env->runner_exits_game_after_tagged, env->still_in_the_game,
+      env->use_full_observation, env->obs, nullptr, env->neighbor_distances,
+      env->neighbor_ids_sorted_by_distance, env->nearest_neighbor_ids, env->rewards,
+      env->step_rewards, env->num_runners, env->distance_margin_for_reward,
+      env->tag_reward_for_tagger, env->tag_penalty_for_runner,
+      env->end_of_game_reward_for_runner, env->done, env->env_timestep, env->episode_length,
+      env->stats);
+  if (err) return err;
+  if (ro->n_policies < 1 || ro->n_policies > kMaxPolicies || !ro->agent_policy ||
+      !ro->agent_slot || ro->n_actions0 < 1 || ro->n_actions1 < 1)
+    return (int)cudaErrorInvalidValue;
+  if (!ro->uniforms && !ro->rng_state) return (int)cudaErrorInvalidValue;
+  if (ro->sampled_actions && ((uintptr_t)ro->sampled_actions & 7))
+    return (int)cudaErrorMisalignedAddress;
+  FusedParams Q = {};
+  Q.rng = ro->rng_state; Q.uniforms = ro->uniforms;
+  Q.n_policies = ro->n_policies; Q.A0 = ro->n_actions0; Q.A1 = ro->n_actions1;
+  Q.agent_policy = ro->agent_policy; Q.agent_slot = ro->agent_slot;
+  int total = 0;
+  for (int p = 0; p < ro->n_policies; p++) {
+    const wdb_tc_policy_io &io = ro->policy[p];
+    if (!io.probs0 || !io.probs1 || io.n_agents < 1) return (int)cudaErrorInvalidValue;
+    if (io.actions_batch && ((uintptr_t)io.actions_batch & 7))
+      return (int)cudaErrorMisalignedAddress;
+    Q.policy_size[p] = io.n_agents;
+    Q.probs0[p] = io.probs0; Q.probs1[p] = io.probs1;
+    Q.actions_batch[p] = io.actions_batch; Q.rewards_batch[p] = io.rewards_batch;
+    Q.obs_next[p] = io.obs_next; Q.reward_running_sum[p] = io.reward_running_sum;
+    Q.episodic_reward_sum[p] = io.episodic_reward_sum;
+    total += io.n_agents;
+  }
+  if (total != env->n_agents) return (int)cudaErrorInvalidValue;
+  // a NULL actions_batch[0] disables the action push for every policy (kernel fast test)
+  Q.actions_out = ro->sampled_actions;
+  Q.actions_head0 = ro->sampled_actions_0; Q.actions_head1 = ro->sampled_actions_1;
+  Q.done_batch = ro->done_batch; Q.step_running_sum = ro->step_running_sum;
+  Q.episodic_step_sum = ro->episodic_step_sum; Q.num_completed = ro->num_completed_episodes;
+  Q.reset_table = ro->reset_table; Q.n_reset = ro->n_reset_arrays;
+  Q.obs_at_reset = ro->obs_at_reset; Q.do_reset = ro->reset_done_envs;
+  if (Q.do_reset && Q.n_reset > 0 && !Q.reset_table) return (int)cudaErrorInvalidValue;
+  LaunchPlan plan;
+  err = plan_launch(P, &Q, env->neighbor_distances && env->neighbor_ids_sorted_by_distance,
+                    plan);
+  if (err) return err;
+  if (!P.stage_obs && !P.use_full_obs) {
+    // the per-policy observation push needs the shared-memory tile
+    for (int p = 0; p < Q.n_policies; p++)
+      if (Q.obs_next[p]) return (int)cudaErrorInvalidValue;
+  }
+  return launch<true>(P, Q, plan, as_stream(stream));
 }

@@ -24,6 +24,55 @@ class ResetDesc(ctypes.Structure):
     _fields_ = [("dst", _vp), ("ref", _vp), ("bytes_per_env", _ll), ("pool_rows", _ll)]
 
 
+_fp = ctypes.c_void_p  # device pointers travel as integers
+
+
+class TcEnv(ctypes.Structure):
+    """struct wdb_tc_env (include/wdb200.h)."""
+
+    _fields_ = [
+        ("n_envs", _i), ("n_agents", _i),
+        ("loc_x", _fp), ("loc_y", _fp), ("speed", _fp), ("direction", _fp),
+        ("acceleration", _fp), ("agent_types", _fp), ("edge_hit_reward_penalty", _fp),
+        ("edge_hit_penalty", _f), ("grid_length", _f),
+        ("acceleration_actions", _fp), ("turn_actions", _fp),
+        ("max_speed", _f), ("num_other_agents_observed", _i), ("skill_levels", _fp),
+        ("runner_exits_game_after_tagged", _i), ("still_in_the_game", _fp),
+        ("use_full_observation", _i), ("obs", _fp), ("neighbor_distances", _fp),
+        ("neighbor_ids_sorted_by_distance", _fp), ("nearest_neighbor_ids", _fp),
+        ("rewards", _fp), ("step_rewards", _fp), ("num_runners", _fp),
+        ("distance_margin_for_reward", _f), ("tag_reward_for_tagger", _f),
+        ("tag_penalty_for_runner", _f), ("end_of_game_reward_for_runner", _f),
+        ("done", _fp), ("env_timestep", _fp), ("episode_length", _i), ("stats", _fp),
+    ]
+
+
+class TcPolicyIO(ctypes.Structure):
+    """struct wdb_tc_policy_io."""
+
+    _fields_ = [
+        ("n_agents", _i), ("probs0", _fp), ("probs1", _fp), ("actions_batch", _fp),
+        ("rewards_batch", _fp), ("obs_next", _fp), ("reward_running_sum", _fp),
+        ("episodic_reward_sum", _fp),
+    ]
+
+
+class TcRollout(ctypes.Structure):
+    """struct wdb_tc_rollout."""
+
+    _fields_ = [
+        ("rng_state", _fp), ("uniforms", _fp),
+        ("n_policies", _i), ("n_actions0", _i), ("n_actions1", _i),
+        ("agent_policy", _fp), ("agent_slot", _fp),
+        ("policy", TcPolicyIO * 4),
+        ("sampled_actions", _fp), ("sampled_actions_0", _fp), ("sampled_actions_1", _fp),
+        ("done_batch", _fp), ("step_running_sum", _fp),
+        ("episodic_step_sum", _fp), ("num_completed_episodes", _fp),
+        ("reset_table", _fp), ("n_reset_arrays", _i), ("obs_at_reset", _fp),
+        ("reset_done_envs", _i),
+    ]
+
+
 _SIGNATURES = {
     "wdb_abi_version": (_i, []),
     "wdb_error_string": (ctypes.c_char_p, [_i]),
@@ -48,6 +97,8 @@ _SIGNATURES = {
          _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _vp,
          _vp, _i, _vp],
     ),
+    "wdb_tag_continuous_rollout_step": (
+        _i, [_vp, ctypes.POINTER(TcEnv), ctypes.POINTER(TcRollout)]),
     "wdb_cartpole_step": (
         _i,
         [_vp, _i, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _f, _f, _f, _f, _vp, _i],

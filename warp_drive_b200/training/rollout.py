@@ -21,7 +21,8 @@ _PROCESSED_OBSERVATIONS = Constants.PROCESSED_OBSERVATIONS
 
 class RolloutEngine:
     def __init__(self, env_wrapper, models, policy_tag_to_agent_id_map, sampler,
-                 batch_size_per_env, use_cuda_graph=True, forward_dtype=None):
+                 batch_size_per_env, use_cuda_graph=True, forward_dtype=None,
+                 use_fused_step=True, write_observations=True):
         self.env_wrapper = env_wrapper
         self.dm = env_wrapper.cuda_data_manager
         self.models = models
@@ -49,12 +50,99 @@ class RolloutEngine:
         # episodic statistics (device scalars: no host sync while rolling out)
         self.reward_running_sum = {p: torch.zeros((self.E, len(ids)), device=dev)
                                    for p, ids in self.policy_map.items()}
-        self.step_running_sum = torch.zeros(self.E, dtype=torch.int64, device=dev)
+        self.step_running_sum = torch.zeros(self.E, dtype=torch.int32, device=dev)
         self.episodic_reward_sum = {p: torch.zeros((), device=dev) for p in self.policies}
         self.episodic_step_sum = torch.zeros((), dtype=torch.int64, device=dev)
         self.num_completed_episodes = torch.zeros((), dtype=torch.int64, device=dev)
         self._graph = None
         self._graph_stream = None
+        # ---- fused single-launch timestep (TagContinuous: 2 discrete heads, Box obs)
+        self.fused = None
+        if use_fused_step and self._fused_eligible():
+            from warp_drive_b200.training.fused_tag_continuous import FusedTagContinuousStep
+
+            self.fused = FusedTagContinuousStep(
+                env_wrapper, self.policy_map, sampler, write_observations=write_observations)
+            self.fused.set_bookkeeping(
+                self.reward_running_sum, self.episodic_reward_sum, self.step_running_sum,
+                self.episodic_step_sum, self.num_completed_episodes)
+            obs = self._tensor(_OBSERVATIONS).view(self.E, self.N, -1)
+            # observations of the *next* forward pass, per policy (filled by the kernel)
+            self.cur_obs = {p: obs.index_select(1, self.ids[p]).contiguous()
+                            for p in self.policies}
+
+    def _fused_eligible(self):
+        from warp_drive_b200.utils.spaces import Box, MultiDiscrete
+
+        env = self.env_wrapper.env
+        if getattr(env, "name", "") != "TagContinuous" or len(self.policies) > 4:
+            return False
+        if self.continuous or self.n_heads != 2:
+            return False
+        if not isinstance(env.action_space[0], MultiDiscrete):
+            return False
+        if not isinstance(env.observation_space[0], Box):
+            return False
+        if self.T < 1 or self.dm.reset_target_to_pool:
+            return False
+        return all(getattr(m, "action_mask", None) is None for m in self.models.values())
+
+    def resync_observations(self):
+        """Re-gather the per-policy observation buffers from `observations` (call after
+        anything outside the engine changed the env state, e.g. reset_all_envs)."""
+        if self.fused is not None:
+            obs = self._tensor(_OBSERVATIONS).view(self.E, self.N, -1)
+            for p in self.policies:
+                self.cur_obs[p].copy_(obs.index_select(1, self.ids[p]))
+
+    def materialize_observations(self):
+        """Scatter the per-policy observation buffers back into the [E, N, F]
+        `observations` array (only needed when the engine runs with
+        write_observations=False and someone wants to read that array)."""
+        if self.fused is not None:
+            obs = self._tensor(_OBSERVATIONS).view(self.E, self.N, -1)
+            for p in self.policies:
+                obs.index_copy_(1, self.ids[p], self.cur_obs[p])
+
+    def _forward(self, model, obs_p):
+        if self.forward_dtype is not None:
+            with torch.autocast("cuda", dtype=self.forward_dtype):
+                probs, _ = model(obs_p)
+            return [q.float().contiguous() for q in probs]
+        probs, _ = model(obs_p)
+        return [q.contiguous() for q in probs]
+
+    def step_fused(self, t, uniforms=None):
+        """One timestep = policy forwards + ONE libwdb200 launch."""
+        with torch.no_grad():
+            T = self.T
+            if t >= 0:
+                batches = {p: self._tensor(f"{_PROCESSED_OBSERVATIONS}_batch_{p}")
+                           for p in self.policies}
+                if t == 0:
+                    for p in self.policies:
+                        batches[p][0].copy_(self.cur_obs[p])
+                obs_in = {p: batches[p][t] for p in self.policies}
+                obs_next = {p: (batches[p][t + 1] if t + 1 < T else self.cur_obs[p])
+                            for p in self.policies}
+                actions_batch = {p: self._tensor(f"{_ACTIONS}_batch_{p}")[t]
+                                 for p in self.policies}
+                rewards_batch = {p: self._tensor(f"{_REWARDS}_batch_{p}")[t]
+                                 for p in self.policies}
+                done_batch = self._tensor(f"{_DONE_FLAGS}_batch")[t]
+            else:   # evaluation-style step: no batch push
+                obs_in = {p: self.cur_obs[p] for p in self.policies}
+                if not hasattr(self, "_scratch_obs"):
+                    self._scratch_obs = {p: torch.empty_like(self.cur_obs[p])
+                                         for p in self.policies}
+                obs_next = self._scratch_obs
+                actions_batch = rewards_batch = done_batch = None
+            probs = {p: self._forward(self.models[p], obs_in[p]) for p in self.policies}
+            self.fused.launch(probs, actions_batch=actions_batch, rewards_batch=rewards_batch,
+                              obs_next=obs_next, done_batch=done_batch, uniforms=uniforms)
+            if t < 0:
+                for p in self.policies:
+                    self.cur_obs[p].copy_(self._scratch_obs[p])
 
     # ------------------------------------------------------------------ one timestep
     def _tensor(self, name):
@@ -69,12 +157,7 @@ class RolloutEngine:
             obs_p = obs if self.covers_all[p] else obs.index_select(1, self.ids[p])
             if t >= 0:
                 self._tensor(f"{_PROCESSED_OBSERVATIONS}_batch_{p}")[t].copy_(obs_p)
-            if self.forward_dtype is not None:
-                with torch.autocast("cuda", dtype=self.forward_dtype):
-                    probs, _ = model(obs_p)
-                probs = [q.float() for q in probs]
-            else:
-                probs, _ = model(obs_p)
+            probs = self._forward(model, obs_p)
             if self.combined is None:
                 out = probs
             else:
@@ -117,12 +200,13 @@ class RolloutEngine:
             self.episodic_reward_sum[p].add_((run * donef[:, None]).sum())
             run.mul_(1.0 - donef[:, None])
         self.step_running_sum.add_(1)
-        done64 = done.to(torch.int64)
-        self.episodic_step_sum.add_((self.step_running_sum * done64).sum())
-        self.step_running_sum.mul_(1 - done64)
-        self.num_completed_episodes.add_(done64.sum())
+        self.episodic_step_sum.add_((self.step_running_sum * done).sum())
+        self.step_running_sum.mul_(1 - done)
+        self.num_completed_episodes.add_(done.sum())
 
     def step(self, t, **sample_params):
+        if self.fused is not None and not sample_params:
+            return self.step_fused(t)
         with torch.no_grad():
             probs = self.evaluate_policies(t)
             self.sample_actions(probs, t, **sample_params)
