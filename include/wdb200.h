@@ -215,6 +215,15 @@ int wdb_cartpole_step(void *stream, int n_envs, float *state, const int *action,
                       float theta_threshold_radians, float x_threshold,
                       int *env_timestep, int episode_length);
 
+/* ------------------------------------------------------------------ update ---- */
+/* Bootstrapped discounted returns of the A2C/PPO update, backwards in time with done
+ * masking (warp_drive/training/algorithms/policygradient/a2c.py:80-93):
+ *   returns[T-1] = done ? r : V ;  returns[t] = r[t] + (done[t] ? 0 : gamma*returns[t+1]).
+ * rewards/values/returns [T, E, Np] f32, done [T, E] i32. */
+int wdb_discounted_returns(void *stream, const float *rewards, const int *done,
+                           const float *values, float *returns, int T, int n_envs,
+                           int n_agents, float gamma);
+
 #ifdef __cplusplus
 }
 #endif

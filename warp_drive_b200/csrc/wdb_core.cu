@@ -353,3 +353,41 @@ WDB_API int wdb_testkernel(void *stream, int n_envs, int n_agents, float *x, int
       x, y, done, actions, multiplier, target, step, episode_length, n_agents);
   return finish_launch();
 }
+
+// ========================================================================= returns
+// Bootstrapped discounted returns, backwards in time (reference: a2c.py:80-93 runs ~6
+// elementwise torch kernels per timestep).  One thread per (env, agent) walks T steps;
+// every step's loads/stores are unit-stride across the CTA.
+__global__ void discounted_returns_kernel(const float *__restrict__ rewards,
+                                          const int *__restrict__ done,
+                                          const float *__restrict__ values,
+                                          float *__restrict__ returns, int T, int E, int Np,
+                                          float gamma) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per_t = (long long)E * Np;
+  if (i >= per_t) return;
+  const int env = (int)(i / Np);
+  long long idx = (long long)(T - 1) * per_t + i;
+  const int d_last = done[(long long)(T - 1) * E + env] > 0;
+  float ret = d_last ? rewards[idx] : values[idx];
+  returns[idx] = ret;
+  for (int t = T - 2; t >= 0; t--) {
+    idx -= per_t;
+    const int d = done[(long long)t * E + env] > 0;
+    const float future = d ? 0.0f : gamma * ret;
+    ret = rewards[idx] + future;
+    returns[idx] = ret;
+  }
+}
+
+WDB_API int wdb_discounted_returns(void *stream, const float *rewards, const int *done,
+                                   const float *values, float *returns, int T, int n_envs,
+                                   int n_agents, float gamma) {
+  if (!rewards || !done || !values || !returns || T < 1 || n_envs < 1 || n_agents < 1)
+    return (int)cudaErrorInvalidValue;
+  const long long n = (long long)n_envs * n_agents;
+  const int block = 128;
+  discounted_returns_kernel<<<(int)((n + block - 1) / block), block, 0, as_stream(stream)>>>(
+      rewards, done, values, returns, T, n_envs, n_agents, gamma);
+  return finish_launch();
+}

@@ -99,6 +99,7 @@ _SIGNATURES = {
     ),
     "wdb_tag_continuous_rollout_step": (
         _i, [_vp, ctypes.POINTER(TcEnv), ctypes.POINTER(TcRollout)]),
+    "wdb_discounted_returns": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f]),
     "wdb_cartpole_step": (
         _i,
         [_vp, _i, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _f, _f, _f, _f, _vp, _i],
