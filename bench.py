@@ -134,9 +134,11 @@ def build_engine(n_envs, seed, graph_steps, use_graph=True, forward_dtype=None):
     wrapper.reset_all_envs()
     # the fused kernel hands observations straight to the per-policy forward buffers; the
     # [E, N, F] `observations` array is only materialised on demand
+    stats = torch.zeros(4, dtype=torch.int32, device="cuda")
     engine = RolloutEngine(wrapper, models, policy_map, sampler, graph_steps,
                            use_cuda_graph=use_graph, forward_dtype=forward_dtype,
-                           write_observations=False)
+                           write_observations=False, stats=stats)
+    engine.stats = stats
     return wrapper, engine, sampler, policy_map
 
 
@@ -351,7 +353,6 @@ def main():
         torch.cuda.synchronize()
 
     # ---- warm-up (also captures the graph)
-    launches0 = wlib.launch_count()
     engine.rollout()
     torch.cuda.synchronize()
     launches_per_rollout = None
@@ -366,6 +367,7 @@ def main():
     torch.cuda.synchronize()
 
     # ---- timed region: exactly K steps
+    engine.stats.zero_()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     with ClockSampler(local_rank) as clocks:
@@ -376,6 +378,7 @@ def main():
         end.record()
         barrier()
     elapsed_ms = start.elapsed_time(end)
+    stats_timed = engine.stats.cpu().numpy().tolist()
     my_launches = (wlib.launch_count() - c0) if args.no_graph else launches_per_rollout * (K // T)
     t = torch.tensor([elapsed_ms], device="cuda", dtype=torch.float64)
     if world > 1:
@@ -425,6 +428,10 @@ def main():
                 "path": "EnvWrapper.step_all_envs with pinned host actions in and "
                         "observations/rewards/done out every step"},
         "gpu_launches": int(my_launches),
+        "kernel_stats": {"exact_tie_path_agents": stats_timed[0], "tags": stats_timed[1],
+                         "agent_steps": E * N * K,
+                         "note": "device counters of the fused kernel over the timed region: "
+                                 "agents that needed the exact tie-resolution path"},
         "roofline": roofline,
     }
     if not args.skip_cpu_baseline:

@@ -207,7 +207,9 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
   int *s_nalive = s_nrun + epb;   // [epb]
   int *s_done = s_nalive + epb;   // [epb]
   int *s_ntag = s_done + epb;     // [4]
-  float *s_scr_d = reinterpret_cast<float *>(s_ntag + 4);
+  int *s_rowbase = s_ntag + 4;    // [N] offset of the agent's obs row inside the tile
+  int *s_rowstride = s_rowbase + N;  // [N] tile stride between consecutive envs
+  float *s_scr_d = reinterpret_cast<float *>(s_rowstride + N);
   int *s_scr_i = reinterpret_cast<int *>(s_scr_d + (P.scratch_in_smem ? nwarps * N : 0));
   // big tile: action probabilities first (fused mode), then the observation tile
   float *s_tile = reinterpret_cast<float *>(s_scr_i + (P.scratch_in_smem ? nwarps * N : 0));
@@ -224,8 +226,33 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
   const int li = le * N + a;
   const float L = P.grid_length;
 
+  const int F = P.use_full_obs ? 7 * (N - 1) + 1 : 7 * K + 1;
+  // observation tile layout == the layout of the destination the next forward pass reads:
+  // per policy p a dense [epb, Np, F] block (one policy covering every agent in step-only
+  // mode), so the copy-out is a plain contiguous block copy per policy
+  int tile_base[kMaxPolicies];
+  {
+    int acc = 0;
+#pragma unroll
+    for (int p = 0; p < kMaxPolicies; p++) {
+      tile_base[p] = acc;
+      if (FUSED && p < Q.n_policies) acc += F * epb * Q.policy_size[p];
+    }
+  }
+
   // ------------------------------------------------------------------ phase 0
-  if (tid < N) stype[tid] = P.agent_types[tid];
+  if (tid < N) {
+    stype[tid] = P.agent_types[tid];
+    int rb = tid * F, rs = N * F;
+    if (FUSED) {
+      const int pol = Q.agent_policy[tid], slot = Q.agent_slot[tid];
+#pragma unroll
+      for (int p = 0; p < kMaxPolicies; p++)
+        if (p == pol) { rb = tile_base[p] + slot * F; rs = Q.policy_size[p] * F; }
+    }
+    s_rowbase[tid] = rb;
+    s_rowstride[tid] = rs;
+  }
   if (tid < epb) s_nalive[tid] = 0;
   if (active && a == 0) {
     const int t = P.timestep[env] + 1;   // :391-393
@@ -367,7 +394,6 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
   const int t_env = active ? s_t[le] : 0;
   const float2 *epos = spos + le * N;
   const int *ealive = salive + le * N;
-  const int F = P.use_full_obs ? 7 * (N - 1) + 1 : 7 * K + 1;
 
   if (!P.use_full_obs) {
     uint32_t R[kListLen];
@@ -406,20 +432,65 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
             bitonic_merge16(R);
           }
         }
-        // verification on exact float32 squared distances of self + the K+1 nearest
+        // ---- verification on EXACT float32 squared distances of the K+1 nearest.
+        // The network ranked keys whose low id_bits were replaced by the id, so (a) two
+        // winners may be mis-ordered when their distances agree in the kept bits -> they
+        // are re-sorted exactly below; (b) every candidate the network left out has a
+        // squared distance >= floor_out, the key of the last winner with its id bits
+        // cleared.  The fast path is valid iff the exact distances are strictly
+        // increasing with relative gaps > 2^-19 (so neither the float rounding of
+        // dx*dx+dy*dy nor the reference's float(sqrt(double)) can reorder or tie them)
+        // and floor_out clears the K-th winner by the same margin.
         const int m = min(nv, K + 1);
         if ((int)(R[0] & idmask) != a) suspect = true;     // a co-located agent sorted first
-        float prev = 0.0f;
+        float es[kListLen];
+        bool misordered = false;
+        {
+          float prev = 0.0f;
 #pragma unroll
-        for (int i = 1; i < kListLen; i++) {
-          if (i <= m) {
-            const float2 pb = epos[R[i] & idmask];
-            const float dx = pa.x - pb.x, dy = pa.y - pb.y;
-            const float s = dx * dx + dy * dy;
-            // relative gap: 2^-19 inside the top K, 2^-15 for the (K, K+1) boundary pair
-            const float tol = (i == K + 1) ? 3.0517578125e-05f : 1.9073486328125e-06f;
-            if (!(s - prev > s * tol)) suspect = true;
-            prev = s;
+          for (int i = 1; i < kListLen; i++) {
+            es[i] = CUDART_INF_F;
+            if (i <= m) {
+              const float2 pb = epos[R[i] & idmask];
+              const float dx = pa.x - pb.x, dy = pa.y - pb.y;
+              es[i] = dx * dx + dy * dy;
+              misordered |= !(es[i] > prev);
+              prev = es[i];
+            }
+          }
+        }
+        uint32_t last_key = 0;     // R[K + 1] without dynamic register indexing
+#pragma unroll
+        for (int i = 1; i < kListLen; i++) last_key = (i == K + 1) ? R[i] : last_key;
+        const float floor_out = __uint_as_float(last_key & ~idmask);
+        if (misordered) {
+          // rare: exact odd-even transposition sort of the (<= 15) winners
+          for (int pass = 0; pass < kListLen - 1; pass++) {
+#pragma unroll
+            for (int i = 1; i + 1 < kListLen; i++) {
+              if (((i + pass) & 1) == 0) continue;
+              const bool sw = es[i + 1] < es[i];
+              const float ts = es[i]; const uint32_t tr = R[i];
+              es[i] = sw ? es[i + 1] : ts;   R[i] = sw ? R[i + 1] : tr;
+              es[i + 1] = sw ? ts : es[i + 1]; R[i + 1] = sw ? tr : R[i + 1];
+            }
+          }
+        }
+        {
+          float prev = 0.0f;
+#pragma unroll
+          for (int i = 1; i < kListLen; i++) {
+            if (i <= m) {
+              if (!(es[i] - prev > es[i] * 1.9073486328125e-06f)) suspect = true;
+              prev = es[i];
+            }
+          }
+          // candidates outside the K+1 winners (exist iff nv > K + 1)
+          if (nv > K + 1) {
+            float xk = 0.0f;
+#pragma unroll
+            for (int i = 1; i < kListLen; i++) xk = (i == K) ? es[i] : xk;
+            if (!(floor_out - xk > floor_out * 1.9073486328125e-06f)) suspect = true;
           }
         }
       } else {
@@ -453,8 +524,17 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
     }
 
     if (active) {
-      float *orow = P.stage_obs ? (s_tile + (long long)li * F) : (P.obs + (long long)gi * F);
-      for (int f = 0; f < F; f++) orow[f] = 0.0f;             // :121-139
+      float *orow = P.stage_obs ? (s_tile + s_rowbase[a] + le * s_rowstride[a])
+                                : (P.obs + (long long)gi * F);
+      // :121-139 zero-initialisation, restricted to what is not overwritten below
+      if (!alive) {
+        for (int f = 0; f < F; f++) orow[f] = 0.0f;
+      } else {
+        for (int p = kk; p < K; p++) {
+#pragma unroll
+          for (int f = 0; f < 7; f++) orow[f * K + p] = 0.0f;
+        }
+      }
       if (alive) {
         int *nn = P.nearest + (long long)gi * K;
         const float2 pa = epos[a];
@@ -643,27 +723,31 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
   }
 
   if (!P.use_full_obs && P.stage_obs) {
-    // coalesced copy-out of the CTA's contiguous observation tile
-    const int total = envs_here * N * F;
-    if (P.obs) {
+    // coalesced copy-out of the observation tile
+    if (!FUSED) {
+      const int total = envs_here * N * F;
       float *dst = P.obs + (long long)env0 * N * F;
       for (int i = tid; i < total; i += blockDim.x) dst[i] = s_tile[i];
-    }
-    if (FUSED) {
-      // per-policy [E, Np, F] copies for the next policy forward: rows of one warp are
-      // written F floats at a time with unit stride inside each row
-      const int rows = envs_here * N;
-      for (int row = warp; row < rows; row += nwarps) {
-        const int re = row / N, ra = row - re * N;
-        const int pol = Q.agent_policy[ra];
-        float *dst = nullptr;
+    } else {
 #pragma unroll
-        for (int p = 0; p < kMaxPolicies; p++)
-          if (p == pol && Q.obs_next[p])
-            dst = Q.obs_next[p] + ((long long)(env0 + re) * Q.policy_size[p] + Q.agent_slot[ra]) * F;
-        if (dst) {
-          const float *src = s_tile + (long long)row * F;
-          for (int f = lane; f < F; f += kWarp) dst[f] = src[f];
+      for (int p = 0; p < kMaxPolicies; p++) {
+        if (p < Q.n_policies && Q.obs_next[p]) {
+          // the tile block of policy p IS the [envs, Np, F] layout of obs_next[p]
+          const int np = Q.policy_size[p];
+          const int total = envs_here * np * F;
+          const float *src = s_tile + tile_base[p];
+          float *dst = Q.obs_next[p] + (long long)env0 * np * F;
+          for (int i = tid; i < total; i += blockDim.x) dst[i] = src[i];
+        }
+      }
+      if (P.obs) {
+        // optional [E, N, F] `observations` array: one warp per agent row
+        for (int e = 0; e < envs_here; e++) {
+          for (int ra = warp; ra < N; ra += nwarps) {
+            const float *src = s_tile + s_rowbase[ra] + e * s_rowstride[ra];
+            float *dst = P.obs + ((long long)(env0 + e) * N + ra) * F;
+            for (int f = lane; f < F; f += kWarp) dst[f] = src[f];
+          }
         }
       }
     }
@@ -715,7 +799,7 @@ int plan_launch(TcParams &P, const FusedParams *Q, bool have_gscratch, LaunchPla
   const int block = round_up(epb * N, 32);
   const int nwarps = block / 32;
   const int F = 7 * K + 1;
-  const size_t base = sizeof(float) * 9ull * epb * N + sizeof(int) * (2ull * N + 4ull * epb + 4);
+  const size_t base = sizeof(float) * 9ull * epb * N + sizeof(int) * (4ull * N + 4ull * epb + 4);
   const size_t scr = 8ull * nwarps * N;
   size_t tile_obs = P.use_full_obs ? 0 : sizeof(float) * (size_t)epb * N * F;
   size_t tile_probs = 0;

@@ -22,7 +22,7 @@ _PROCESSED_OBSERVATIONS = Constants.PROCESSED_OBSERVATIONS
 class RolloutEngine:
     def __init__(self, env_wrapper, models, policy_tag_to_agent_id_map, sampler,
                  batch_size_per_env, use_cuda_graph=True, forward_dtype=None,
-                 use_fused_step=True, write_observations=True):
+                 use_fused_step=True, write_observations=True, stats=None):
         self.env_wrapper = env_wrapper
         self.dm = env_wrapper.cuda_data_manager
         self.models = models
@@ -62,7 +62,8 @@ class RolloutEngine:
             from warp_drive_b200.training.fused_tag_continuous import FusedTagContinuousStep
 
             self.fused = FusedTagContinuousStep(
-                env_wrapper, self.policy_map, sampler, write_observations=write_observations)
+                env_wrapper, self.policy_map, sampler, write_observations=write_observations,
+                stats=stats)
             self.fused.set_bookkeeping(
                 self.reward_running_sum, self.episodic_reward_sum, self.step_running_sum,
                 self.episodic_step_sum, self.num_completed_episodes)
