@@ -44,6 +44,7 @@
 #include <math_constants.h>
 
 #include "wdb_common.cuh"
+#include "wdb_sortnet.cuh"
 
 using namespace wdb;
 
@@ -139,39 +140,10 @@ __device__ __noinline__ int exact_select(const float2 *pos, const int *salive, i
 }
 
 // ---------------------------------------------------------------- sorting networks
-__device__ __forceinline__ void cex(uint32_t &a, uint32_t &b) {
-  const uint32_t lo = min(a, b), hi = max(a, b);
-  a = lo; b = hi;
-}
-
-// Batcher odd-even merge sort of 16 keys (63 compare-exchanges, fully unrolled)
-__device__ __forceinline__ void sort16(uint32_t (&v)[kListLen]) {
-#pragma unroll
-  for (int p = 1; p < kListLen; p <<= 1) {
-#pragma unroll
-    for (int k = p; k >= 1; k >>= 1) {
-#pragma unroll
-      for (int j = k % p; j + k < kListLen; j += 2 * k) {
-#pragma unroll
-        for (int i = 0; i < k; i++) {
-          if (i + j + k < kListLen && (i + j) / (2 * p) == (i + j + k) / (2 * p))
-            cex(v[i + j], v[i + j + k]);
-        }
-      }
-    }
-  }
-}
-
-// bitonic merge of a 16-element bitonic sequence into ascending order (32 CEs)
-__device__ __forceinline__ void bitonic_merge16(uint32_t (&v)[kListLen]) {
-#pragma unroll
-  for (int k = kListLen / 2; k >= 1; k >>= 1) {
-#pragma unroll
-    for (int i = 0; i < kListLen; i++) {
-      if ((i & k) == 0) cex(v[i], v[i | k]);
-    }
-  }
-}
+// (wdb_sortnet.cuh, generated): WDB_SORT16 / WDB_BITONIC_MERGE16 operate on 16 NAMED
+// registers v0..v15 -- an array indexed through nested unrolled loops ended up in local
+// memory (ncu: LDL/STL inside every compare-exchange), named scalars cannot.
+#define WDB_REP16(M) M(0) M(1) M(2) M(3) M(4) M(5) M(6) M(7) M(8) M(9) M(10) M(11) M(12) M(13) M(14) M(15)
 
 // q = (float)((double)d / c) bit-exactly, with inv_c = 1.0 / c: the float64 product can
 // differ from the float64 quotient by a few ulp(53), which changes the float32 rounding
@@ -409,29 +381,38 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
         // agents sit at +inf and sort last; self has key (0 | a).
         const float2 pa = epos[a];
         const float2 *kp = skey + le * N;
-        for (int base = 0; base < N; base += kListLen) {
-          uint32_t c[kListLen];
-#pragma unroll
-          for (int i = 0; i < kListLen; i++) {
-            const int b = base + i;
-            if (b < N) {
-              const float2 pb = kp[b];
-              const float dx = pa.x - pb.x, dy = pa.y - pb.y;
-              c[i] = (__float_as_uint(dx * dx + dy * dy) & ~idmask) | (uint32_t)b;
-            } else {
-              c[i] = 0x7f800000u | idmask;
-            }
-          }
-          sort16(c);
-          if (base == 0) {
-#pragma unroll
-            for (int i = 0; i < kListLen; i++) R[i] = c[i];
-          } else {
-#pragma unroll
-            for (int i = 0; i < kListLen; i++) R[i] = min(R[i], c[kListLen - 1 - i]);
-            bitonic_merge16(R);
-          }
+        uint32_t r0, r1, r2, r3, r4, r5, r6, r7, r8, r9, r10, r11, r12, r13, r14, r15;
+        const uint32_t pad_key = 0x7f800000u | idmask;
+#define WDB_KEY(i)                                                                  \
+  uint32_t c##i = pad_key;                                                          \
+  if (base + i < N) {                                                               \
+    const float2 pb = kp[base + i];                                                 \
+    const float dx = pa.x - pb.x, dy = pa.y - pb.y;                                 \
+    c##i = (__float_as_uint(dx * dx + dy * dy) & ~idmask) | (uint32_t)(base + i);   \
+  }
+#define WDB_COPY(i) r##i = c##i;
+        {
+          const int base = 0;
+          WDB_REP16(WDB_KEY)
+          WDB_SORT16(c)
+          WDB_REP16(WDB_COPY)
         }
+        for (int base = kListLen; base < N; base += kListLen) {
+          WDB_REP16(WDB_KEY)
+          WDB_SORT16(c)
+          // half-cleaner: the 16 smallest of (r ascending) U (c ascending), as a bitonic
+          // sequence, then the bitonic merger restores ascending order
+          r0 = min(r0, c15); r1 = min(r1, c14); r2 = min(r2, c13); r3 = min(r3, c12);
+          r4 = min(r4, c11); r5 = min(r5, c10); r6 = min(r6, c9); r7 = min(r7, c8);
+          r8 = min(r8, c7); r9 = min(r9, c6); r10 = min(r10, c5); r11 = min(r11, c4);
+          r12 = min(r12, c3); r13 = min(r13, c2); r14 = min(r14, c1); r15 = min(r15, c0);
+          WDB_BITONIC_MERGE16(r)
+        }
+#undef WDB_KEY
+#undef WDB_COPY
+        R[0] = r0; R[1] = r1; R[2] = r2; R[3] = r3; R[4] = r4; R[5] = r5; R[6] = r6;
+        R[7] = r7; R[8] = r8; R[9] = r9; R[10] = r10; R[11] = r11; R[12] = r12;
+        R[13] = r13; R[14] = r14; R[15] = r15;
         // ---- verification on EXACT float32 squared distances of the K+1 nearest.
         // The network ranked keys whose low id_bits were replaced by the id, so (a) two
         // winners may be mis-ordered when their distances agree in the kept bits -> they
