@@ -40,6 +40,11 @@ const char *wdb_error_string(int err);
  * `gpu_launches` evidence) */
 long long wdb_launch_count(void);
 
+/* Tuning / A-B switches (results are identical either way).  "tc_history": use last step's
+ * neighbour lists as a distance threshold in the tag_continuous k-nearest search (1, default)
+ * or always run the full sorting network (0). */
+int wdb_set_option(const char *name, int value);
+
 /* ------------------------------------------------------------------ RNG ------ */
 /* Replaces init_random / free_random (warp_drive/cuda_includes/core/random.cu:14-31):
  * the reference heap-allocates one XORWOW curandState per (env, agent) thread; here the

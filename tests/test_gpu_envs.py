@@ -20,6 +20,15 @@ STATE_F = ("loc_x", "loc_y", "speed", "direction", "acceleration", "edge_hit_rew
 STATE_I = ("still_in_the_game", "num_runners", "_done_", "_timestep_")
 
 
+@pytest.fixture(params=[1, 0], ids=["history", "network"])
+def tc_history(request, wdb_lib):
+    """Run the tag_continuous tests with both k-nearest strategies (temporal-coherence
+    threshold vs. full sorting network); results must be identical."""
+    assert wdb_lib.wdb_set_option(b"tc_history", request.param) == 0
+    yield request.param
+    wdb_lib.wdb_set_option(b"tc_history", 1)
+
+
 def _dev(d):
     return {k: (torch.from_numpy(np.ascontiguousarray(v)).cuda() if isinstance(v, np.ndarray) else v)
             for k, v in d.items()}
@@ -56,7 +65,7 @@ def _obs_dim(cfg, N):
 
 
 @pytest.mark.parametrize("name", TC_FIXTURES)
-def test_tag_continuous_teacher_forced_vs_oracle(wdb_lib, name):
+def test_tag_continuous_teacher_forced_vs_oracle(wdb_lib, name, tc_history):
     """Every step starts the oracle from the GPU's current state, so differences cannot
     accumulate: a full multi-episode rollout with device-side resets."""
     fx = load_golden(f"tag_continuous_numpy_{name}.npz")
@@ -104,7 +113,7 @@ def test_tag_continuous_teacher_forced_vs_oracle(wdb_lib, name):
 
 @pytest.mark.parametrize("shape", [(2, 5), (4, 23), (8, 105)])
 @pytest.mark.parametrize("full_obs", [False, True])
-def test_tag_continuous_bit_exact_vs_reference_cuda(wdb_lib, shape, full_obs):
+def test_tag_continuous_bit_exact_vs_reference_cuda(wdb_lib, shape, full_obs, tc_history):
     """Free-running rollouts of OUR kernel and the REFERENCE kernel from the same
     initial state with the same actions; every output array must be bit-identical.
     (Steps where one tagger is credited for >= 2 tags are where the reference has a data
@@ -174,7 +183,7 @@ def test_tag_continuous_bit_exact_vs_reference_cuda(wdb_lib, shape, full_obs):
     assert racy_steps < 40
 
 
-def test_tag_continuous_tie_order_matches_reference_selection(wdb_lib):
+def test_tag_continuous_tie_order_matches_reference_selection(wdb_lib, tc_history):
     """Agents pinned to the same corner produce exact distance ties; the reference's
     swap-based selection does NOT return them in id order (SURVEY.md section 7 'Hard
     parts').  Construct such states and compare ids with the oracle's literal algorithm."""
@@ -212,7 +221,7 @@ def test_tag_continuous_tie_order_matches_reference_selection(wdb_lib):
     assert int(stats[0]) > 0       # the exact tie-resolution path really ran
 
 
-def test_tag_continuous_full_size_properties(wdb_lib):
+def test_tag_continuous_full_size_properties(wdb_lib, tc_history):
     """BASELINE config 2 at full size (2000 x 105, K = 10): size-independent invariants
     over a whole 500-step episode with device-side resets."""
     fx = load_golden("tag_continuous_numpy_config2_short.npz")

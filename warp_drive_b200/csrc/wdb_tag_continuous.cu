@@ -60,6 +60,7 @@ constexpr int kListLen = 16;   // sorted candidate list kept per agent (self + K
 struct TcParams {
   int n_envs, N, epb, K, episode_length;
   int use_full_obs, runner_exits, stage_obs, scratch_in_smem, id_bits;
+  int use_history, scr_warp_bytes;   // per-warp scratch: history candidate list / exact path
   float *loc_x, *loc_y, *speed, *direction, *acceleration;
   const int *agent_types;
   float *edge_pen;
@@ -110,31 +111,110 @@ struct FusedParams {
   int do_reset;
 };
 
+// Byte offsets of the small shared-memory arrays (must agree between the kernel and
+// plan_launch): everything before the per-warp scratch, rounded up to 16 bytes so that the
+// scratch and the big tile behind it are valid TMA (cp.async.bulk) destinations.
+__host__ __device__ inline size_t tc_small_bytes(int epb, int N) {
+  const size_t b = sizeof(float) * 9ull * epb * N + sizeof(int) * (4ull * N + 4ull * epb + 4)
+                   + 16 /* mbarrier + pad */;
+  return (b + 15) & ~(size_t)15;
+}
+
+// ---- TMA 1-D bulk copies (cp.async.bulk) + mbarrier, raw PTX for sm_100a ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; "
+        "selp.u32 %0, 1, 0, p; }"
+        : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst_smem, const void *src, uint32_t bytes,
+                                            uint32_t mbar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void tma_store_1d(void *dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool tma_ok(const void *g, uint32_t s, size_t bytes) {
+  return ((reinterpret_cast<uintptr_t>(g) | (uintptr_t)s | bytes) & 15) == 0 && bytes > 0;
+}
+
 // ComputeDistance (:13-26) -- the reference's exact expression (float args, int exponent:
 // resolves to the double pow, double sqrt, narrowed to float).
 __device__ __forceinline__ float exact_distance(float x1, float y1, float x2, float y2) {
   return sqrt(pow(x1 - x2, 2) + pow(y1 - y2, 2));
 }
 
-// Literal restatement of :154-199 for ONE agent on a private scratch list.
-__device__ __noinline__ int exact_select(const float2 *pos, const int *salive, int N, int a,
-                                         int K, float *d, int *ids) {
-  int nv = 0;
-  for (int b = 0; b < N; b++)
-    if (b != a && salive[b]) ids[nv++] = b;
+// Exact k-nearest selection of ONE agent, executed cooperatively by the 32 lanes of a warp:
+// the reference's literal algorithm (:154-199) -- candidates in id order, float64-derived
+// float distances, K rounds of "for j > i: if d[j] < d[i] swap" -- restated as a scan.
+// One round of that loop leaves at position i the left-most minimum of d[i..], and every
+// element that was a strict new running minimum receives the previous running minimum;
+// that is an exclusive prefix-min (left-biased on ties) over positions i.., which the
+// warp evaluates 32 positions at a time.  Results are bit-identical to the sequential
+// loop, including the order of exact ties.
+__device__ __noinline__ int exact_select_warp(const float2 *pos, const int *salive, int N,
+                                              int a, int K, float *d, int *ids, int lane) {
+  const unsigned full = 0xffffffffu;
   const float2 pa = pos[a];
-  for (int i = 0; i < nv; i++) {
-    const float2 pb = pos[ids[i]];
-    d[i] = exact_distance(pa.x, pa.y, pb.x, pb.y);
-  }
-  const int kk = min(nv, K);
-  for (int i = 0; i < kk; i++) {
-    for (int j = i + 1; j < nv; j++) {
-      if (d[j] < d[i]) {
-        const float td = d[i]; d[i] = d[j]; d[j] = td;
-        const int ti = ids[i]; ids[i] = ids[j]; ids[j] = ti;
-      }
+  int nv = 0;
+  for (int base = 0; base < N; base += kWarp) {            // :154-176
+    const int b = base + lane;
+    const bool valid = (b < N) && (b != a) && (salive[b] != 0);
+    const unsigned m = __ballot_sync(full, valid);
+    if (valid) {
+      const int at = nv + __popc(m & ((1u << lane) - 1));
+      const float2 pb = pos[b];
+      ids[at] = b;
+      d[at] = exact_distance(pa.x, pa.y, pb.x, pb.y);
     }
+    nv += __popc(m);
+  }
+  __syncwarp();
+  const int kk = min(nv, K);
+  for (int i = 0; i < kk; i++) {                           // :179-199
+    float cd = d[i];
+    int cid = ids[i];
+    for (int base = i + 1; base < nv; base += kWarp) {
+      const int j = base + lane;
+      const bool valid = j < nv;
+      const float vd = valid ? d[j] : CUDART_INF_F;
+      const int vid = valid ? ids[j] : -1;
+      float sd = vd;                                        // inclusive left-biased min-scan
+      int sid = vid;
+#pragma unroll
+      for (int off = 1; off < kWarp; off <<= 1) {
+        const float od = __shfl_up_sync(full, sd, off);
+        const int oid = __shfl_up_sync(full, sid, off);
+        if (lane >= off && !(sd < od)) { sd = od; sid = oid; }
+      }
+      float pd = __shfl_up_sync(full, sd, 1);               // exclusive prefix incl. carry
+      int pid = __shfl_up_sync(full, sid, 1);
+      if (lane == 0 || !(pd < cd)) { pd = cd; pid = cid; }
+      if (valid && vd < pd) { d[j] = pd; ids[j] = pid; }    // a new running minimum: swap
+      const float td = __shfl_sync(full, sd, kWarp - 1);
+      const int tid_ = __shfl_sync(full, sid, kWarp - 1);
+      if (td < cd) { cd = td; cid = tid_; }
+      __syncwarp();
+    }
+    if (lane == 0) { d[i] = cd; ids[i] = cid; }
+    __syncwarp();
   }
   return kk;
 }
@@ -181,10 +261,12 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
   int *s_ntag = s_done + epb;     // [4]
   int *s_rowbase = s_ntag + 4;    // [N] offset of the agent's obs row inside the tile
   int *s_rowstride = s_rowbase + N;  // [N] tile stride between consecutive envs
-  float *s_scr_d = reinterpret_cast<float *>(s_rowstride + N);
-  int *s_scr_i = reinterpret_cast<int *>(s_scr_d + (P.scratch_in_smem ? nwarps * N : 0));
+  unsigned long long *s_mbar = reinterpret_cast<unsigned long long *>(
+      smem_raw + tc_small_bytes(epb, N) - 16);   // 8-byte aligned mbarrier
+  // per-warp scratch (history candidate list, then the exact path's distance/id lists)
+  unsigned char *s_scr = smem_raw + tc_small_bytes(epb, N);
   // big tile: action probabilities first (fused mode), then the observation tile
-  float *s_tile = reinterpret_cast<float *>(s_scr_i + (P.scratch_in_smem ? nwarps * N : 0));
+  float *s_tile = reinterpret_cast<float *>(s_scr + (size_t)nwarps * P.scr_warp_bytes);
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -239,36 +321,78 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
     // stage every policy's [envs_here, Np, A] block (contiguous in global memory) with
     // unit-stride loads; rows keep their global layout (stride A is odd for A = 21, so a
     // thread walking its own row is bank-conflict free)
-    int off = 0;
+    // block offsets inside the tile (floats): [p0 head0][p0 head1][p1 head0]...
     int p_off0[kMaxPolicies], p_off1[kMaxPolicies];
+    {
+      int off = 0;
+#pragma unroll
+      for (int p = 0; p < kMaxPolicies; p++) {
+        const int np = (p < Q.n_policies) ? Q.policy_size[p] : 0;
+        p_off0[p] = off; off += epb * np * Q.A0;
+        p_off1[p] = off; off += epb * np * Q.A1;
+      }
+    }
+    // contiguous blocks whose global address, shared address and size are 16-byte aligned
+    // go through the TMA (one elected thread issues cp.async.bulk, the bytes land while
+    // every thread draws its random numbers and loads its state); the rest is copied by
+    // the threads with unit-stride loads
+    const uint32_t mbar = smem_u32(s_mbar);
+    if (tid == 0) mbar_init(mbar, 1);
+    __syncthreads();
+    uint32_t tma_mask = 0;   // bit 2p / 2p+1: block (p, head) travels by TMA
 #pragma unroll
     for (int p = 0; p < kMaxPolicies; p++) {
       if (p < Q.n_policies) {
         const int np = Q.policy_size[p];
-        p_off0[p] = off;
-        {
-          const int n = envs_here * np * Q.A0;
-          const float *src = Q.probs0[p] + (long long)env0 * np * Q.A0;
-          for (int i = tid; i < n; i += blockDim.x) s_tile[off + i] = src[i];
-          off += epb * np * Q.A0;
+        const float *g0 = Q.probs0[p] + (long long)env0 * np * Q.A0;
+        const float *g1 = Q.probs1[p] + (long long)env0 * np * Q.A1;
+        if (tma_ok(g0, smem_u32(s_tile + p_off0[p]), 4ull * envs_here * np * Q.A0)) tma_mask |= 1u << (2 * p);
+        if (tma_ok(g1, smem_u32(s_tile + p_off1[p]), 4ull * envs_here * np * Q.A1)) tma_mask |= 2u << (2 * p);
+      }
+    }
+    if (tid == 0 && tma_mask) {
+      uint32_t total = 0;
+#pragma unroll
+      for (int p = 0; p < kMaxPolicies; p++) {
+        if (p < Q.n_policies) {
+          const int np = Q.policy_size[p];
+          if (tma_mask & (1u << (2 * p))) total += 4u * envs_here * np * Q.A0;
+          if (tma_mask & (2u << (2 * p))) total += 4u * envs_here * np * Q.A1;
         }
-        p_off1[p] = off;
-        {
-          const int n = envs_here * np * Q.A1;
-          const float *src = Q.probs1[p] + (long long)env0 * np * Q.A1;
-          for (int i = tid; i < n; i += blockDim.x) s_tile[off + i] = src[i];
-          off += epb * np * Q.A1;
+      }
+      mbar_expect_tx(mbar, total);
+#pragma unroll
+      for (int p = 0; p < kMaxPolicies; p++) {
+        if (p < Q.n_policies) {
+          const int np = Q.policy_size[p];
+          if (tma_mask & (1u << (2 * p)))
+            tma_load_1d(smem_u32(s_tile + p_off0[p]), Q.probs0[p] + (long long)env0 * np * Q.A0,
+                        4u * envs_here * np * Q.A0, mbar);
+          if (tma_mask & (2u << (2 * p)))
+            tma_load_1d(smem_u32(s_tile + p_off1[p]), Q.probs1[p] + (long long)env0 * np * Q.A1,
+                        4u * envs_here * np * Q.A1, mbar);
         }
       }
     }
-    __syncthreads();
-    if (active) {
-      const int pol = Q.agent_policy[a], slot = Q.agent_slot[a];
-      int np = 0, o0 = 0, o1 = 0;
 #pragma unroll
-      for (int p = 0; p < kMaxPolicies; p++)
-        if (p == pol) { np = Q.policy_size[p]; o0 = p_off0[p]; o1 = p_off1[p]; }
-      float u0, u1;
+    for (int p = 0; p < kMaxPolicies; p++) {
+      if (p < Q.n_policies) {
+        const int np = Q.policy_size[p];
+        if (!(tma_mask & (1u << (2 * p)))) {
+          const int n = envs_here * np * Q.A0;
+          const float *src = Q.probs0[p] + (long long)env0 * np * Q.A0;
+          for (int i = tid; i < n; i += blockDim.x) s_tile[p_off0[p] + i] = src[i];
+        }
+        if (!(tma_mask & (2u << (2 * p)))) {
+          const int n = envs_here * np * Q.A1;
+          const float *src = Q.probs1[p] + (long long)env0 * np * Q.A1;
+          for (int i = tid; i < n; i += blockDim.x) s_tile[p_off1[p] + i] = src[i];
+        }
+      }
+    }
+    // random draw for both heads (independent of the probabilities: overlaps the copies)
+    float u0 = 0.f, u1 = 0.f;
+    if (active) {
       if (Q.uniforms) {
         u0 = Q.uniforms[2ll * gi];
         u1 = Q.uniforms[2ll * gi + 1];
@@ -281,6 +405,15 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
         u0 = u32_to_uniform(d.x);
         u1 = u32_to_uniform(d.y);
       }
+    }
+    __syncthreads();                       // thread-copied blocks visible
+    if (tma_mask) mbar_wait(mbar, 0);      // TMA blocks landed
+    if (active) {
+      const int pol = Q.agent_policy[a], slot = Q.agent_slot[a];
+      int np = 0, o0 = 0, o1 = 0;
+#pragma unroll
+      for (int p = 0; p < kMaxPolicies; p++)
+        if (p == pol) { np = Q.policy_size[p]; o0 = p_off0[p]; o1 = p_off1[p]; }
       {
         float *row = s_tile + o0 + (le * np + slot) * Q.A0;
         float c = row[0];
@@ -383,6 +516,70 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
         const float2 *kp = skey + le * N;
         uint32_t r0, r1, r2, r3, r4, r5, r6, r7, r8, r9, r10, r11, r12, r13, r14, r15;
         const uint32_t pad_key = 0x7f800000u | idmask;
+        bool have = false;          // candidate list already complete (history path)
+        float m_out = CUDART_INF_F; // smallest squared distance NOT in the candidate list
+        int n_have = min(nv, kListLen - 1);
+        if (P.use_history) {
+          // ---- temporal-coherence path.  Threshold tau = the largest current squared
+          // distance to last step's neighbours (any tau is safe: the result is accepted
+          // only if it provably contains the K nearest, see `hist_ok`).  One pass over
+          // the candidates collects everything with s <= tau (typically K + a few) into a
+          // per-lane byte list and tracks the minimum of the rest; no sorting network runs
+          // over the 100+ candidates.
+          const int *pn = P.nearest + (long long)gi * K;
+          float tau = 0.0f;
+          int seen = 0;
+          for (int p = 0; p < K; p++) {
+            int b = pn[p];
+            b = min(max(b, 0), N - 1);
+            if (b != a && ealive[b]) {
+              const float2 pb = epos[b];
+              const float dx = pa.x - pb.x, dy = pa.y - pb.y;
+              tau = fmaxf(tau, dx * dx + dy * dy);
+              seen++;
+            }
+          }
+          // neighbours that left the game shrink the list: widen the disc accordingly
+          if (seen < kk) tau *= 1.0f + 0.45f * (float)(kk - seen);
+          if (seen == 0) tau = -1.0f;
+          unsigned char *lst = s_scr + (size_t)warp * P.scr_warp_bytes + lane;
+          int cnt = 0;
+#pragma unroll 4
+          for (int b = 0; b < N; b++) {
+            const float2 pb = kp[b];
+            const float dx = pa.x - pb.x, dy = pa.y - pb.y;
+            const float sq = dx * dx + dy * dy;
+            if (sq <= tau) {
+              lst[min(cnt, kListLen) * kWarp] = (unsigned char)b;
+              cnt++;
+            } else {
+              m_out = fminf(m_out, sq);
+            }
+          }
+          const bool hist_ok = (cnt >= kk + 1) && (cnt <= kListLen);   // self + >= kk others
+          if (hist_ok) {
+#define WDB_HKEY(i)                                                                 \
+  uint32_t c##i = pad_key;                                                          \
+  if (i < cnt) {                                                                    \
+    const int b = lst[i * kWarp];                                                   \
+    const float2 pb = kp[b];                                                        \
+    const float dx = pa.x - pb.x, dy = pa.y - pb.y;                                 \
+    c##i = (__float_as_uint(dx * dx + dy * dy) & ~idmask) | (uint32_t)b;            \
+  }
+#define WDB_HCOPY(i) r##i = c##i;
+            WDB_REP16(WDB_HKEY)
+            WDB_SORT16(c)
+            WDB_REP16(WDB_HCOPY)
+#undef WDB_HKEY
+#undef WDB_HCOPY
+            have = true;
+            n_have = cnt - 1;
+          } else {
+            m_out = CUDART_INF_F;
+            if (P.stats) atomicAdd(&P.stats[2], 1);
+          }
+        }
+        if (!have) {
 #define WDB_KEY(i)                                                                  \
   uint32_t c##i = pad_key;                                                          \
   if (base + i < N) {                                                               \
@@ -410,6 +607,7 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
         }
 #undef WDB_KEY
 #undef WDB_COPY
+        }   // !have
         R[0] = r0; R[1] = r1; R[2] = r2; R[3] = r3; R[4] = r4; R[5] = r5; R[6] = r6;
         R[7] = r7; R[8] = r8; R[9] = r9; R[10] = r10; R[11] = r11; R[12] = r12;
         R[13] = r13; R[14] = r14; R[15] = r15;
@@ -422,7 +620,7 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
         // increasing with relative gaps > 2^-19 (so neither the float rounding of
         // dx*dx+dy*dy nor the reference's float(sqrt(double)) can reorder or tie them)
         // and floor_out clears the K-th winner by the same margin.
-        const int m = min(nv, K + 1);
+        const int m = min(n_have, K + 1);
         if ((int)(R[0] & idmask) != a) suspect = true;     // a co-located agent sorted first
         float es[kListLen];
         bool misordered = false;
@@ -466,34 +664,42 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
               prev = es[i];
             }
           }
-          // candidates outside the K+1 winners (exist iff nv > K + 1)
-          if (nv > K + 1) {
+          // everything NOT examined above: list entries behind the K+1 winners are
+          // >= floor_out (truncated key of winner K+1), candidates outside the list are
+          // >= m_out (history path) or >= floor_out (network path, only if nv > 15)
+          float rest = m_out;
+          if (n_have > K + 1 || (!have && nv > kListLen - 1)) rest = fminf(rest, floor_out);
+          if (rest < CUDART_INF_F && m >= K) {
             float xk = 0.0f;
 #pragma unroll
             for (int i = 1; i < kListLen; i++) xk = (i == K) ? es[i] : xk;
-            if (!(floor_out - xk > floor_out * 1.9073486328125e-06f)) suspect = true;
+            if (!(rest - xk > rest * 1.9073486328125e-06f)) suspect = true;
           }
         }
       } else {
         suspect = true;
       }
     }
-    // exact path, one lane of the warp at a time on the warp's private scratch
+    // exact path: the warp resolves its suspect agents one at a time, cooperatively
     unsigned todo = __ballot_sync(0xffffffffu, suspect);
     while (todo) {
       const int Lx = __ffs(todo) - 1;
       todo &= todo - 1;
+      const int ax = __shfl_sync(0xffffffffu, a, Lx);
+      const int lex = __shfl_sync(0xffffffffu, le, Lx);
+      const int gix = __shfl_sync(0xffffffffu, gi, Lx);
+      float *d;
+      int *ids;
+      if (P.scratch_in_smem) {
+        d = reinterpret_cast<float *>(s_scr + (size_t)warp * P.scr_warp_bytes);
+        ids = reinterpret_cast<int *>(d + N);
+      } else {
+        d = P.g_nd + (long long)gix * (N - 1);
+        ids = P.g_nid + (long long)gix * (N - 1);
+      }
+      const int kx = exact_select_warp(spos + lex * N, salive + lex * N, N, ax, K, d, ids, lane);
       if (lane == Lx) {
-        float *d;
-        int *ids;
-        if (P.scratch_in_smem) {
-          d = s_scr_d + warp * N;
-          ids = s_scr_i + warp * N;
-        } else {
-          d = P.g_nd + (long long)gi * (N - 1);
-          ids = P.g_nid + (long long)gi * (N - 1);
-        }
-        kk = exact_select(epos, ealive, N, a, K, d, ids);
+        kk = kx;
         if (net_ok) {
 #pragma unroll
           for (int i = 1; i < kListLen; i++)
@@ -608,7 +814,44 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
       }
     }
   }
+  // make the tile (written through the generic proxy) visible to the TMA engine
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();   // obs tile complete; srew initialised; tagger list ready
+
+  // observation copy-out, part 1: every block of the tile whose shared / global addresses
+  // and size are 16-byte aligned leaves through the TMA (cp.async.bulk), issued by one
+  // thread now so that it overlaps the reward phase; the rest is copied by the threads at
+  // the end of the kernel.
+  uint32_t out_mask = 0;   // bit p: policy block p went by TMA;  bit 8: the [E,N,F] array
+  if (!P.use_full_obs && P.stage_obs) {
+    if (!FUSED) {
+      if (tma_ok(P.obs + (long long)env0 * N * F, smem_u32(s_tile), 4ull * envs_here * N * F))
+        out_mask |= 1u << 8;
+    } else {
+#pragma unroll
+      for (int p = 0; p < kMaxPolicies; p++) {
+        if (p < Q.n_policies && Q.obs_next[p]) {
+          const int np = Q.policy_size[p];
+          if (tma_ok(Q.obs_next[p] + (long long)env0 * np * F, smem_u32(s_tile + tile_base[p]),
+                     4ull * envs_here * np * F))
+            out_mask |= 1u << p;
+        }
+      }
+    }
+    if (tid == 0 && out_mask) {
+      if (out_mask & (1u << 8))
+        tma_store_1d(P.obs + (long long)env0 * N * F, smem_u32(s_tile), 4u * envs_here * N * F);
+#pragma unroll
+      for (int p = 0; p < kMaxPolicies; p++) {
+        if (FUSED && (out_mask & (1u << p))) {
+          const int np = Q.policy_size[p];
+          tma_store_1d(Q.obs_next[p] + (long long)env0 * np * F,
+                       smem_u32(s_tile + tile_base[p]), 4u * envs_here * np * F);
+        }
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
 
   // ------------------------------------------------------------------ rewards / tags
   float r = active ? srew[li] : 0.0f;
@@ -706,13 +949,15 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
   if (!P.use_full_obs && P.stage_obs) {
     // coalesced copy-out of the observation tile
     if (!FUSED) {
-      const int total = envs_here * N * F;
-      float *dst = P.obs + (long long)env0 * N * F;
-      for (int i = tid; i < total; i += blockDim.x) dst[i] = s_tile[i];
+      if (!(out_mask & (1u << 8))) {
+        const int total = envs_here * N * F;
+        float *dst = P.obs + (long long)env0 * N * F;
+        for (int i = tid; i < total; i += blockDim.x) dst[i] = s_tile[i];
+      }
     } else {
 #pragma unroll
       for (int p = 0; p < kMaxPolicies; p++) {
-        if (p < Q.n_policies && Q.obs_next[p]) {
+        if (p < Q.n_policies && Q.obs_next[p] && !(out_mask & (1u << p))) {
           // the tile block of policy p IS the [envs, Np, F] layout of obs_next[p]
           const int np = Q.policy_size[p];
           const int total = envs_here * np * F;
@@ -733,6 +978,10 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
       }
     }
   }
+
+  // the TMA stores must have read the tile (and, before the reset below overwrites the same
+  // global rows for finished envs, must have completed) before the CTA goes on / exits
+  if (tid == 0 && out_mask) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 
   if (FUSED && Q.do_reset) {
     // done-masked reset of this CTA's envs (core/reset.cu:9-75 for every registered array
@@ -767,6 +1016,8 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
   }
 }
 
+int g_tc_history = 1;   // wdb_set_option("tc_history", 0/1)
+
 struct LaunchPlan {
   int epb, block, grid;
   size_t smem;
@@ -780,8 +1031,14 @@ int plan_launch(TcParams &P, const FusedParams *Q, bool have_gscratch, LaunchPla
   const int block = round_up(epb * N, 32);
   const int nwarps = block / 32;
   const int F = 7 * K + 1;
-  const size_t base = sizeof(float) * 9ull * epb * N + sizeof(int) * (4ull * N + 4ull * epb + 4);
-  const size_t scr = 8ull * nwarps * N;
+  const size_t base = tc_small_bytes(epb, N);
+  // per-warp scratch: exact-path lists (8 B per agent) and/or the history byte list
+  P.use_history = (g_tc_history && !P.use_full_obs && N <= 256 && K + 2 <= kListLen) ? 1 : 0;
+  size_t warp_bytes = 8ull * N;
+  const size_t hist_bytes = (size_t)(kListLen + 1) * kWarp;
+  if (P.use_history && hist_bytes > warp_bytes) warp_bytes = hist_bytes;
+  warp_bytes = (warp_bytes + 15) & ~(size_t)15;
+  const size_t scr = warp_bytes * nwarps;
   size_t tile_obs = P.use_full_obs ? 0 : sizeof(float) * (size_t)epb * N * F;
   size_t tile_probs = 0;
   if (Q) {
@@ -791,7 +1048,11 @@ int plan_launch(TcParams &P, const FusedParams *Q, bool have_gscratch, LaunchPla
   const size_t kMaxSmem = 200 * 1024;
   P.scratch_in_smem = (base + scr <= 64 * 1024) || !have_gscratch;
   if (P.scratch_in_smem && base + scr > kMaxSmem) return (int)cudaErrorInvalidValue;
-  size_t smem = base + (P.scratch_in_smem ? scr : 0);
+  if (!P.scratch_in_smem) {
+    warp_bytes = P.use_history ? ((hist_bytes + 15) & ~(size_t)15) : 0;
+  }
+  P.scr_warp_bytes = (int)warp_bytes;
+  size_t smem = base + warp_bytes * nwarps;
   P.stage_obs = !P.use_full_obs && (smem + tile_obs <= 110 * 1024);
   size_t tile = P.stage_obs ? tile_obs : 0;
   if (tile_probs > tile) tile = tile_probs;
@@ -807,6 +1068,7 @@ int plan_launch(TcParams &P, const FusedParams *Q, bool have_gscratch, LaunchPla
     // observation is written -> per-agent global scratch
     if (!have_gscratch) return (int)cudaErrorInvalidValue;
     P.scratch_in_smem = 0;
+    P.scr_warp_bytes = 0;
     smem = base + tile;
   }
   plan.epb = epb;
@@ -875,6 +1137,16 @@ int fill_params(TcParams &P, int n_envs, int n_agents, float *loc_x, float *loc_
 }
 
 }  // namespace
+
+WDB_API int wdb_set_option(const char *name, int value) {
+  if (!name) return (int)cudaErrorInvalidValue;
+  const char *want = "tc_history";
+  int i = 0;
+  for (; want[i] && name[i] == want[i]; i++) {}
+  if (want[i] || name[i]) return (int)cudaErrorInvalidValue;
+  g_tc_history = value ? 1 : 0;
+  return 0;
+}
 
 WDB_API int wdb_tag_continuous_step(
     void *stream, int n_envs, int n_agents, int blocks_per_env, float *loc_x,

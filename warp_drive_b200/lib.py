@@ -77,6 +77,7 @@ _SIGNATURES = {
     "wdb_abi_version": (_i, []),
     "wdb_error_string": (ctypes.c_char_p, [_i]),
     "wdb_launch_count": (_ll, []),
+    "wdb_set_option": (_i, [ctypes.c_char_p, _i]),
     "wdb_rng_state_bytes": (_ll, [_ll]),
     "wdb_rng_init": (_i, [_vp, _vp, _ll, _ull]),
     "wdb_rng_draw_u32x4": (_i, [_vp, _vp, _vp, _ll]),
