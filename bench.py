@@ -320,6 +320,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=2000, help="env replicas per GPU")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--forward-precision", default="tf32", choices=["fp32", "tf32", "bf16"],
+                    help="precision of the policy/value MLP GEMMs (the env path is fp32)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -343,8 +345,12 @@ def main():
     W = max(3, args.warmup)
     # the rollout is captured as CUDA graphs of T timesteps; T divides K
     T = max(d for d in range(1, min(K, 50) + 1) if K % d == 0)
+    if args.forward_precision == "tf32":
+        torch.backends.cuda.matmul.allow_tf32 = True
+        torch.backends.cudnn.allow_tf32 = True
     wrapper, engine, sampler, policy_map = build_engine(
-        args.envs, seed=1234 + rank, graph_steps=T, use_graph=not args.no_graph)
+        args.envs, seed=1234 + rank, graph_steps=T, use_graph=not args.no_graph,
+        forward_dtype=torch.bfloat16 if args.forward_precision == "bf16" else None)
     E, N = wrapper.n_envs, wrapper.n_agents
 
     def barrier():
@@ -417,6 +423,7 @@ def main():
                                "discrete 21x21 actions, K=10 partial obs, 2 policies "
                                "fully_connected [256,256], rollout step = forward + sample "
                                "+ step + reset + push-to-batch",
+                   "policy_forward": f"torch/cuBLAS {args.forward_precision} GEMMs (library)",
                    "envs_per_gpu": E, "agents": N, "graph_steps": T,
                    "cuda_graph": not args.no_graph,
                    "l2": "working set per step (~110 MB obs+probs+batch slots, batch slot "
@@ -429,6 +436,7 @@ def main():
                         "observations/rewards/done out every step"},
         "gpu_launches": int(my_launches),
         "kernel_stats": {"exact_tie_path_agents": stats_timed[0], "tags": stats_timed[1],
+                         "history_path_fallbacks": stats_timed[2],
                          "agent_steps": E * N * K,
                          "note": "device counters of the fused kernel over the timed region: "
                                  "agents that needed the exact tie-resolution path"},

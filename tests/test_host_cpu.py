@@ -239,3 +239,70 @@ def test_spaces_and_registrar():
     assert reg.get("TagGridWorld", "cpu") is TagGridWorld
     assert reg.get("taggridworld", "numba") is CUDATagGridWorld
     assert reg.has_env("TagGridWorld", "pycuda") and not reg.has_env("Nope")
+
+
+# ------------------------------------------------------------------ update-path math
+def test_a2c_ppo_losses_follow_the_reference_formulas():
+    """compute_loss_and_metrics on host tensors vs a literal transcription of the
+    reference's formulas (a2c.py:80-130, ppo.py:127-136) for one small batch."""
+    import torch
+    from torch.distributions import Categorical
+
+    from warp_drive_b200.training.algorithms.policygradient import A2C, PPO, discounted_returns
+
+    g = torch.Generator().manual_seed(1)
+    T, E, Np, A = 6, 3, 4, 5
+    rewards = torch.randn(T, E, Np, generator=g)
+    done = (torch.rand(T, E, generator=g) < 0.25).int()
+    done[2, 1] = 1
+    values = torch.randn(T, E, Np, generator=g, requires_grad=True)
+    logits = [torch.randn(T, E, Np, A, generator=g, requires_grad=True) for _ in range(2)]
+    probs = [torch.softmax(l, -1) for l in logits]
+    actions = torch.randint(0, A, (T, E, Np, 2), generator=g)
+    gamma = 0.9
+    # literal reference recursion
+    ret = torch.zeros_like(rewards)
+    d = done.float()
+    ret[-1] = d[-1][:, None] * rewards[-1] + (1 - d[-1][:, None]) * values.detach()[-1]
+    for step in range(-2, -T - 1, -1):
+        ret[step] = rewards[step] + (1 - d[step][:, None]) * gamma * ret[step + 1]
+    assert torch.allclose(discounted_returns(rewards, done, values.detach(), gamma), ret)
+    adv = ret - values.detach()
+    logp = sum(Categorical(p).log_prob(actions[..., k]) for k, p in enumerate(probs))
+    ent = sum(Categorical(p).entropy().mean() for p in probs)
+    vf = torch.nn.MSELoss()(ret, values)
+    want_a2c = (-logp * adv).mean() + 0.5 * vf - 0.05 * ent
+    algo = A2C(discount_factor_gamma=gamma, vf_loss_coeff=0.5, entropy_coeff=0.05)
+    loss, metrics = algo.compute_loss_and_metrics(10, actions, rewards, done, probs, values,
+                                                  perform_logging=True)
+    assert torch.allclose(loss, want_a2c, atol=1e-6)
+    assert abs(metrics["Value function loss"] - vf.item()) < 1e-6
+    loss.backward()
+    assert values.grad is not None and logits[0].grad.abs().sum() > 0
+    ratio = torch.exp(logp - logp.detach())
+    surr = torch.minimum(ratio * adv, torch.clamp(ratio, 0.9, 1.1) * adv)
+    want_ppo = -surr.mean() + 0.5 * vf - 0.05 * ent
+    ppo = PPO(clip_param=0.1, discount_factor_gamma=gamma, vf_loss_coeff=0.5, entropy_coeff=0.05)
+    loss2, _ = ppo.compute_loss_and_metrics(10, actions, rewards, done, probs, values)
+    assert torch.allclose(loss2, want_ppo, atol=1e-6)
+    # normalisation switches
+    n = A2C(discount_factor_gamma=gamma, normalize_advantage=True, normalize_return=True)
+    l3, _ = n.compute_loss_and_metrics(0, actions, rewards, done, probs, values)
+    assert torch.isfinite(l3)
+
+
+def test_param_scheduler_and_config_merge():
+    from warp_drive_b200.training.trainer import load_run_config, recursive_merge_config_dicts
+    from warp_drive_b200.training.utils.param_scheduler import ParamScheduler
+
+    assert ParamScheduler(0.3).get_param_value(123) == 0.3
+    s = ParamScheduler([[1000, 0.1], [2000, 0.05]])
+    assert s.get_param_value(0) == 0.1 and s.get_param_value(5000) == 0.05
+    assert abs(s.get_param_value(1500) - 0.075) < 1e-12
+    cfg = load_run_config("tag_continuous")
+    assert cfg["env"]["num_runners"] == 100 and cfg["policy"]["runner"]["lr"] == 0.005
+    default = load_run_config("default_configs")
+    merged = recursive_merge_config_dicts({"num_envs": 7}, default["trainer"])
+    assert merged["num_envs"] == 7 and merged["train_batch_size"] == 10000
+    for name in ("tag_gridworld", "single_cartpole"):
+        assert load_run_config(name)["name"] == name

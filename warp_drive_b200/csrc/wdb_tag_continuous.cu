@@ -56,6 +56,7 @@ __constant__ float kEpsilon = 1.0e-10;
 
 constexpr int kMaxPolicies = 4;
 constexpr int kListLen = 16;   // sorted candidate list kept per agent (self + K+1 <= 16)
+constexpr int kHistCap = 32;   // history path: candidates one lane may collect
 
 struct TcParams {
   int n_envs, N, epb, K, episode_length;
@@ -519,6 +520,7 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
         bool have = false;          // candidate list already complete (history path)
         float m_out = CUDART_INF_F; // smallest squared distance NOT in the candidate list
         int n_have = min(nv, kListLen - 1);
+        int n_cand = nv;            // candidates >= everything the sorted list stands for
         if (P.use_history) {
           // ---- temporal-coherence path.  Threshold tau = the largest current squared
           // distance to last step's neighbours (any tau is safe: the result is accepted
@@ -550,30 +552,45 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
             const float dx = pa.x - pb.x, dy = pa.y - pb.y;
             const float sq = dx * dx + dy * dy;
             if (sq <= tau) {
-              lst[min(cnt, kListLen) * kWarp] = (unsigned char)b;
+              lst[min(cnt, kHistCap) * kWarp] = (unsigned char)b;
               cnt++;
             } else {
               m_out = fminf(m_out, sq);
             }
           }
-          const bool hist_ok = (cnt >= kk + 1) && (cnt <= kListLen);   // self + >= kk others
+          const bool hist_ok = (cnt >= kk + 1) && (cnt <= kHistCap);   // self + >= kk others
           if (hist_ok) {
 #define WDB_HKEY(i)                                                                 \
   uint32_t c##i = pad_key;                                                          \
-  if (i < cnt) {                                                                    \
-    const int b = lst[i * kWarp];                                                   \
+  if (hbase + i < cnt) {                                                            \
+    const int b = lst[(hbase + i) * kWarp];                                         \
     const float2 pb = kp[b];                                                        \
     const float dx = pa.x - pb.x, dy = pa.y - pb.y;                                 \
     c##i = (__float_as_uint(dx * dx + dy * dy) & ~idmask) | (uint32_t)b;            \
   }
 #define WDB_HCOPY(i) r##i = c##i;
-            WDB_REP16(WDB_HKEY)
-            WDB_SORT16(c)
-            WDB_REP16(WDB_HCOPY)
+            {
+              const int hbase = 0;
+              WDB_REP16(WDB_HKEY)
+              WDB_SORT16(c)
+              WDB_REP16(WDB_HCOPY)
+            }
+            if (cnt > kListLen) {
+              // 17..32 candidates: sort the second half and merge, keeping the 16 smallest
+              const int hbase = kListLen;
+              WDB_REP16(WDB_HKEY)
+              WDB_SORT16(c)
+              r0 = min(r0, c15); r1 = min(r1, c14); r2 = min(r2, c13); r3 = min(r3, c12);
+              r4 = min(r4, c11); r5 = min(r5, c10); r6 = min(r6, c9); r7 = min(r7, c8);
+              r8 = min(r8, c7); r9 = min(r9, c6); r10 = min(r10, c5); r11 = min(r11, c4);
+              r12 = min(r12, c3); r13 = min(r13, c2); r14 = min(r14, c1); r15 = min(r15, c0);
+              WDB_BITONIC_MERGE16(r)
+            }
 #undef WDB_HKEY
 #undef WDB_HCOPY
             have = true;
-            n_have = cnt - 1;
+            n_have = min(cnt - 1, kListLen - 1);
+            n_cand = cnt - 1;
           } else {
             m_out = CUDART_INF_F;
             if (P.stats) atomicAdd(&P.stats[2], 1);
@@ -667,8 +684,9 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
           // everything NOT examined above: list entries behind the K+1 winners are
           // >= floor_out (truncated key of winner K+1), candidates outside the list are
           // >= m_out (history path) or >= floor_out (network path, only if nv > 15)
+          // (n_cand = others in the candidate list: all alive others on the network path)
           float rest = m_out;
-          if (n_have > K + 1 || (!have && nv > kListLen - 1)) rest = fminf(rest, floor_out);
+          if (n_cand > K + 1) rest = fminf(rest, floor_out);
           if (rest < CUDART_INF_F && m >= K) {
             float xk = 0.0f;
 #pragma unroll
@@ -1035,7 +1053,7 @@ int plan_launch(TcParams &P, const FusedParams *Q, bool have_gscratch, LaunchPla
   // per-warp scratch: exact-path lists (8 B per agent) and/or the history byte list
   P.use_history = (g_tc_history && !P.use_full_obs && N <= 256 && K + 2 <= kListLen) ? 1 : 0;
   size_t warp_bytes = 8ull * N;
-  const size_t hist_bytes = (size_t)(kListLen + 1) * kWarp;
+  const size_t hist_bytes = (size_t)(kHistCap + 1) * kWarp;
   if (P.use_history && hist_bytes > warp_bytes) warp_bytes = hist_bytes;
   warp_bytes = (warp_bytes + 15) & ~(size_t)15;
   const size_t scr = warp_bytes * nwarps;
