@@ -220,6 +220,24 @@ int wdb_cartpole_step(void *stream, int n_envs, float *state, const int *action,
                       float theta_threshold_radians, float x_threshold,
                       int *env_timestep, int episode_length);
 
+/* ------------------------------------------------------------- policy forward ---- */
+/* Fused policy/value MLP forward on the tensor cores (tcgen05 + TMEM), replacing the
+ * rollout-time FullyConnected.forward (warp_drive/training/models/fully_connected.py:51-89):
+ *   obs [rows, F] -> Linear(F,H)+ReLU -> Linear(H,H)+ReLU -> softmax(Linear(H,A0)),
+ *   softmax(Linear(H,A1)), Linear(H,1).
+ * Weights are nn.Linear tensors ([out, in] fp32); wdb_mlp_pack_weights converts them to bf16
+ * tiles inside a caller-owned blob of wdb_mlp_blob_bytes() bytes (re-pack after every
+ * optimizer step).  H must be a multiple of 32 <= 256, A0 + A1 + 1 <= 64, F <= 256;
+ * wdb_mlp_blob_bytes returns -1 for unsupported shapes. */
+long long wdb_mlp_blob_bytes(int F, int H, int A0, int A1);
+int wdb_mlp_pack_weights(void *stream, void *blob, const float *w1, const float *b1,
+                         const float *w2, const float *b2, const float *wh0, const float *bh0,
+                         const float *wh1, const float *bh1, const float *wv, const float *bv,
+                         int F, int H, int A0, int A1);
+int wdb_mlp_policy_forward(void *stream, const void *blob, int F, int H, int A0, int A1,
+                           const float *obs, long long rows, float *probs0, float *probs1,
+                           float *values /* may be NULL */);
+
 /* ------------------------------------------------------------------ update ---- */
 /* Bootstrapped discounted returns of the A2C/PPO update, backwards in time with done
  * masking (warp_drive/training/algorithms/policygradient/a2c.py:80-93):

@@ -1,0 +1,61 @@
+"""GPU test of the fused tcgen05 policy forward against the float32 torch module.
+bf16 operands / fp32 accumulation: probabilities agree to 2e-2 absolute (typically 3e-3),
+rows sum to 1, values to 5e-2 relative-ish."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+class _Model(torch.nn.Module):
+    """Minimal stand-in with the attribute names FusedPolicyForward reads."""
+
+    def __init__(self, F, H, A0, A1):
+        super().__init__()
+        self.flattened_obs_size, self.fc_dims, self.output_dims = F, [H, H], [A0, A1]
+        self.is_deterministic = False
+        self.fc = torch.nn.ModuleDict({
+            "0": torch.nn.Sequential(torch.nn.Linear(F, H), torch.nn.ReLU()),
+            "1": torch.nn.Sequential(torch.nn.Linear(H, H), torch.nn.ReLU())})
+        self.policy_head = torch.nn.ModuleList([torch.nn.Linear(H, A0), torch.nn.Linear(H, A1)])
+        self.vf_head = torch.nn.Linear(H, 1)
+
+    def forward(self, x):
+        x = self.fc["1"](self.fc["0"](x))
+        return [torch.softmax(h(x), -1) for h in self.policy_head], self.vf_head(x)[..., 0]
+
+
+@pytest.mark.parametrize("F,H,A0,A1,rows", [(71, 256, 21, 21, 128), (71, 256, 21, 21, 2000 * 100),
+                                            (71, 256, 21, 21, 10000), (36, 64, 21, 21, 333),
+                                            (15, 32, 4, 4, 77), (200, 128, 30, 10, 5000)])
+def test_fused_mlp_matches_torch(F, H, A0, A1, rows):
+    from warp_drive_b200.training.models.fused_forward import FusedPolicyForward
+
+    torch.manual_seed(F * 1000 + H)
+    model = _Model(F, H, A0, A1).cuda()
+    for p in model.parameters():          # larger weights than default init: sharper softmax
+        p.data.mul_(2.0)
+    assert FusedPolicyForward.supported(model)
+    fwd = FusedPolicyForward(model)
+    obs = torch.randn(rows, F, device="cuda")
+    p0 = torch.full((rows, A0), -1.0, device="cuda")
+    p1 = torch.full((rows, A1), -1.0, device="cuda")
+    v = torch.full((rows,), -1.0, device="cuda")
+    fwd(obs, p0, p1, v)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        (q0, q1), qv = model(obs)
+    assert torch.isfinite(p0).all() and torch.isfinite(p1).all()
+    assert (p0.sum(-1) - 1).abs().max() < 1e-4 and (p1.sum(-1) - 1).abs().max() < 1e-4
+    e0, e1 = (p0 - q0).abs().max().item(), (p1 - q1).abs().max().item()
+    ev = ((v - qv).abs() / (1 + qv.abs())).max().item()
+    assert e0 < 2e-2 and e1 < 2e-2 and ev < 5e-2, (e0, e1, ev)
+    # refresh() picks up new parameters
+    with torch.no_grad():
+        model.policy_head[0].bias.add_(3.0 * torch.arange(A0, device="cuda") / A0)
+    fwd.refresh()
+    fwd(obs, p0, p1, None)
+    with torch.no_grad():
+        (q0, _), _ = model(obs)
+    assert (p0 - q0).abs().max().item() < 2e-2

@@ -1,0 +1,480 @@
+// wdb_mlp.cu -- fused policy/value MLP forward on the 5th-gen tensor cores (tcgen05 + TMEM).
+//
+// Replaces, for the rollout path, FullyConnected.forward of the reference
+// (warp_drive/training/models/fully_connected.py:51-89): obs -> Linear+ReLU -> Linear+ReLU ->
+// {head0 softmax, head1 softmax, value}.  The reference (and the torch fallback) runs it as
+// 5 GEMMs + 7 elementwise kernels that round-trip the [rows, 256] activations through HBM;
+// here one persistent kernel keeps them on chip:
+//
+//   * all weights (bf16, pre-packed by wdb_mlp_pack_weights into the UMMA canonical K-major
+//     no-swizzle layout) are TMA-bulk-loaded into shared memory ONCE per CTA (192 KB);
+//   * per 128-row tile: obs (fp32, unit-stride loads) -> bf16 A tile in shared memory;
+//     layer 1 = tcgen05.mma (A from smem) into TMEM; epilogue (tcgen05.ld, +bias, ReLU,
+//     bf16 pack) writes the hidden activations BACK INTO TMEM (tcgen05.st); layers 2 and 3
+//     take their A operand straight from TMEM (tcgen05.mma .ts form) -- hidden activations
+//     never touch shared or global memory; final epilogue = bias + two softmaxes + value,
+//     staged in shared memory and written with TMA bulk stores.
+//   * one elected thread issues the MMAs; completion is signalled through an mbarrier
+//     (tcgen05.commit), 4 warps = 128 TMEM lanes = 128 rows run the epilogues.
+//
+// Numerics: bf16 operands, fp32 accumulation (the reference is fp32; SURVEY.md section 8
+// row a3 allows TF32/BF16 for the forward that feeds the sampler).  Tested against a
+// float32 torch reference in tests/test_gpu_mlp.py (probabilities within 2e-2 abs, sums to 1).
+#include <cuda_bf16.h>
+#include <math_constants.h>
+
+#include "wdb_common.cuh"
+
+using namespace wdb;
+
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kThreads = 128;
+constexpr int kTmemCols = 512;
+constexpr int kColD = 0;      // accumulator columns [0, 256)
+constexpr int kColH = 256;    // packed bf16 hidden activations [256, 384)
+
+struct MlpHeader {            // start of the packed weight blob (device memory)
+  int F, K1, H, A0, A1, N3;   // input features, padded K of layer 1, hidden width, heads, padded N3
+  int off_w1, off_w2, off_w3, off_b, total_bytes, pad;
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// UMMA shared-memory descriptor, K-major, no swizzle ("interleaved" 8x16B core matrices):
+// element (r, k) of a [rows, K] bf16 tile lives at
+//   (r / 8) * SBO + (k / 8) * 128 + (r % 8) * 16 + (k % 8) * 2     [LBO = 128]
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((128u >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;     // descriptor version (sm_100)
+  return d;                   // layout_type = 0 (SWIZZLE_NONE), base_offset = 0
+}
+
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4)            // D format  = F32
+         | (1u << 7)          // A format  = BF16
+         | (1u << 10)         // B format  = BF16
+         | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);   // K-major A and B
+}
+
+__device__ __forceinline__ void mma_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                       uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc,
+                                       uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+               ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; "
+        "selp.u32 %0, 1, 0, p; }"
+        : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load(uint32_t dst, const void *src, uint32_t bytes,
+                                         uint32_t mbar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void tma_store(void *dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+
+// 32 consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
+        "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]),
+        "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),
+        "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]),
+        "r"(v[14]), "r"(v[15]) : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t *>(&h);
+}
+
+// hidden epilogue: D[lane, 0..H) (+bias, ReLU) -> packed bf16 into TMEM columns kColH..
+__device__ __forceinline__ void hidden_epilogue(uint32_t tmem_lane_base, const float *bias,
+                                                int H) {
+  for (int c = 0; c < H; c += 32) {
+    uint32_t v[32];
+    tmem_ld32(tmem_lane_base + kColD + c, v);
+    uint32_t out[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      const float a = fmaxf(__uint_as_float(v[2 * i]) + bias[c + 2 * i], 0.0f);
+      const float b = fmaxf(__uint_as_float(v[2 * i + 1]) + bias[c + 2 * i + 1], 0.0f);
+      out[i] = pack_bf16(a, b);
+    }
+    tmem_st16(tmem_lane_base + kColH + c / 2, out);
+  }
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+mlp_forward_kernel(const unsigned char *__restrict__ blob, const float *__restrict__ obs,
+                   long long rows, float *__restrict__ probs0, float *__restrict__ probs1,
+                   float *__restrict__ values) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const MlpHeader hd = *reinterpret_cast<const MlpHeader *>(blob);
+  const int F = hd.F, K1 = hd.K1, H = hd.H, A0 = hd.A0, A1 = hd.A1, N3 = hd.N3;
+  const int w_bytes = hd.total_bytes - hd.off_w1;        // W1 | W2 | W3 | biases, contiguous
+  unsigned char *s_w = smem;                             // packed weights + biases
+  const __nv_bfloat16 *s_w1 = reinterpret_cast<const __nv_bfloat16 *>(s_w);
+  const unsigned char *s_w2 = s_w + (hd.off_w2 - hd.off_w1);
+  const unsigned char *s_w3 = s_w + (hd.off_w3 - hd.off_w1);
+  const float *s_b1 = reinterpret_cast<const float *>(s_w + (hd.off_b - hd.off_w1));
+  const float *s_b2 = s_b1 + H;
+  const float *s_b3 = s_b2 + H;
+  unsigned char *s_a = s_w + ((w_bytes + 127) & ~127);   // A tile (layer 1) / output staging
+  const int a_bytes = max(kTileM * K1 * 2, kTileM * (A0 + A1 + 1) * 4);
+  unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(s_a + ((a_bytes + 15) & ~15));
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 2);
+  (void)s_w1;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t bar_w = smem_addr(&s_bar[0]);           // weights landed
+  const uint32_t bar_mma = smem_addr(&s_bar[1]);         // MMA group done
+
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar_mma, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_addr(s_tmem)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  const uint32_t tmem_lane = tmem_base + ((uint32_t)(warp * 32) << 16);   // this warp's lanes
+
+  if (tid == 0) {                                         // weights: one TMA bulk copy
+    mbar_expect_tx(bar_w, (uint32_t)w_bytes);
+    uint32_t off = 0;
+    while (off < (uint32_t)w_bytes) {                     // <= 64 KB per bulk copy is plenty safe
+      const uint32_t n = min((uint32_t)w_bytes - off, 65536u);
+      tma_load(smem_addr(s_w + off), blob + hd.off_w1 + off, n, bar_w);
+      off += n;
+    }
+  }
+  mbar_wait(bar_w, 0);
+
+  const uint32_t idesc_h = make_idesc(kTileM, H);
+  const uint32_t idesc_o = make_idesc(kTileM, N3);
+  const uint32_t sbo_a = (uint32_t)(K1 / 8) * 128u;       // A tile / W1: K1/8 core matrices per row group
+  const uint32_t sbo_h = (uint32_t)(H / 8) * 128u;        // W2 / W3: H/8 core matrices per row group
+  uint32_t mma_phase = 0;
+  const long long n_tiles = (rows + kTileM - 1) / kTileM;
+  float *s_p0 = reinterpret_cast<float *>(s_a);
+  float *s_p1 = s_p0 + kTileM * A0;
+  float *s_v = s_p1 + kTileM * A1;
+
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long r0 = tile * kTileM;
+    const int valid = (int)min((long long)kTileM, rows - r0);
+
+    // ---- obs tile -> bf16, canonical K-major layout (unit-stride global loads)
+    {
+      // zero the K padding and (for a partial tile) the missing rows
+      uint4 *z = reinterpret_cast<uint4 *>(s_a);
+      for (int i = tid; i < kTileM * K1 * 2 / 16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
+      __syncthreads();
+      const float *src = obs + r0 * F;
+      const int total = valid * F;
+      int r = tid / F, k = tid - (tid / F) * F;            // element (r, k) of index tid
+      const int dr = kThreads / F, dk = kThreads - dr * F; // += kThreads in (r, k) form
+      __nv_bfloat16 *a16 = reinterpret_cast<__nv_bfloat16 *>(s_a);
+      for (int i = tid; i < total; i += kThreads) {
+        const float x = src[i];
+        const int off = (r >> 3) * (int)(sbo_a / 2) + (k >> 3) * 64 + (r & 7) * 8 + (k & 7);
+        a16[off] = __float2bfloat16_rn(x);
+        r += dr; k += dk;
+        if (k >= F) { k -= F; r += 1; }
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+
+    // ---- layer 1: D[128, H] = A[128, K1] * W1^T          (A, B from shared memory)
+    if (tid == 0) {
+      fence_after();
+      const uint32_t a0 = smem_addr(s_a), b0 = smem_addr(s_w);
+      for (int kk = 0; kk < K1 / 16; kk++)
+        mma_ss(tmem_base + kColD, make_desc(a0 + kk * 256, sbo_a), make_desc(b0 + kk * 256, sbo_a),
+               idesc_h, kk > 0);
+      mma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, mma_phase); mma_phase ^= 1;
+    fence_after();
+    hidden_epilogue(tmem_lane, s_b1, H);
+    fence_before();
+    __syncthreads();
+
+    // ---- layer 2: D[128, H] = H1[128, H] * W2^T           (A from TMEM)
+    if (tid == 0) {
+      fence_after();
+      const uint32_t b0 = smem_addr(s_w2);
+      for (int kk = 0; kk < H / 16; kk++)
+        mma_ts(tmem_base + kColD, tmem_base + kColH + kk * 8, make_desc(b0 + kk * 256, sbo_h),
+               idesc_h, kk > 0);
+      mma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, mma_phase); mma_phase ^= 1;
+    fence_after();
+    hidden_epilogue(tmem_lane, s_b2, H);
+    fence_before();
+    __syncthreads();
+
+    // ---- layer 3: D[128, N3] = H2[128, H] * W3^T          (heads + value)
+    if (tid == 0) {
+      fence_after();
+      const uint32_t b0 = smem_addr(s_w3);
+      for (int kk = 0; kk < H / 16; kk++)
+        mma_ts(tmem_base + kColD, tmem_base + kColH + kk * 8, make_desc(b0 + kk * 256, sbo_h),
+               idesc_o, kk > 0);
+      mma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, mma_phase); mma_phase ^= 1;
+    fence_after();
+
+    // ---- output epilogue: bias, softmax per head, value -> staging -> global
+    {
+      float lg[64];
+      for (int c = 0; c < N3; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_lane + kColD + c, v);
+#pragma unroll
+        for (int i = 0; i < 16; i++) lg[c + i] = __uint_as_float(v[i]) + s_b3[c + i];
+      }
+      const int row = tid;                                 // TMEM lane == row of the tile
+      float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F;
+#pragma unroll
+      for (int i = 0; i < 64; i++) {
+        if (i < A0) m0 = fmaxf(m0, lg[i]);
+        else if (i < A0 + A1) m1 = fmaxf(m1, lg[i]);
+      }
+      float z0 = 0.f, z1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 64; i++) {
+        if (i < A0) { lg[i] = expf(lg[i] - m0); z0 += lg[i]; }
+        else if (i < A0 + A1) { lg[i] = expf(lg[i] - m1); z1 += lg[i]; }
+      }
+      const float i0 = 1.0f / z0, i1 = 1.0f / z1;
+#pragma unroll
+      for (int i = 0; i < 64; i++) {
+        if (i < A0) s_p0[row * A0 + i] = lg[i] * i0;
+        else if (i < A0 + A1) s_p1[row * A1 + (i - A0)] = lg[i] * i1;
+        else if (i == A0 + A1) s_v[row] = lg[i];
+      }
+    }
+    fence_before();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    {
+      float *g0 = probs0 + r0 * A0, *g1 = probs1 + r0 * A1;
+      const uint32_t n0 = (uint32_t)valid * A0 * 4, n1 = (uint32_t)valid * A1 * 4;
+      const bool tma_ok = (((uintptr_t)g0 | (uintptr_t)g1 | n0 | n1) & 15) == 0 &&
+                          ((smem_addr(s_p0) | smem_addr(s_p1)) & 15) == 0;
+      if (tma_ok) {
+        if (tid == 0) {
+          tma_store(g0, smem_addr(s_p0), n0);
+          tma_store(g1, smem_addr(s_p1), n1);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+      } else {
+        for (int i = tid; i < valid * A0; i += kThreads) g0[i] = s_p0[i];
+        for (int i = tid; i < valid * A1; i += kThreads) g1[i] = s_p1[i];
+      }
+      if (values && tid < valid) values[r0 + tid] = s_v[tid];
+    }
+    fence_after();
+    __syncthreads();      // staging (aliases the A tile) free again; TMEM D free
+  }
+
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
+                 ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+}
+
+// ---- weight packing: fp32 nn.Linear weights [out, in] -> bf16 canonical K-major tiles ------
+__global__ void pack_matrix_kernel(const float *__restrict__ w, int n_rows, int n_cols,
+                                   int n_pad, int k_pad, __nv_bfloat16 *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;    // over n_pad * k_pad
+  if (i >= n_pad * k_pad) return;
+  const int n = i / k_pad, k = i - n * k_pad;
+  const float v = (n < n_rows && k < n_cols) ? w[(long long)n * n_cols + k] : 0.0f;
+  const int off = (n >> 3) * (k_pad / 8) * 64 + (k >> 3) * 64 + (n & 7) * 8 + (k & 7);
+  out[off] = __float2bfloat16_rn(v);
+}
+
+__global__ void pack_rows_kernel(const float *__restrict__ w, int rows, int n_cols, int row0,
+                                 int k_pad, __nv_bfloat16 *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * n_cols) return;
+  const int rr = i / n_cols, k = i - rr * n_cols;
+  const int n = row0 + rr;
+  const int off = (n >> 3) * (k_pad / 8) * 64 + (k >> 3) * 64 + (n & 7) * 8 + (k & 7);
+  out[off] = __float2bfloat16_rn(w[i]);
+}
+
+__global__ void pack_misc_kernel(MlpHeader hd, unsigned char *blob, const float *b1,
+                                 const float *b2, const float *bh0, const float *bh1,
+                                 const float *bv) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *reinterpret_cast<MlpHeader *>(blob) = hd;
+  float *b = reinterpret_cast<float *>(blob + hd.off_b);
+  if (i < hd.H) { b[i] = b1[i]; b[hd.H + i] = b2[i]; }
+  if (i < hd.N3) {
+    float v = 0.0f;
+    if (i < hd.A0) v = bh0[i];
+    else if (i < hd.A0 + hd.A1) v = bh1[i - hd.A0];
+    else if (i == hd.A0 + hd.A1) v = bv[0];
+    b[2 * hd.H + i] = v;
+  }
+}
+
+MlpHeader make_header(int F, int H, int A0, int A1) {
+  MlpHeader hd;
+  hd.F = F; hd.K1 = round_up(F, 16); hd.H = H; hd.A0 = A0; hd.A1 = A1;
+  hd.N3 = round_up(A0 + A1 + 1, 16);
+  hd.off_w1 = 128;
+  hd.off_w2 = hd.off_w1 + H * hd.K1 * 2;
+  hd.off_w3 = hd.off_w2 + H * H * 2;
+  hd.off_b = hd.off_w3 + hd.N3 * H * 2;
+  hd.total_bytes = round_up(hd.off_b + (2 * H + hd.N3) * 4, 16);
+  hd.pad = 0;
+  return hd;
+}
+
+size_t mlp_smem_bytes(const MlpHeader &hd) {
+  const size_t w = (size_t)hd.total_bytes - hd.off_w1;
+  const size_t a = (size_t)max(kTileM * hd.K1 * 2, kTileM * (hd.A0 + hd.A1 + 1) * 4);
+  return ((w + 127) & ~(size_t)127) + ((a + 15) & ~(size_t)15) + 64;
+}
+
+bool mlp_shape_ok(int F, int H, int A0, int A1) {
+  return F >= 1 && F <= 256 && H >= 16 && H <= 256 && (H % 32) == 0 && A0 >= 1 && A1 >= 1 &&
+         A0 + A1 + 1 <= 64;
+}
+
+}  // namespace
+
+WDB_API long long wdb_mlp_blob_bytes(int F, int H, int A0, int A1) {
+  if (!mlp_shape_ok(F, H, A0, A1)) return -1;
+  const MlpHeader hd = make_header(F, H, A0, A1);
+  if (mlp_smem_bytes(hd) > 227 * 1024) return -1;
+  return hd.total_bytes;
+}
+
+WDB_API int wdb_mlp_pack_weights(void *stream, void *blob, const float *w1, const float *b1,
+                                 const float *w2, const float *b2, const float *wh0,
+                                 const float *bh0, const float *wh1, const float *bh1,
+                                 const float *wv, const float *bv, int F, int H, int A0,
+                                 int A1) {
+  if (!blob || !w1 || !b1 || !w2 || !b2 || !wh0 || !bh0 || !wh1 || !bh1 || !wv || !bv)
+    return (int)cudaErrorInvalidValue;
+  if (!mlp_shape_ok(F, H, A0, A1)) return (int)cudaErrorInvalidValue;
+  const MlpHeader hd = make_header(F, H, A0, A1);
+  cudaStream_t st = as_stream(stream);
+  unsigned char *b = reinterpret_cast<unsigned char *>(blob);
+  auto bf = [&](int off) { return reinterpret_cast<__nv_bfloat16 *>(b + off); };
+  cudaError_t e = cudaMemsetAsync(b + hd.off_w3, 0, (size_t)hd.N3 * H * 2, st);
+  if (e != cudaSuccess) return (int)e;
+  const int T = 256;
+  pack_matrix_kernel<<<(H * hd.K1 + T - 1) / T, T, 0, st>>>(w1, H, F, H, hd.K1, bf(hd.off_w1));
+  pack_matrix_kernel<<<(H * H + T - 1) / T, T, 0, st>>>(w2, H, H, H, H, bf(hd.off_w2));
+  // W3 = [head0; head1; value] stacked along N (zero padded to N3 rows by the memset)
+  pack_rows_kernel<<<(A0 * H + T - 1) / T, T, 0, st>>>(wh0, A0, H, 0, H, bf(hd.off_w3));
+  pack_rows_kernel<<<(A1 * H + T - 1) / T, T, 0, st>>>(wh1, A1, H, A0, H, bf(hd.off_w3));
+  pack_rows_kernel<<<(H + T - 1) / T, T, 0, st>>>(wv, 1, H, A0 + A1, H, bf(hd.off_w3));
+  g_launch_count += 5;
+  pack_misc_kernel<<<(max(H, hd.N3) + T - 1) / T, T, 0, st>>>(hd, b, b1, b2, bh0, bh1, bv);
+  return finish_launch();
+}
+
+WDB_API int wdb_mlp_policy_forward(void *stream, const void *blob, int F, int H, int A0, int A1,
+                                   const float *obs, long long rows, float *probs0,
+                                   float *probs1, float *values) {
+  if (!blob || !obs || !probs0 || !probs1 || rows <= 0) return (int)cudaErrorInvalidValue;
+  if (!mlp_shape_ok(F, H, A0, A1)) return (int)cudaErrorInvalidValue;
+  const MlpHeader hd = make_header(F, H, A0, A1);
+  const size_t smem = mlp_smem_bytes(hd);
+  if (smem > 227 * 1024) return (int)cudaErrorInvalidValue;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(mlp_forward_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = smem;
+  }
+  const long long n_tiles = (rows + kTileM - 1) / kTileM;
+  const int grid = (int)min((long long)kNumSMs, n_tiles);
+  mlp_forward_kernel<<<grid, kThreads, smem, as_stream(stream)>>>(
+      reinterpret_cast<const unsigned char *>(blob), obs, rows, probs0, probs1, values);
+  return finish_launch();
+}

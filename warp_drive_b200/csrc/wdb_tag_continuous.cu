@@ -1071,7 +1071,7 @@ int plan_launch(TcParams &P, const FusedParams *Q, bool have_gscratch, LaunchPla
   }
   P.scr_warp_bytes = (int)warp_bytes;
   size_t smem = base + warp_bytes * nwarps;
-  P.stage_obs = !P.use_full_obs && (smem + tile_obs <= 110 * 1024);
+  P.stage_obs = !P.use_full_obs && (smem + tile_obs <= 113 * 1024);   // two CTAs per SM
   size_t tile = P.stage_obs ? tile_obs : 0;
   if (tile_probs > tile) tile = tile_probs;
   smem += tile;

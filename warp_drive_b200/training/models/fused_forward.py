@@ -1,0 +1,60 @@
+"""Rollout-time forward of a FullyConnected policy on the tensor cores:
+`wdb_mlp_policy_forward` (csrc/wdb_mlp.cu, tcgen05 + TMEM), one kernel per policy instead
+of the 12-kernel torch module call.  The torch module stays the owner of the parameters
+(training / autograd go through it); this wrapper re-packs them into the kernel's bf16
+layout whenever they changed (`refresh()` after an optimizer step).
+"""
+import torch
+
+from warp_drive_b200 import lib as _lib
+
+
+class FusedPolicyForward:
+    @staticmethod
+    def supported(model):
+        """Two hidden layers of equal width (multiple of 32, <= 256), two softmax heads."""
+        try:
+            if getattr(model, "is_deterministic", True) or len(model.fc) != 2:
+                return False
+            dims = list(model.fc_dims)
+            if dims[0] != dims[1] or len(model.output_dims) != 2:
+                return False
+            L = _lib.load()
+            return L.wdb_mlp_blob_bytes(int(model.flattened_obs_size), int(dims[0]),
+                                        int(model.output_dims[0]),
+                                        int(model.output_dims[1])) > 0
+        except Exception:  # noqa: BLE001
+            return False
+
+    def __init__(self, model):
+        assert self.supported(model)
+        self.model = model
+        self.F = int(model.flattened_obs_size)
+        self.H = int(model.fc_dims[0])
+        self.A0, self.A1 = (int(a) for a in model.output_dims)
+        self.lib = _lib.load()
+        nbytes = int(self.lib.wdb_mlp_blob_bytes(self.F, self.H, self.A0, self.A1))
+        dev = next(model.parameters()).device
+        self.blob = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+        self.refresh()
+
+    def refresh(self):
+        """Re-pack the module's current parameters (call after every optimizer step)."""
+        m = self.model
+        l1, l2 = m.fc["0"][0], m.fc["1"][0]
+        h0, h1 = m.policy_head[0], m.policy_head[1]
+        ts = [l1.weight, l1.bias, l2.weight, l2.bias, h0.weight, h0.bias, h1.weight, h1.bias,
+              m.vf_head.weight, m.vf_head.bias]
+        ts = [t.detach().float().contiguous() for t in ts]
+        _lib.check(self.lib.wdb_mlp_pack_weights(
+            _lib.stream_ptr(), _lib.ptr(self.blob), *[_lib.ptr(t) for t in ts],
+            self.F, self.H, self.A0, self.A1), "mlp_pack_weights")
+        self._keep = ts
+
+    def __call__(self, obs, probs0, probs1, values=None):
+        """obs [..., F] float32 contiguous -> probs0 [..., A0], probs1 [..., A1] (written)."""
+        rows = obs.numel() // self.F
+        _lib.check(self.lib.wdb_mlp_policy_forward(
+            _lib.stream_ptr(), _lib.ptr(self.blob), self.F, self.H, self.A0, self.A1,
+            _lib.ptr(obs), rows, _lib.ptr(probs0), _lib.ptr(probs1), _lib.ptr(values)),
+            "mlp_policy_forward")
