@@ -109,7 +109,8 @@ class ClockSampler:
                 "reasons": reasons}
 
 
-def build_engine(n_envs, seed, graph_steps, use_graph=True, forward_dtype=None):
+def build_engine(n_envs, seed, graph_steps, use_graph=True, forward_dtype=None,
+                 fused_forward=True):
     import torch
 
     from warp_drive_b200.env_wrapper import EnvWrapper
@@ -137,7 +138,8 @@ def build_engine(n_envs, seed, graph_steps, use_graph=True, forward_dtype=None):
     stats = torch.zeros(4, dtype=torch.int32, device="cuda")
     engine = RolloutEngine(wrapper, models, policy_map, sampler, graph_steps,
                            use_cuda_graph=use_graph, forward_dtype=forward_dtype,
-                           write_observations=False, stats=stats)
+                           write_observations=False, stats=stats,
+                           use_fused_forward=fused_forward)
     engine.stats = stats
     return wrapper, engine, sampler, policy_map
 
@@ -321,7 +323,10 @@ def main():
     ap.add_argument("--envs", type=int, default=2000, help="env replicas per GPU")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--forward-precision", default="tf32", choices=["fp32", "tf32", "bf16"],
-                    help="precision of the policy/value MLP GEMMs (the env path is fp32)")
+                    help="precision of the torch policy forward when --torch-forward is given")
+    ap.add_argument("--torch-forward", action="store_true",
+                    help="run the policy forward through torch/cuBLAS instead of the fused "
+                         "tcgen05 kernel (wdb_mlp_policy_forward)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -350,7 +355,8 @@ def main():
         torch.backends.cudnn.allow_tf32 = True
     wrapper, engine, sampler, policy_map = build_engine(
         args.envs, seed=1234 + rank, graph_steps=T, use_graph=not args.no_graph,
-        forward_dtype=torch.bfloat16 if args.forward_precision == "bf16" else None)
+        forward_dtype=torch.bfloat16 if args.forward_precision == "bf16" else None,
+        fused_forward=not args.torch_forward)
     E, N = wrapper.n_envs, wrapper.n_agents
 
     def barrier():
@@ -423,7 +429,9 @@ def main():
                                "discrete 21x21 actions, K=10 partial obs, 2 policies "
                                "fully_connected [256,256], rollout step = forward + sample "
                                "+ step + reset + push-to-batch",
-                   "policy_forward": f"torch/cuBLAS {args.forward_precision} GEMMs (library)",
+                   "policy_forward": ("wdb_mlp_policy_forward: fused tcgen05/TMEM MLP kernel, "
+                                      "bf16 operands, fp32 accumulate" if engine.fused_forward
+                                      else f"torch/cuBLAS {args.forward_precision} GEMMs (library)"),
                    "envs_per_gpu": E, "agents": N, "graph_steps": T,
                    "cuda_graph": not args.no_graph,
                    "l2": "working set per step (~110 MB obs+probs+batch slots, batch slot "

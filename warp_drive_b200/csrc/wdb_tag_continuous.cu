@@ -239,6 +239,56 @@ __device__ __forceinline__ float div_by_const_f64(float d, double c, double inv_
 
 // MAXT = 320: the common geometry (EPB * N <= 320 threads, two CTAs per SM, <= 96
 // registers per thread); MAXT = 1024: one env of up to 1024 agents per CTA.
+// Branch-free top-16 of ALL candidates (packed squared-distance | id keys), 16 at a time:
+// sort16 + half-cleaner + bitonic merger on named registers (wdb_sortnet.cuh).
+__device__ __noinline__ void network_top16(float2 pa, const float2 *kp, int N, uint32_t idmask,
+                                           uint32_t *out) {
+  uint32_t r0, r1, r2, r3, r4, r5, r6, r7, r8, r9, r10, r11, r12, r13, r14, r15;
+  const uint32_t pad_key = 0x7f800000u | idmask;
+#define WDB_KEY(i)                                                                  \
+  uint32_t c##i = pad_key;                                                          \
+  if (base + i < N) {                                                               \
+    const float2 pb = kp[base + i];                                                 \
+    const float dx = pa.x - pb.x, dy = pa.y - pb.y;                                 \
+    c##i = (__float_as_uint(dx * dx + dy * dy) & ~idmask) | (uint32_t)(base + i);   \
+  }
+#define WDB_COPY(i) r##i = c##i;
+  {
+    const int base = 0;
+    WDB_REP16(WDB_KEY)
+    WDB_SORT16(c)
+    WDB_REP16(WDB_COPY)
+  }
+  for (int base = kListLen; base < N; base += kListLen) {
+    WDB_REP16(WDB_KEY)
+    WDB_SORT16(c)
+    // half-cleaner: the 16 smallest of (r ascending) U (c ascending), as a bitonic
+    // sequence, then the bitonic merger restores ascending order
+    r0 = min(r0, c15); r1 = min(r1, c14); r2 = min(r2, c13); r3 = min(r3, c12);
+    r4 = min(r4, c11); r5 = min(r5, c10); r6 = min(r6, c9); r7 = min(r7, c8);
+    r8 = min(r8, c7); r9 = min(r9, c6); r10 = min(r10, c5); r11 = min(r11, c4);
+    r12 = min(r12, c3); r13 = min(r13, c2); r14 = min(r14, c1); r15 = min(r15, c0);
+    WDB_BITONIC_MERGE16(r)
+  }
+#undef WDB_KEY
+#undef WDB_COPY
+  out[0] = r0; out[1] = r1; out[2] = r2; out[3] = r3; out[4] = r4; out[5] = r5;
+  out[6] = r6; out[7] = r7; out[8] = r8; out[9] = r9; out[10] = r10; out[11] = r11;
+  out[12] = r12; out[13] = r13; out[14] = r14; out[15] = r15;
+}
+
+// x / kTwoPi (IEEE round-to-nearest) as reciprocal multiply + one residual correction.
+// Verified EXHAUSTIVELY over all 2^32 float inputs against the division for
+// c = 6.283185308f, r = 1.0f / c: identical bits whenever 1e-30 < |x| < 1e30 (and for 0);
+// outside that range (never reached by direction differences) the true division runs.
+__device__ __forceinline__ float div_by_two_pi(float x, float c, float r) {
+  const float ax = fabsf(x);
+  if (__builtin_expect((ax < 1e-30f && ax > 0.0f) || ax > 1e30f, 0)) return x / c;
+  const float q0 = x * r;
+  const float rem = __fmaf_rn(-q0, c, x);
+  return __fmaf_rn(rem, r, q0);
+}
+
 template <bool FUSED, int MAXT>
 __global__ void __launch_bounds__(MAXT, MAXT == 320 ? 2 : 1)
 tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant__ FusedParams Q) {
@@ -497,6 +547,7 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
   const double diag = sqrt(2.0) * L;                // :94
   const double inv_diag = 1.0 / diag;
   const float vnorm = P.max_speed + kEpsilon;       // :101
+  const float two_pi = kTwoPi, inv_two_pi = 1.0f / kTwoPi;
   const int t_env = active ? s_t[le] : 0;
   const float2 *epos = spos + le * N;
   const int *ealive = salive + le * N;
@@ -546,17 +597,16 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
           if (seen == 0) tau = -1.0f;
           unsigned char *lst = s_scr + (size_t)warp * P.scr_warp_bytes + lane;
           int cnt = 0;
-#pragma unroll 4
+          // branch-free: rejected candidates are stored into the spare row kHistCap
+#pragma unroll 8
           for (int b = 0; b < N; b++) {
             const float2 pb = kp[b];
             const float dx = pa.x - pb.x, dy = pa.y - pb.y;
             const float sq = dx * dx + dy * dy;
-            if (sq <= tau) {
-              lst[min(cnt, kHistCap) * kWarp] = (unsigned char)b;
-              cnt++;
-            } else {
-              m_out = fminf(m_out, sq);
-            }
+            const bool in = sq <= tau;
+            lst[(in ? min(cnt, kHistCap) : kHistCap) * kWarp] = (unsigned char)b;
+            cnt += in ? 1 : 0;
+            m_out = in ? m_out : fminf(m_out, sq);
           }
           const bool hist_ok = (cnt >= kk + 1) && (cnt <= kHistCap);   // self + >= kk others
           if (hist_ok) {
@@ -597,33 +647,13 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
           }
         }
         if (!have) {
-#define WDB_KEY(i)                                                                  \
-  uint32_t c##i = pad_key;                                                          \
-  if (base + i < N) {                                                               \
-    const float2 pb = kp[base + i];                                                 \
-    const float dx = pa.x - pb.x, dy = pa.y - pb.y;                                 \
-    c##i = (__float_as_uint(dx * dx + dy * dy) & ~idmask) | (uint32_t)(base + i);   \
-  }
-#define WDB_COPY(i) r##i = c##i;
-        {
-          const int base = 0;
-          WDB_REP16(WDB_KEY)
-          WDB_SORT16(c)
-          WDB_REP16(WDB_COPY)
-        }
-        for (int base = kListLen; base < N; base += kListLen) {
-          WDB_REP16(WDB_KEY)
-          WDB_SORT16(c)
-          // half-cleaner: the 16 smallest of (r ascending) U (c ascending), as a bitonic
-          // sequence, then the bitonic merger restores ascending order
-          r0 = min(r0, c15); r1 = min(r1, c14); r2 = min(r2, c13); r3 = min(r3, c12);
-          r4 = min(r4, c11); r5 = min(r5, c10); r6 = min(r6, c9); r7 = min(r7, c8);
-          r8 = min(r8, c7); r9 = min(r9, c6); r10 = min(r10, c5); r11 = min(r11, c4);
-          r12 = min(r12, c3); r13 = min(r13, c2); r14 = min(r14, c1); r15 = min(r15, c0);
-          WDB_BITONIC_MERGE16(r)
-        }
-#undef WDB_KEY
-#undef WDB_COPY
+          // rare (first step after a reset, list over/underflow): out-of-line so that the
+          // hot path stays small in the instruction cache
+          uint32_t out[kListLen];
+          network_top16(pa, kp, N, idmask, out);
+          r0 = out[0]; r1 = out[1]; r2 = out[2]; r3 = out[3]; r4 = out[4]; r5 = out[5];
+          r6 = out[6]; r7 = out[7]; r8 = out[8]; r9 = out[9]; r10 = out[10]; r11 = out[11];
+          r12 = out[12]; r13 = out[13]; r14 = out[14]; r15 = out[15];
         }   // !have
         R[0] = r0; R[1] = r1; R[2] = r2; R[3] = r3; R[4] = r4; R[5] = r5; R[6] = r6;
         R[7] = r7; R[8] = r8; R[9] = r9; R[10] = r10; R[11] = r11; R[12] = r12;
@@ -759,7 +789,7 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
             const float dsp = ssp[lb] - spa, dac = sacc[lb] - acca;
             orow[2 * K + p] = unit_v ? dsp : dsp / vnorm;
             orow[3 * K + p] = unit_v ? dac : dac / vnorm;
-            orow[4 * K + p] = static_cast<float>(sdir[lb] - dira) / (kTwoPi);
+            orow[4 * K + p] = div_by_two_pi(sdir[lb] - dira, two_pi, inv_two_pi);
             orow[5 * K + p] = stype[b];
             orow[6 * K + p] = ealive[b];
           }
@@ -774,7 +804,7 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
             orow[1 * K + p] = div_by_const_f64(pb.y - pa.y, diag, inv_diag);
             orow[2 * K + p] = static_cast<float>(ssp[lb] - spa) / vnorm;
             orow[3 * K + p] = static_cast<float>(sacc[lb] - acca) / vnorm;
-            orow[4 * K + p] = static_cast<float>(sdir[lb] - dira) / (kTwoPi);
+            orow[4 * K + p] = div_by_two_pi(sdir[lb] - dira, two_pi, inv_two_pi);
             orow[5 * K + p] = stype[b];
             orow[6 * K + p] = ealive[b];
           }
@@ -811,7 +841,7 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
           f1 = div_by_const_f64(rpos[b].y - rpos[ra].y, diag, inv_diag);
           f2 = static_cast<float>(rsp[b] - rsp[ra]) / vnorm;
           f3 = static_cast<float>(racc[b] - racc[ra]) / vnorm;
-          f4 = static_cast<float>(rdir[b] - rdir[ra]) / (kTwoPi);
+          f4 = div_by_two_pi(rdir[b] - rdir[ra], two_pi, inv_two_pi);
         }
         const float f5 = stype[b], f6 = ral[b];
         if (orow) {

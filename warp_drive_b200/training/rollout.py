@@ -22,7 +22,8 @@ _PROCESSED_OBSERVATIONS = Constants.PROCESSED_OBSERVATIONS
 class RolloutEngine:
     def __init__(self, env_wrapper, models, policy_tag_to_agent_id_map, sampler,
                  batch_size_per_env, use_cuda_graph=True, forward_dtype=None,
-                 use_fused_step=True, write_observations=True, stats=None):
+                 use_fused_step=True, write_observations=True, stats=None,
+                 use_fused_forward=True):
         self.env_wrapper = env_wrapper
         self.dm = env_wrapper.cuda_data_manager
         self.models = models
@@ -71,6 +72,22 @@ class RolloutEngine:
             # observations of the *next* forward pass, per policy (filled by the kernel)
             self.cur_obs = {p: obs.index_select(1, self.ids[p]).contiguous()
                             for p in self.policies}
+
+        # ---- tensor-core forward (tcgen05 MLP kernel) for the fused path
+        self.fused_forward = {}
+        if self.fused is not None and use_fused_forward and forward_dtype is None:
+            from warp_drive_b200.training.models.fused_forward import FusedPolicyForward
+
+            if all(FusedPolicyForward.supported(m) for m in self.models.values()):
+                self.fused_forward = {p: FusedPolicyForward(self.models[p]) for p in self.policies}
+                self._probs = {p: [torch.empty((self.E, len(self.policy_map[p]), h), device=dev)
+                                   for h in self.heads] for p in self.policies}
+
+    def refresh_forward_weights(self):
+        """Re-pack the policies' parameters for the tensor-core forward (after every
+        optimizer step / checkpoint load)."""
+        for fwd in self.fused_forward.values():
+            fwd.refresh()
 
     def _fused_eligible(self):
         from warp_drive_b200.utils.spaces import Box, MultiDiscrete
@@ -138,7 +155,12 @@ class RolloutEngine:
                                          for p in self.policies}
                 obs_next = self._scratch_obs
                 actions_batch = rewards_batch = done_batch = None
-            probs = {p: self._forward(self.models[p], obs_in[p]) for p in self.policies}
+            if self.fused_forward:
+                probs = self._probs
+                for p in self.policies:
+                    self.fused_forward[p](obs_in[p], probs[p][0], probs[p][1])
+            else:
+                probs = {p: self._forward(self.models[p], obs_in[p]) for p in self.policies}
             self.fused.launch(probs, actions_batch=actions_batch, rewards_batch=rewards_batch,
                               obs_next=obs_next, done_batch=done_batch, uniforms=uniforms)
             if t < 0:

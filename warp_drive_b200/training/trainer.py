@@ -311,6 +311,7 @@ class Trainer:
                     "Mean episodic steps":
                         float(self.engine.episodic_step_sum) / (n_done + _EPSILON)})
                 metrics_dict[policy] = metrics
+        self.engine.refresh_forward_weights()
         if logging_flag:
             for policy in self.policies:
                 self.engine.episodic_reward_sum[policy].zero_()
