@@ -54,7 +54,7 @@ def test_train_tag_continuous_fused_rollouts(tmp_path):
     from warp_drive_b200.envs.tag_continuous import TagContinuous
     from warp_drive_b200.training.trainer import Trainer
 
-    cfg = _run_config("tag_continuous", num_envs=32, train_batch_size=32 * 25, num_episodes=8)
+    cfg = _run_config("tag_continuous", num_envs=32, train_batch_size=32 * 25, num_episodes=96)
     cfg["env"].update(num_taggers=2, num_runners=10, episode_length=50)
     cfg["saving"]["basedir"] = str(tmp_path)
     env = TagContinuous(**cfg["env"])
@@ -94,7 +94,7 @@ def test_train_tag_gridworld_generic_path(tmp_path):
     from warp_drive_b200.envs.tag_gridworld import CUDATagGridWorld
     from warp_drive_b200.training.trainer import Trainer
 
-    cfg = _run_config("tag_gridworld", num_envs=50, train_batch_size=50 * 20, num_episodes=10)
+    cfg = _run_config("tag_gridworld", num_envs=50, train_batch_size=50 * 20, num_episodes=100)
     cfg["env"].update(grid_length=10, episode_length=40)
     cfg["saving"]["basedir"] = str(tmp_path)
     env = CUDATagGridWorld(**cfg["env"])
@@ -112,7 +112,7 @@ def test_train_cartpole_with_reset_pool(tmp_path):
     from warp_drive_b200.training.trainer import Trainer
 
     cfg = _run_config("single_cartpole", num_envs=256, train_batch_size=256 * 16,
-                      num_episodes=40)
+                      num_episodes=164)
     cfg["env"].update(episode_length=100, reset_pool_size=64)
     cfg["saving"]["basedir"] = str(tmp_path)
     env = CUDAClassicControlCartPoleEnv(**cfg["env"])

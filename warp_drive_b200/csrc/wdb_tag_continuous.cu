@@ -596,48 +596,55 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
           if (seen < kk) tau *= 1.0f + 0.45f * (float)(kk - seen);
           if (seen == 0) tau = -1.0f;
           unsigned char *lst = s_scr + (size_t)warp * P.scr_warp_bytes + lane;
-          int cnt = 0;
-          // branch-free: rejected candidates are stored into the spare row kHistCap
+          // branch-free scan: `wp` walks the lane's column of the byte list (rows are kWarp
+          // bytes apart), clamped to the spare row kHistCap where rejected ids also land
+          unsigned char *wp = lst;
+          unsigned char *const trash = lst + kHistCap * kWarp;
 #pragma unroll 8
           for (int b = 0; b < N; b++) {
             const float2 pb = kp[b];
             const float dx = pa.x - pb.x, dy = pa.y - pb.y;
             const float sq = dx * dx + dy * dy;
             const bool in = sq <= tau;
-            lst[(in ? min(cnt, kHistCap) : kHistCap) * kWarp] = (unsigned char)b;
-            cnt += in ? 1 : 0;
+            *(in ? wp : trash) = (unsigned char)b;
+            wp = in ? wp + kWarp : wp;
+            wp = wp < trash ? wp : trash;
             m_out = in ? m_out : fminf(m_out, sq);
           }
+          // overflow (> kHistCap accepted) leaves wp pinned at the spare row: not accepted
+          const int cnt = (wp == trash) ? kHistCap + 1 : (int)(wp - lst) / kWarp;
           const bool hist_ok = (cnt >= kk + 1) && (cnt <= kHistCap);   // self + >= kk others
           if (hist_ok) {
+            // keys of the collected candidates (ids beyond cnt are stale bytes: clamped and
+            // masked to the pad key), sorted 16 at a time; one code instance for both halves
 #define WDB_HKEY(i)                                                                 \
-  uint32_t c##i = pad_key;                                                          \
-  if (hbase + i < cnt) {                                                            \
-    const int b = lst[(hbase + i) * kWarp];                                         \
+  uint32_t c##i;                                                                    \
+  {                                                                                 \
+    const int b = min((int)lst[(hbase + i) * kWarp], N - 1);                        \
     const float2 pb = kp[b];                                                        \
     const float dx = pa.x - pb.x, dy = pa.y - pb.y;                                 \
-    c##i = (__float_as_uint(dx * dx + dy * dy) & ~idmask) | (uint32_t)b;            \
+    const uint32_t key = (__float_as_uint(dx * dx + dy * dy) & ~idmask) | (uint32_t)b; \
+    c##i = (hbase + i < cnt) ? key : pad_key;                                       \
   }
-#define WDB_HCOPY(i) r##i = c##i;
-            {
-              const int hbase = 0;
+#pragma unroll 1
+            for (int hbase = 0; hbase < kHistCap; hbase += kListLen) {
+              if (hbase >= cnt) break;
               WDB_REP16(WDB_HKEY)
               WDB_SORT16(c)
-              WDB_REP16(WDB_HCOPY)
-            }
-            if (cnt > kListLen) {
-              // 17..32 candidates: sort the second half and merge, keeping the 16 smallest
-              const int hbase = kListLen;
-              WDB_REP16(WDB_HKEY)
-              WDB_SORT16(c)
-              r0 = min(r0, c15); r1 = min(r1, c14); r2 = min(r2, c13); r3 = min(r3, c12);
-              r4 = min(r4, c11); r5 = min(r5, c10); r6 = min(r6, c9); r7 = min(r7, c8);
-              r8 = min(r8, c7); r9 = min(r9, c6); r10 = min(r10, c5); r11 = min(r11, c4);
-              r12 = min(r12, c3); r13 = min(r13, c2); r14 = min(r14, c1); r15 = min(r15, c0);
-              WDB_BITONIC_MERGE16(r)
+              if (hbase == 0) {
+                r0 = c0; r1 = c1; r2 = c2; r3 = c3; r4 = c4; r5 = c5; r6 = c6; r7 = c7;
+                r8 = c8; r9 = c9; r10 = c10; r11 = c11; r12 = c12; r13 = c13; r14 = c14;
+                r15 = c15;
+              } else {
+                // 17..32 candidates: merge, keeping the 16 smallest (half-cleaner + merger)
+                r0 = min(r0, c15); r1 = min(r1, c14); r2 = min(r2, c13); r3 = min(r3, c12);
+                r4 = min(r4, c11); r5 = min(r5, c10); r6 = min(r6, c9); r7 = min(r7, c8);
+                r8 = min(r8, c7); r9 = min(r9, c6); r10 = min(r10, c5); r11 = min(r11, c4);
+                r12 = min(r12, c3); r13 = min(r13, c2); r14 = min(r14, c1); r15 = min(r15, c0);
+                WDB_BITONIC_MERGE16(r)
+              }
             }
 #undef WDB_HKEY
-#undef WDB_HCOPY
             have = true;
             n_have = min(cnt - 1, kListLen - 1);
             n_cand = cnt - 1;
@@ -777,23 +784,28 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
         const bool unit_v = (vnorm == 1.0f);
         const int *gids = (!net_ok && !P.scratch_in_smem)
                               ? P.g_nid + (long long)gi * (N - 1) : nullptr;
-#pragma unroll
-        for (int p = 0; p < kListLen - 1; p++) {
-          if (p < kk) {
-            const int b = net_ok ? (int)(R[p + 1] & idmask) : gids[p];
-            nn[p] = b;                                          // :202-211
-            const int lb = le * N + b;                          // :214-250
-            const float2 pb = epos[b];
-            orow[0 * K + p] = div_by_const_f64(pb.x - pa.x, diag, inv_diag);
-            orow[1 * K + p] = div_by_const_f64(pb.y - pa.y, diag, inv_diag);
-            const float dsp = ssp[lb] - spa, dac = sacc[lb] - acca;
-            orow[2 * K + p] = unit_v ? dsp : dsp / vnorm;
-            orow[3 * K + p] = unit_v ? dac : dac / vnorm;
-            orow[4 * K + p] = div_by_two_pi(sdir[lb] - dira, two_pi, inv_two_pi);
-            orow[5 * K + p] = stype[b];
-            orow[6 * K + p] = ealive[b];
-          }
+        // (x / vnorm with vnorm == 1.0f -- max_speed 1 -- is the identity: skipping the
+        //  IEEE division also avoids its slow path, which a zero numerator always takes)
+#define WDB_FEATURES(UNIT)                                                          \
+        _Pragma("unroll")                                                           \
+        for (int p = 0; p < kListLen - 1; p++) {                                    \
+          if (p < kk) {                                                             \
+            const int b = net_ok ? (int)(R[p + 1] & idmask) : gids[p];              \
+            nn[p] = b;                                          /* :202-211 */      \
+            const int lb = le * N + b;                          /* :214-250 */      \
+            const float2 pb = epos[b];                                              \
+            orow[0 * K + p] = div_by_const_f64(pb.x - pa.x, diag, inv_diag);        \
+            orow[1 * K + p] = div_by_const_f64(pb.y - pa.y, diag, inv_diag);        \
+            const float dsp = ssp[lb] - spa, dac = sacc[lb] - acca;                 \
+            orow[2 * K + p] = UNIT ? dsp : dsp / vnorm;                             \
+            orow[3 * K + p] = UNIT ? dac : dac / vnorm;                             \
+            orow[4 * K + p] = div_by_two_pi(sdir[lb] - dira, two_pi, inv_two_pi);   \
+            orow[5 * K + p] = stype[b];                                             \
+            orow[6 * K + p] = ealive[b];                                            \
+          }                                                                         \
         }
+        if (unit_v) { WDB_FEATURES(true) } else { WDB_FEATURES(false) }
+#undef WDB_FEATURES
         if (!net_ok) {
           for (int p = kListLen - 1; p < kk; p++) {
             const int b = gids[p];
