@@ -79,7 +79,7 @@ def test_train_tag_continuous_fused_rollouts(tmp_path):
     w2 = EnvWrapper(env2, num_envs=32, env_backend="numba")
     t2 = Trainer(env_wrapper=w2, config=cfg2, policy_tag_to_agent_id_map=pm,
                  results_dir="t2", verbose=False)
-    assert t2.current_timestep["runner"] == int(os.path.basename(ck).split("_")[-1].split(".")[0])
+    assert t2.current_timestep["runner"] == int(os.path.basename(ck).split(".state_dict")[0].split("_")[-1])
     for a, b in zip(trainer.models["runner"].parameters(), t2.models["runner"].parameters()):
         assert torch.equal(a.cpu(), b.cpu())
     states = t2.fetch_episode_states(["loc_x", "loc_y", "still_in_the_game"], env_id=1,
