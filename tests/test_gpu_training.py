@@ -72,14 +72,15 @@ def test_train_tag_continuous_fused_rollouts(tmp_path):
     done = dm.data_on_device_via_torch("done_flags_batch")
     assert set(done.unique().tolist()) <= {0, 1}
     # checkpoint round trip through the reference's file naming
-    ck = sorted(glob.glob(os.path.join(trainer.save_dir, "runner_*.state_dict")))[-1]
+    step_of = lambda f: int(os.path.basename(f).split(".state_dict")[0].split("_")[-1])  # noqa: E731
+    ck = max(glob.glob(os.path.join(trainer.save_dir, "runner_*.state_dict")), key=step_of)
     cfg2 = copy.deepcopy(cfg)
     cfg2["policy"]["runner"]["model"]["model_ckpt_filepath"] = ck
     env2 = TagContinuous(**cfg["env"])
     w2 = EnvWrapper(env2, num_envs=32, env_backend="numba")
     t2 = Trainer(env_wrapper=w2, config=cfg2, policy_tag_to_agent_id_map=pm,
                  results_dir="t2", verbose=False)
-    assert t2.current_timestep["runner"] == int(os.path.basename(ck).split(".state_dict")[0].split("_")[-1])
+    assert t2.current_timestep["runner"] == step_of(ck) == trainer.current_timestep["runner"]
     for a, b in zip(trainer.models["runner"].parameters(), t2.models["runner"].parameters()):
         assert torch.equal(a.cpu(), b.cpu())
     states = t2.fetch_episode_states(["loc_x", "loc_y", "still_in_the_game"], env_id=1,

@@ -15,7 +15,8 @@
 //     never touch shared or global memory; final epilogue = bias + two softmaxes + value,
 //     staged in shared memory and written with TMA bulk stores.
 //   * one elected thread issues the MMAs; completion is signalled through an mbarrier
-//     (tcgen05.commit), 4 warps = 128 TMEM lanes = 128 rows run the epilogues.
+//     (tcgen05.commit); 8 warps run the epilogues (4 lane quadrants x 2 column halves);
+//   * the next tile's obs are prefetched into registers while the current tile computes.
 //
 // Numerics: bf16 operands, fp32 accumulation (the reference is fp32; SURVEY.md section 8
 // row a3 allows TF32/BF16 for the forward that feeds the sampler).  Tested against a
@@ -30,7 +31,8 @@ using namespace wdb;
 namespace {
 
 constexpr int kTileM = 128;
-constexpr int kThreads = 128;
+constexpr int kThreads = 256;
+constexpr int kPrefetch = 48;   // fp32 obs values per thread held across a tile
 constexpr int kTmemCols = 512;
 constexpr int kColD = 0;      // accumulator columns [0, 256)
 constexpr int kColH = 256;    // packed bf16 hidden activations [256, 384)
@@ -152,24 +154,33 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<const uint32_t *>(&h);
 }
 
-// hidden epilogue: D[lane, 0..H) (+bias, ReLU) -> packed bf16 into TMEM columns kColH..
+// hidden epilogue: D[lane, c0..c1) (+bias, ReLU) -> packed bf16 into TMEM columns kColH + c/2
 __device__ __forceinline__ void hidden_epilogue(uint32_t tmem_lane_base, const float *bias,
-                                                int H) {
-  for (int c = 0; c < H; c += 32) {
+                                                int c0, int c1) {
+  for (int c = c0; c < c1; c += 32) {
     uint32_t v[32];
     tmem_ld32(tmem_lane_base + kColD + c, v);
     uint32_t out[16];
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
-      const float a = fmaxf(__uint_as_float(v[2 * i]) + bias[c + 2 * i], 0.0f);
-      const float b = fmaxf(__uint_as_float(v[2 * i + 1]) + bias[c + 2 * i + 1], 0.0f);
-      out[i] = pack_bf16(a, b);
+    for (int i = 0; i < 8; i++) {
+      const float4 b = *reinterpret_cast<const float4 *>(bias + c + 4 * i);   // broadcast LDS.128
+      const float x0 = fmaxf(__uint_as_float(v[4 * i]) + b.x, 0.0f);
+      const float x1 = fmaxf(__uint_as_float(v[4 * i + 1]) + b.y, 0.0f);
+      const float x2 = fmaxf(__uint_as_float(v[4 * i + 2]) + b.z, 0.0f);
+      const float x3 = fmaxf(__uint_as_float(v[4 * i + 3]) + b.w, 0.0f);
+      out[2 * i] = pack_bf16(x0, x1);
+      out[2 * i + 1] = pack_bf16(x2, x3);
     }
     tmem_st16(tmem_lane_base + kColH + c / 2, out);
   }
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+// 8 warps: warp w owns TMEM lanes 32 (w & 3) .. +31 (= rows of the tile) and, in the hidden
+// epilogues, the column half (w >> 2); in the output epilogue half 0 does head 0 and half 1
+// does head 1 + the value.  The fp32 obs of the NEXT tile are prefetched into registers
+// (unit-stride loads issued right after the current A tile is built) so their latency hides
+// behind the three MMAs and epilogues of the current tile.
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_forward_kernel(const unsigned char *__restrict__ blob, const float *__restrict__ obs,
                    long long rows, float *__restrict__ probs0, float *__restrict__ probs1,
@@ -179,7 +190,6 @@ mlp_forward_kernel(const unsigned char *__restrict__ blob, const float *__restri
   const int F = hd.F, K1 = hd.K1, H = hd.H, A0 = hd.A0, A1 = hd.A1, N3 = hd.N3;
   const int w_bytes = hd.total_bytes - hd.off_w1;        // W1 | W2 | W3 | biases, contiguous
   unsigned char *s_w = smem;                             // packed weights + biases
-  const __nv_bfloat16 *s_w1 = reinterpret_cast<const __nv_bfloat16 *>(s_w);
   const unsigned char *s_w2 = s_w + (hd.off_w2 - hd.off_w1);
   const unsigned char *s_w3 = s_w + (hd.off_w3 - hd.off_w1);
   const float *s_b1 = reinterpret_cast<const float *>(s_w + (hd.off_b - hd.off_w1));
@@ -189,9 +199,9 @@ mlp_forward_kernel(const unsigned char *__restrict__ blob, const float *__restri
   const int a_bytes = max(kTileM * K1 * 2, kTileM * (A0 + A1 + 1) * 4);
   unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(s_a + ((a_bytes + 15) & ~15));
   uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 2);
-  (void)s_w1;
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quad = warp & 3, half = warp >> 2;
   const uint32_t bar_w = smem_addr(&s_bar[0]);           // weights landed
   const uint32_t bar_mma = smem_addr(&s_bar[1]);         // MMA group done
 
@@ -209,17 +219,35 @@ mlp_forward_kernel(const unsigned char *__restrict__ blob, const float *__restri
   __syncthreads();
   fence_after();
   const uint32_t tmem_base = *s_tmem;
-  const uint32_t tmem_lane = tmem_base + ((uint32_t)(warp * 32) << 16);   // this warp's lanes
+  const uint32_t tmem_lane = tmem_base + ((uint32_t)(quad * 32) << 16);   // this warp's lanes
 
-  if (tid == 0) {                                         // weights: one TMA bulk copy
+  if (tid == 0) {                                         // weights: TMA bulk copies
     mbar_expect_tx(bar_w, (uint32_t)w_bytes);
     uint32_t off = 0;
-    while (off < (uint32_t)w_bytes) {                     // <= 64 KB per bulk copy is plenty safe
+    while (off < (uint32_t)w_bytes) {
       const uint32_t n = min((uint32_t)w_bytes - off, 65536u);
       tma_load(smem_addr(s_w + off), blob + hd.off_w1 + off, n, bar_w);
       off += n;
     }
   }
+
+  const long long n_tiles = (rows + kTileM - 1) / kTileM;
+  const int batch_elems = kThreads * kPrefetch;
+  const bool single_batch = kTileM * F <= batch_elems;    // whole tile fits the register prefetch
+  const int dr = kThreads / F, dk = kThreads - dr * F;    // element index += kThreads in (r, k) form
+  float pf[kPrefetch];
+  auto load_batch = [&](long long tile, int base) {
+    const long long r0 = tile * kTileM;
+    const int total = (int)min((long long)kTileM, rows - r0) * F - base;
+    const float *src = obs + r0 * F + base;
+#pragma unroll
+    for (int j = 0; j < kPrefetch; j++) {
+      const int i = tid + j * kThreads;
+      pf[j] = i < total ? __ldg(src + i) : 0.0f;
+    }
+  };
+  if (single_batch && (long long)blockIdx.x < n_tiles) load_batch(blockIdx.x, 0);
+
   mbar_wait(bar_w, 0);
 
   const uint32_t idesc_h = make_idesc(kTileM, H);
@@ -227,7 +255,6 @@ mlp_forward_kernel(const unsigned char *__restrict__ blob, const float *__restri
   const uint32_t sbo_a = (uint32_t)(K1 / 8) * 128u;       // A tile / W1: K1/8 core matrices per row group
   const uint32_t sbo_h = (uint32_t)(H / 8) * 128u;        // W2 / W3: H/8 core matrices per row group
   uint32_t mma_phase = 0;
-  const long long n_tiles = (rows + kTileM - 1) / kTileM;
   float *s_p0 = reinterpret_cast<float *>(s_a);
   float *s_p1 = s_p0 + kTileM * A0;
   float *s_v = s_p1 + kTileM * A1;
@@ -236,24 +263,27 @@ mlp_forward_kernel(const unsigned char *__restrict__ blob, const float *__restri
     const long long r0 = tile * kTileM;
     const int valid = (int)min((long long)kTileM, rows - r0);
 
-    // ---- obs tile -> bf16, canonical K-major layout (unit-stride global loads)
+    // ---- obs tile -> bf16, canonical K-major layout
     {
-      // zero the K padding and (for a partial tile) the missing rows
-      uint4 *z = reinterpret_cast<uint4 *>(s_a);
+      uint4 *z = reinterpret_cast<uint4 *>(s_a);          // K padding / missing rows = 0
       for (int i = tid; i < kTileM * K1 * 2 / 16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
       __syncthreads();
-      const float *src = obs + r0 * F;
       const int total = valid * F;
-      int r = tid / F, k = tid - (tid / F) * F;            // element (r, k) of index tid
-      const int dr = kThreads / F, dk = kThreads - dr * F; // += kThreads in (r, k) form
       __nv_bfloat16 *a16 = reinterpret_cast<__nv_bfloat16 *>(s_a);
-      for (int i = tid; i < total; i += kThreads) {
-        const float x = src[i];
-        const int off = (r >> 3) * (int)(sbo_a / 2) + (k >> 3) * 64 + (r & 7) * 8 + (k & 7);
-        a16[off] = __float2bfloat16_rn(x);
-        r += dr; k += dk;
-        if (k >= F) { k -= F; r += 1; }
+      for (int base = 0; base < total; base += batch_elems) {
+        if (!single_batch) load_batch(tile, base);
+        int r = (base + tid) / F, k = (base + tid) - r * F;
+#pragma unroll
+        for (int j = 0; j < kPrefetch; j++) {
+          if (base + tid + j * kThreads < total) {
+            const int off = (r >> 3) * (int)(sbo_a / 2) + (k >> 3) * 64 + (r & 7) * 8 + (k & 7);
+            a16[off] = __float2bfloat16_rn(pf[j]);
+          }
+          r += dr; k += dk;
+          if (k >= F) { k -= F; r += 1; }
+        }
       }
+      if (single_batch && tile + gridDim.x < n_tiles) load_batch(tile + gridDim.x, 0);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
@@ -269,7 +299,7 @@ mlp_forward_kernel(const unsigned char *__restrict__ blob, const float *__restri
     }
     mbar_wait(bar_mma, mma_phase); mma_phase ^= 1;
     fence_after();
-    hidden_epilogue(tmem_lane, s_b1, H);
+    hidden_epilogue(tmem_lane, s_b1, half * (H / 2), (half + 1) * (H / 2));
     fence_before();
     __syncthreads();
 
@@ -284,7 +314,7 @@ mlp_forward_kernel(const unsigned char *__restrict__ blob, const float *__restri
     }
     mbar_wait(bar_mma, mma_phase); mma_phase ^= 1;
     fence_after();
-    hidden_epilogue(tmem_lane, s_b2, H);
+    hidden_epilogue(tmem_lane, s_b2, half * (H / 2), (half + 1) * (H / 2));
     fence_before();
     __syncthreads();
 
@@ -300,35 +330,32 @@ mlp_forward_kernel(const unsigned char *__restrict__ blob, const float *__restri
     mbar_wait(bar_mma, mma_phase); mma_phase ^= 1;
     fence_after();
 
-    // ---- output epilogue: bias, softmax per head, value -> staging -> global
+    // ---- output epilogue: bias, softmax of this half's head (+ value) -> staging
     {
-      float lg[64];
-      for (int c = 0; c < N3; c += 16) {
-        uint32_t v[16];
-        tmem_ld16(tmem_lane + kColD + c, v);
+      const int cbase = half ? A0 : 0, cnt = half ? A1 : A0;
+      const int row = quad * 32 + lane;                    // TMEM lane == row of the tile
+      uint32_t v[32];
+      tmem_ld32(tmem_lane + kColD + cbase, v);             // columns past N3 hold stale data: unused
+      float lg[32];
+      float m = -CUDART_INF_F, value = 0.0f;
 #pragma unroll
-        for (int i = 0; i < 16; i++) lg[c + i] = __uint_as_float(v[i]) + s_b3[c + i];
+      for (int i = 0; i < 32; i++) {
+        lg[i] = __uint_as_float(v[i]) + s_b3[min(cbase + i, N3 - 1)];
+        if (i < cnt) m = fmaxf(m, lg[i]);
+        if (i == cnt) value = lg[i];
       }
-      const int row = tid;                                 // TMEM lane == row of the tile
-      float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F;
+      float z = 0.0f;
 #pragma unroll
-      for (int i = 0; i < 64; i++) {
-        if (i < A0) m0 = fmaxf(m0, lg[i]);
-        else if (i < A0 + A1) m1 = fmaxf(m1, lg[i]);
+      for (int i = 0; i < 32; i++) {
+        lg[i] = i < cnt ? __expf(lg[i] - m) : 0.0f;
+        z += lg[i];
       }
-      float z0 = 0.f, z1 = 0.f;
+      const float inv = 1.0f / z;
+      float *dst = (half ? s_p1 : s_p0) + row * cnt;
 #pragma unroll
-      for (int i = 0; i < 64; i++) {
-        if (i < A0) { lg[i] = expf(lg[i] - m0); z0 += lg[i]; }
-        else if (i < A0 + A1) { lg[i] = expf(lg[i] - m1); z1 += lg[i]; }
-      }
-      const float i0 = 1.0f / z0, i1 = 1.0f / z1;
-#pragma unroll
-      for (int i = 0; i < 64; i++) {
-        if (i < A0) s_p0[row * A0 + i] = lg[i] * i0;
-        else if (i < A0 + A1) s_p1[row * A1 + (i - A0)] = lg[i] * i1;
-        else if (i == A0 + A1) s_v[row] = lg[i];
-      }
+      for (int i = 0; i < 32; i++)
+        if (i < cnt) dst[i] = lg[i] * inv;
+      if (half) s_v[row] = value;
     }
     fence_before();
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -419,7 +446,7 @@ size_t mlp_smem_bytes(const MlpHeader &hd) {
 
 bool mlp_shape_ok(int F, int H, int A0, int A1) {
   return F >= 1 && F <= 256 && H >= 16 && H <= 256 && (H % 32) == 0 && A0 >= 1 && A1 >= 1 &&
-         A0 + A1 + 1 <= 64;
+         A0 <= 32 && A1 + 1 <= 32;
 }
 
 }  // namespace

@@ -115,9 +115,10 @@ struct FusedParams {
 // Byte offsets of the small shared-memory arrays (must agree between the kernel and
 // plan_launch): everything before the per-warp scratch, rounded up to 16 bytes so that the
 // scratch and the big tile behind it are valid TMA (cp.async.bulk) destinations.
+__host__ __device__ inline int tc_key_stride(int N) { return (N + 15) & ~15; }
 __host__ __device__ inline size_t tc_small_bytes(int epb, int N) {
-  const size_t b = sizeof(float) * 9ull * epb * N + sizeof(int) * (4ull * N + 4ull * epb + 4)
-                   + 16 /* mbarrier + pad */;
+  const size_t b = sizeof(float) * (7ull * epb * N + 2ull * epb * tc_key_stride(N))
+                   + sizeof(int) * (4ull * N + 4ull * epb + 4) + 16 /* mbarrier + pad */;
   return (b + 15) & ~(size_t)15;
 }
 
@@ -237,20 +238,75 @@ __device__ __forceinline__ float div_by_const_f64(float d, double c, double inv_
   return (float)prod;
 }
 
+// Squared distance with a FIXED operation order (dx * dx rounded, then fused dy * dy + .):
+// the history scan (packed FMUL2 / FFMA2), its threshold tau, the sort keys and the exact
+// check must all see the same float for the same pair of agents.
+__device__ __forceinline__ float sqdist(float ax, float ay, float bx, float by) {
+  const float dx = ax - bx, dy = ay - by;
+  return __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
+}
+
+// History-path scan step for TWO candidates (bits BIT, BIT + 1 of the word `m`): packed
+// float32x2 arithmetic (FADD2 / FMUL2 / FFMA2), then per candidate one compare, one
+// predicated OR into the candidate bit mask and one predicated MIN that tracks the smallest
+// squared distance left OUT of the mask.
+template <int BIT>
+__device__ __forceinline__ void scan_pair(uint32_t &m, float &mo_a, float &mo_b, uint32_t x_lo,
+                                          uint32_t x_hi, uint32_t y_lo, uint32_t y_hi,
+                                          unsigned long long pax2, unsigned long long pay2,
+                                          float tau) {
+  asm("{\n\t"
+      ".reg .b64 x2, y2, dx, dy, sq;\n\t"
+      ".reg .f32 lo, hi;\n\t"
+      ".reg .pred p, q;\n\t"
+      "mov.b64 x2, {%3, %4};\n\t"
+      "mov.b64 y2, {%5, %6};\n\t"
+      "sub.f32x2 dx, %7, x2;\n\t"
+      "sub.f32x2 dy, %8, y2;\n\t"
+      "mul.f32x2 sq, dx, dx;\n\t"
+      "fma.rn.f32x2 sq, dy, dy, sq;\n\t"
+      "mov.b64 {lo, hi}, sq;\n\t"
+      "setp.le.f32 p, lo, %9;\n\t"
+      "setp.le.f32 q, hi, %9;\n\t"
+      "@p or.b32 %0, %0, %10;\n\t"
+      "@q or.b32 %0, %0, %11;\n\t"
+      "@!p min.f32 %1, %1, lo;\n\t"
+      "@!q min.f32 %2, %2, hi;\n\t"
+      "}"
+      : "+r"(m), "+f"(mo_a), "+f"(mo_b)
+      : "r"(x_lo), "r"(x_hi), "r"(y_lo), "r"(y_hi), "l"(pax2), "l"(pay2), "f"(tau),
+        "n"(1u << BIT), "n"(2u << BIT));
+}
+// 16 candidates (4 x 16-byte loads per plane), bits BIT0 .. BIT0 + 15 of `m`
+template <int BIT0>
+__device__ __forceinline__ void scan_16(uint32_t &m, float &mo_a, float &mo_b, const uint4 *kx4,
+                                        const uint4 *ky4, unsigned long long pax2,
+                                        unsigned long long pay2, float tau) {
+  const uint4 X0 = kx4[0], Y0 = ky4[0], X1 = kx4[1], Y1 = ky4[1];
+  const uint4 X2 = kx4[2], Y2 = ky4[2], X3 = kx4[3], Y3 = ky4[3];
+  scan_pair<BIT0 + 0>(m, mo_a, mo_b, X0.x, X0.y, Y0.x, Y0.y, pax2, pay2, tau);
+  scan_pair<BIT0 + 2>(m, mo_a, mo_b, X0.z, X0.w, Y0.z, Y0.w, pax2, pay2, tau);
+  scan_pair<BIT0 + 4>(m, mo_a, mo_b, X1.x, X1.y, Y1.x, Y1.y, pax2, pay2, tau);
+  scan_pair<BIT0 + 6>(m, mo_a, mo_b, X1.z, X1.w, Y1.z, Y1.w, pax2, pay2, tau);
+  scan_pair<BIT0 + 8>(m, mo_a, mo_b, X2.x, X2.y, Y2.x, Y2.y, pax2, pay2, tau);
+  scan_pair<BIT0 + 10>(m, mo_a, mo_b, X2.z, X2.w, Y2.z, Y2.w, pax2, pay2, tau);
+  scan_pair<BIT0 + 12>(m, mo_a, mo_b, X3.x, X3.y, Y3.x, Y3.y, pax2, pay2, tau);
+  scan_pair<BIT0 + 14>(m, mo_a, mo_b, X3.z, X3.w, Y3.z, Y3.w, pax2, pay2, tau);
+}
+
 // MAXT = 320: the common geometry (EPB * N <= 320 threads, two CTAs per SM, <= 96
 // registers per thread); MAXT = 1024: one env of up to 1024 agents per CTA.
 // Branch-free top-16 of ALL candidates (packed squared-distance | id keys), 16 at a time:
 // sort16 + half-cleaner + bitonic merger on named registers (wdb_sortnet.cuh).
-__device__ __noinline__ void network_top16(float2 pa, const float2 *kp, int N, uint32_t idmask,
-                                           uint32_t *out) {
+__device__ __noinline__ void network_top16(float2 pa, const float *kx, const float *ky, int N,
+                                           uint32_t idmask, uint32_t *out) {
   uint32_t r0, r1, r2, r3, r4, r5, r6, r7, r8, r9, r10, r11, r12, r13, r14, r15;
   const uint32_t pad_key = 0x7f800000u | idmask;
 #define WDB_KEY(i)                                                                  \
   uint32_t c##i = pad_key;                                                          \
   if (base + i < N) {                                                               \
-    const float2 pb = kp[base + i];                                                 \
-    const float dx = pa.x - pb.x, dy = pa.y - pb.y;                                 \
-    c##i = (__float_as_uint(dx * dx + dy * dy) & ~idmask) | (uint32_t)(base + i);   \
+    c##i = (__float_as_uint(sqdist(pa.x, pa.y, kx[base + i], ky[base + i])) & ~idmask) \
+           | (uint32_t)(base + i);                                                  \
   }
 #define WDB_COPY(i) r##i = c##i;
   {
@@ -296,9 +352,13 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
   const int N = P.N, epb = P.epb, K = P.K;
   const int EN = epb * N;
   const int nwarps = blockDim.x / kWarp;
-  float2 *spos = reinterpret_cast<float2 *>(smem_raw);   // real positions
-  float2 *skey = spos + EN;                              // positions, dead agents = +inf
-  float *ssp = reinterpret_cast<float *>(skey + EN);
+  // selection keys: x / y of every agent as separate planes (dead agents and the padding up
+  // to a multiple of 16 = +inf), 16-byte aligned rows so the scan reads 4 candidates per load
+  const int Ne = tc_key_stride(N);
+  float *skx = reinterpret_cast<float *>(smem_raw);
+  float *sky = skx + epb * Ne;
+  float2 *spos = reinterpret_cast<float2 *>(sky + epb * Ne);   // real positions
+  float *ssp = reinterpret_cast<float *>(spos + EN);
   float *sacc = ssp + EN;
   float *sdir = sacc + EN;
   float *srew = sdir + EN;
@@ -359,6 +419,16 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
     s_rowstride[tid] = rs;
   }
   if (tid < epb) s_nalive[tid] = 0;
+  for (int i = tid; i < epb * (Ne - N); i += blockDim.x) {   // key padding: never a candidate
+    const int e = i / (Ne - N), j = N + (i - e * (Ne - N));
+    skx[e * Ne + j] = CUDART_INF_F;
+    sky[e * Ne + j] = CUDART_INF_F;
+  }
+  // last step's neighbour ids (history path): requested now, consumed after the kinematics
+  int pnr[kListLen - 2];
+#pragma unroll
+  for (int p = 0; p < kListLen - 2; p++)
+    pnr[p] = (P.use_history && active && p < K) ? P.nearest[(long long)gi * K + p] : 0;
   if (active && a == 0) {
     const int t = P.timestep[env] + 1;   // :391-393
     P.timestep[env] = t;
@@ -518,7 +588,8 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
     P.loc_x[gi] = x; P.loc_y[gi] = y; P.speed[gi] = sp;
     P.direction[gi] = dir; P.acceleration[gi] = acc; P.edge_pen[gi] = ep;
     spos[li] = make_float2(x, y);
-    skey[li] = alive ? make_float2(x, y) : make_float2(CUDART_INF_F, CUDART_INF_F);
+    skx[le * Ne + a] = alive ? x : CUDART_INF_F;
+    sky[le * Ne + a] = alive ? y : CUDART_INF_F;
     ssp[li] = sp; sacc[li] = acc; sdir[li] = dir;
     salive[li] = alive;
     if (alive) atomicAdd(&s_nalive[le], 1);
@@ -565,7 +636,7 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
         // fast path: branch-free top-16 of packed (squared distance | id) keys.  Dead
         // agents sit at +inf and sort last; self has key (0 | a).
         const float2 pa = epos[a];
-        const float2 *kp = skey + le * N;
+        const float *kx = skx + le * Ne, *ky = sky + le * Ne;
         uint32_t r0, r1, r2, r3, r4, r5, r6, r7, r8, r9, r10, r11, r12, r13, r14, r15;
         const uint32_t pad_key = 0x7f800000u | idmask;
         bool have = false;          // candidate list already complete (history path)
@@ -576,54 +647,66 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
           // ---- temporal-coherence path.  Threshold tau = the largest current squared
           // distance to last step's neighbours (any tau is safe: the result is accepted
           // only if it provably contains the K nearest, see `hist_ok`).  One pass over
-          // the candidates collects everything with s <= tau (typically K + a few) into a
-          // per-lane byte list and tracks the minimum of the rest; no sorting network runs
-          // over the 100+ candidates.
-          const int *pn = P.nearest + (long long)gi * K;
+          // the candidates marks everything with s <= tau (typically K + a few) in a
+          // 128-bit mask and tracks the minimum of the rest; no sorting network runs over
+          // the 100+ candidates.
           float tau = 0.0f;
           int seen = 0;
-          for (int p = 0; p < K; p++) {
-            int b = pn[p];
-            b = min(max(b, 0), N - 1);
-            if (b != a && ealive[b]) {
-              const float2 pb = epos[b];
-              const float dx = pa.x - pb.x, dy = pa.y - pb.y;
-              tau = fmaxf(tau, dx * dx + dy * dy);
-              seen++;
+#pragma unroll
+          for (int p = 0; p < kListLen - 2; p++) {
+            if (p < K) {
+              const int b = min(max(pnr[p], 0), N - 1);
+              if (b != a && ealive[b]) {
+                const float2 pb = epos[b];
+                tau = fmaxf(tau, sqdist(pa.x, pa.y, pb.x, pb.y));
+                seen++;
+              }
             }
           }
           // neighbours that left the game shrink the list: widen the disc accordingly
           if (seen < kk) tau *= 1.0f + 0.45f * (float)(kk - seen);
           if (seen == 0) tau = -1.0f;
-          unsigned char *lst = s_scr + (size_t)warp * P.scr_warp_bytes + lane;
-          // branch-free scan: `wp` walks the lane's column of the byte list (rows are kWarp
-          // bytes apart), clamped to the spare row kHistCap where rejected ids also land
-          unsigned char *wp = lst;
-          unsigned char *const trash = lst + kHistCap * kWarp;
-#pragma unroll 8
-          for (int b = 0; b < N; b++) {
-            const float2 pb = kp[b];
-            const float dx = pa.x - pb.x, dy = pa.y - pb.y;
-            const float sq = dx * dx + dy * dy;
-            const bool in = sq <= tau;
-            *(in ? wp : trash) = (unsigned char)b;
-            wp = in ? wp + kWarp : wp;
-            wp = wp < trash ? wp : trash;
-            m_out = in ? m_out : fminf(m_out, sq);
+          uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+          {
+            unsigned long long pax2, pay2;
+            asm("mov.b64 %0, {%1, %1};" : "=l"(pax2) : "f"(pa.x));
+            asm("mov.b64 %0, {%1, %1};" : "=l"(pay2) : "f"(pa.y));
+            const uint4 *kx4 = reinterpret_cast<const uint4 *>(kx);
+            const uint4 *ky4 = reinterpret_cast<const uint4 *>(ky);
+            float mo_a = CUDART_INF_F, mo_b = CUDART_INF_F;
+#define WDB_SCAN_WORD(W, M)                                                          \
+            if (W * 32 < N) {                                                        \
+              scan_16<0>(M, mo_a, mo_b, kx4 + W * 8, ky4 + W * 8, pax2, pay2, tau);  \
+              if (W * 32 + 16 < N)                                                   \
+                scan_16<16>(M, mo_a, mo_b, kx4 + W * 8 + 4, ky4 + W * 8 + 4, pax2, pay2, tau); \
+            }
+            WDB_SCAN_WORD(0, m0) WDB_SCAN_WORD(1, m1) WDB_SCAN_WORD(2, m2) WDB_SCAN_WORD(3, m3)
+#undef WDB_SCAN_WORD
+            m_out = fminf(mo_a, mo_b);
           }
-          // overflow (> kHistCap accepted) leaves wp pinned at the spare row: not accepted
-          const int cnt = (wp == trash) ? kHistCap + 1 : (int)(wp - lst) / kWarp;
+          const int cnt = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
           const bool hist_ok = (cnt >= kk + 1) && (cnt <= kHistCap);   // self + >= kk others
           if (hist_ok) {
-            // keys of the collected candidates (ids beyond cnt are stale bytes: clamped and
-            // masked to the pad key), sorted 16 at a time; one code instance for both halves
+            // candidate ids -> this lane's column of the per-warp byte list (rows are kWarp
+            // bytes apart), then their keys sorted 16 at a time (slots beyond cnt are stale
+            // bytes: clamped and masked to the pad key); one code instance for both halves
+            unsigned char *lst = s_scr + (size_t)warp * P.scr_warp_bytes + lane;
+            {
+              unsigned char *wp = lst;
+#define WDB_EXTRACT(M, BASE)                                                         \
+              for (uint32_t mm = M; mm; mm &= mm - 1) {                              \
+                *wp = (unsigned char)(__ffs(mm) - 1 + BASE);                         \
+                wp += kWarp;                                                         \
+              }
+              WDB_EXTRACT(m0, 0) WDB_EXTRACT(m1, 32) WDB_EXTRACT(m2, 64) WDB_EXTRACT(m3, 96)
+#undef WDB_EXTRACT
+            }
 #define WDB_HKEY(i)                                                                 \
   uint32_t c##i;                                                                    \
   {                                                                                 \
     const int b = min((int)lst[(hbase + i) * kWarp], N - 1);                        \
-    const float2 pb = kp[b];                                                        \
-    const float dx = pa.x - pb.x, dy = pa.y - pb.y;                                 \
-    const uint32_t key = (__float_as_uint(dx * dx + dy * dy) & ~idmask) | (uint32_t)b; \
+    const uint32_t key = (__float_as_uint(sqdist(pa.x, pa.y, kx[b], ky[b])) & ~idmask) \
+                         | (uint32_t)b;                                             \
     c##i = (hbase + i < cnt) ? key : pad_key;                                       \
   }
 #pragma unroll 1
@@ -657,7 +740,7 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
           // rare (first step after a reset, list over/underflow): out-of-line so that the
           // hot path stays small in the instruction cache
           uint32_t out[kListLen];
-          network_top16(pa, kp, N, idmask, out);
+          network_top16(pa, kx, ky, N, idmask, out);
           r0 = out[0]; r1 = out[1]; r2 = out[2]; r3 = out[3]; r4 = out[4]; r5 = out[5];
           r6 = out[6]; r7 = out[7]; r8 = out[8]; r9 = out[9]; r10 = out[10]; r11 = out[11];
           r12 = out[12]; r13 = out[13]; r14 = out[14]; r15 = out[15];
@@ -685,8 +768,7 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
             es[i] = CUDART_INF_F;
             if (i <= m) {
               const float2 pb = epos[R[i] & idmask];
-              const float dx = pa.x - pb.x, dy = pa.y - pb.y;
-              es[i] = dx * dx + dy * dy;
+              es[i] = sqdist(pa.x, pa.y, pb.x, pb.y);
               misordered |= !(es[i] > prev);
               prev = es[i];
             }
@@ -765,6 +847,15 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
       __syncwarp();
     }
 
+    // sorted ids -> this lane's uint16 column of the per-warp scratch (free again: the exact
+    // path is done with it), so that the feature loop below is a short runtime loop
+    uint16_t *idcol = reinterpret_cast<uint16_t *>(s_scr + (size_t)warp * P.scr_warp_bytes) + lane;
+    if (net_ok) {
+#pragma unroll
+      for (int i = 1; i < kListLen; i++)
+        if (i <= kk) idcol[(i - 1) * kWarp] = (uint16_t)(R[i] & idmask);
+    }
+
     if (active) {
       float *orow = P.stage_obs ? (s_tile + s_rowbase[a] + le * s_rowstride[a])
                                 : (P.obs + (long long)gi * F);
@@ -787,40 +878,23 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
         // (x / vnorm with vnorm == 1.0f -- max_speed 1 -- is the identity: skipping the
         //  IEEE division also avoids its slow path, which a zero numerator always takes)
 #define WDB_FEATURES(UNIT)                                                          \
-        _Pragma("unroll")                                                           \
-        for (int p = 0; p < kListLen - 1; p++) {                                    \
-          if (p < kk) {                                                             \
-            const int b = net_ok ? (int)(R[p + 1] & idmask) : gids[p];              \
-            nn[p] = b;                                          /* :202-211 */      \
-            const int lb = le * N + b;                          /* :214-250 */      \
-            const float2 pb = epos[b];                                              \
-            orow[0 * K + p] = div_by_const_f64(pb.x - pa.x, diag, inv_diag);        \
-            orow[1 * K + p] = div_by_const_f64(pb.y - pa.y, diag, inv_diag);        \
-            const float dsp = ssp[lb] - spa, dac = sacc[lb] - acca;                 \
-            orow[2 * K + p] = UNIT ? dsp : dsp / vnorm;                             \
-            orow[3 * K + p] = UNIT ? dac : dac / vnorm;                             \
-            orow[4 * K + p] = div_by_two_pi(sdir[lb] - dira, two_pi, inv_two_pi);   \
-            orow[5 * K + p] = stype[b];                                             \
-            orow[6 * K + p] = ealive[b];                                            \
-          }                                                                         \
+        _Pragma("unroll 2")                                                         \
+        for (int p = 0; p < kk; p++) {                                              \
+          const int b = net_ok ? (int)idcol[p * kWarp] : gids[p];                   \
+          nn[p] = b;                                            /* :202-211 */      \
+          const int lb = le * N + b;                            /* :214-250 */      \
+          const float2 pb = epos[b];                                                \
+          orow[0 * K + p] = div_by_const_f64(pb.x - pa.x, diag, inv_diag);          \
+          orow[1 * K + p] = div_by_const_f64(pb.y - pa.y, diag, inv_diag);          \
+          const float dsp = ssp[lb] - spa, dac = sacc[lb] - acca;                   \
+          orow[2 * K + p] = UNIT ? dsp : dsp / vnorm;                               \
+          orow[3 * K + p] = UNIT ? dac : dac / vnorm;                               \
+          orow[4 * K + p] = div_by_two_pi(sdir[lb] - dira, two_pi, inv_two_pi);     \
+          orow[5 * K + p] = stype[b];                                               \
+          orow[6 * K + p] = ealive[b];                                              \
         }
         if (unit_v) { WDB_FEATURES(true) } else { WDB_FEATURES(false) }
 #undef WDB_FEATURES
-        if (!net_ok) {
-          for (int p = kListLen - 1; p < kk; p++) {
-            const int b = gids[p];
-            nn[p] = b;
-            const int lb = le * N + b;
-            const float2 pb = epos[b];
-            orow[0 * K + p] = div_by_const_f64(pb.x - pa.x, diag, inv_diag);
-            orow[1 * K + p] = div_by_const_f64(pb.y - pa.y, diag, inv_diag);
-            orow[2 * K + p] = static_cast<float>(ssp[lb] - spa) / vnorm;
-            orow[3 * K + p] = static_cast<float>(sacc[lb] - acca) / vnorm;
-            orow[4 * K + p] = div_by_two_pi(sdir[lb] - dira, two_pi, inv_two_pi);
-            orow[5 * K + p] = stype[b];
-            orow[6 * K + p] = ealive[b];
-          }
-        }
         orow[7 * K] = static_cast<float>(t_env) / P.episode_length;   // :251-253
       }
     }
@@ -1093,10 +1167,13 @@ int plan_launch(TcParams &P, const FusedParams *Q, bool have_gscratch, LaunchPla
   const int F = 7 * K + 1;
   const size_t base = tc_small_bytes(epb, N);
   // per-warp scratch: exact-path lists (8 B per agent) and/or the history byte list
-  P.use_history = (g_tc_history && !P.use_full_obs && N <= 256 && K + 2 <= kListLen) ? 1 : 0;
+  P.use_history = (g_tc_history && !P.use_full_obs && N <= 128 && K + 2 <= kListLen) ? 1 : 0;
   size_t warp_bytes = 8ull * N;
   const size_t hist_bytes = (size_t)(kHistCap + 1) * kWarp;
   if (P.use_history && hist_bytes > warp_bytes) warp_bytes = hist_bytes;
+  // sorted neighbour ids of every lane (uint16 columns) for the feature loop
+  const size_t id_bytes = (!P.use_full_obs && K + 2 <= kListLen) ? (kListLen - 1) * kWarp * 2 : 0;
+  if (id_bytes > warp_bytes) warp_bytes = id_bytes;
   warp_bytes = (warp_bytes + 15) & ~(size_t)15;
   const size_t scr = warp_bytes * nwarps;
   size_t tile_obs = P.use_full_obs ? 0 : sizeof(float) * (size_t)epb * N * F;
@@ -1110,6 +1187,7 @@ int plan_launch(TcParams &P, const FusedParams *Q, bool have_gscratch, LaunchPla
   if (P.scratch_in_smem && base + scr > kMaxSmem) return (int)cudaErrorInvalidValue;
   if (!P.scratch_in_smem) {
     warp_bytes = P.use_history ? ((hist_bytes + 15) & ~(size_t)15) : 0;
+    if (id_bytes > warp_bytes) warp_bytes = id_bytes;
   }
   P.scr_warp_bytes = (int)warp_bytes;
   size_t smem = base + warp_bytes * nwarps;
