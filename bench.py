@@ -328,6 +328,8 @@ def main():
                     help="run the policy forward through torch/cuBLAS instead of the fused "
                          "tcgen05 kernel (wdb_mlp_policy_forward)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--cta-threads", type=int, default=0,
+                    help="A/B switch: thread budget of one tag_continuous CTA (wdb_set_option)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -346,6 +348,8 @@ def main():
 
     from warp_drive_b200 import lib as wlib
 
+    if args.cta_threads:
+        wlib.check(wlib.load().wdb_set_option(b"tc_cta_threads", args.cta_threads))
     K = args.steps
     W = max(3, args.warmup)
     # the rollout is captured as CUDA graphs of T timesteps; T divides K

@@ -15,6 +15,11 @@ try:
 except Exception as e:
     print("bench parse failed", e); print(open("gpurun_out/bench_$TAG.err").read()[-3000:])
 PY
+for CT in 224 128; do
+  timeout 300 python bench.py --steps 100 --warmup 20 --skip-cpu-baseline --cta-threads $CT > gpurun_out/bench_${TAG}_ct$CT.json 2>/dev/null
+  python -c "
+import json; d=json.loads(open('gpurun_out/bench_${TAG}_ct$CT.json').read().strip().splitlines()[-1]); print('CT$CT', d['value'], d['ms_per_step'], d['roofline']['kernel_ms'])"
+done
 timeout 300 ncu --set full --import-source on --clock-control none -k regex:tag_continuous_kernel -s 30 -c 1 \
   -o gpurun_out/prof_fused_$TAG -f python bench.py --steps 3 --warmup 3 --skip-cpu-baseline > gpurun_out/ncu_fused_$TAG.log 2>&1
 timeout 300 ncu --set full --import-source on --clock-control none -k regex:mlp_forward_kernel -s 4 -c 1 \

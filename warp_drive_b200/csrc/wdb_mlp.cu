@@ -32,7 +32,7 @@ namespace {
 
 constexpr int kTileM = 128;
 constexpr int kThreads = 256;
-constexpr int kPrefetch = 48;   // fp32 obs values per thread held across a tile
+constexpr int kTasks = 6;       // A-tile build tasks (8 fp32 obs values each) per thread held across a tile
 constexpr int kTmemCols = 512;
 constexpr int kColD = 0;      // accumulator columns [0, 256)
 constexpr int kColH = 256;    // packed bf16 hidden activations [256, 384)
@@ -130,16 +130,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
-        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
-        "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
@@ -154,6 +144,23 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<const uint32_t *>(&h);
 }
 
+// (lo + b_lo, hi + b_hi) -> ReLU -> packed bf16x2: one FADD2 + one F2FP.RELU per 2 columns
+__device__ __forceinline__ uint32_t bias_relu_pack(uint32_t lo, uint32_t hi, float b_lo,
+                                                   float b_hi) {
+  uint32_t out;
+  asm("{\n\t"
+      ".reg .b64 v, b, s;\n\t"
+      ".reg .f32 x, y;\n\t"
+      "mov.b64 v, {%1, %2};\n\t"
+      "mov.b64 b, {%3, %4};\n\t"
+      "add.rn.f32x2 s, v, b;\n\t"
+      "mov.b64 {x, y}, s;\n\t"
+      "cvt.rn.relu.bf16x2.f32 %0, y, x;\n\t"
+      "}"
+      : "=r"(out) : "r"(lo), "r"(hi), "f"(b_lo), "f"(b_hi));
+  return out;
+}
+
 // hidden epilogue: D[lane, c0..c1) (+bias, ReLU) -> packed bf16 into TMEM columns kColH + c/2
 __device__ __forceinline__ void hidden_epilogue(uint32_t tmem_lane_base, const float *bias,
                                                 int c0, int c1) {
@@ -164,12 +171,8 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t tmem_lane_base, const f
 #pragma unroll
     for (int i = 0; i < 8; i++) {
       const float4 b = *reinterpret_cast<const float4 *>(bias + c + 4 * i);   // broadcast LDS.128
-      const float x0 = fmaxf(__uint_as_float(v[4 * i]) + b.x, 0.0f);
-      const float x1 = fmaxf(__uint_as_float(v[4 * i + 1]) + b.y, 0.0f);
-      const float x2 = fmaxf(__uint_as_float(v[4 * i + 2]) + b.z, 0.0f);
-      const float x3 = fmaxf(__uint_as_float(v[4 * i + 3]) + b.w, 0.0f);
-      out[2 * i] = pack_bf16(x0, x1);
-      out[2 * i + 1] = pack_bf16(x2, x3);
+      out[2 * i] = bias_relu_pack(v[4 * i], v[4 * i + 1], b.x, b.y);
+      out[2 * i + 1] = bias_relu_pack(v[4 * i + 2], v[4 * i + 3], b.z, b.w);
     }
     tmem_st16(tmem_lane_base + kColH + c / 2, out);
   }
@@ -232,18 +235,43 @@ mlp_forward_kernel(const unsigned char *__restrict__ blob, const float *__restri
   }
 
   const long long n_tiles = (rows + kTileM - 1) / kTileM;
-  const int batch_elems = kThreads * kPrefetch;
-  const bool single_batch = kTileM * F <= batch_elems;    // whole tile fits the register prefetch
-  const int dr = kThreads / F, dk = kThreads - dr * F;    // element index += kThreads in (r, k) form
-  float pf[kPrefetch];
-  auto load_batch = [&](long long tile, int base) {
+  // A-tile build: a warp task = 8 rows x 4 k-chunks (chunk = 8 consecutive k = one 16-byte
+  // row of a core matrix): lane -> (row = 8 g + lane % 8, chunk = 4 q + lane / 8), so the 8
+  // global loads of a task read 128 contiguous bytes of each of 8 obs rows and the one
+  // 16-byte shared store per lane is bank-conflict free.  16 * ncg tasks per tile, dealt
+  // round-robin to the 8 warps; up to kTasks per thread live in registers (pf).
+  const int nchunk = K1 / 8, ncg = (nchunk + 3) / 4;
+  const int tasks_per_warp = (16 * ncg + 7) / 8;
+  const bool single_batch = tasks_per_warp <= kTasks;     // whole tile fits the register prefetch
+  float pf[kTasks * 8];
+  auto load_batch = [&](long long tile, int batch) {
     const long long r0 = tile * kTileM;
-    const int total = (int)min((long long)kTileM, rows - r0) * F - base;
-    const float *src = obs + r0 * F + base;
+    const int valid = (int)min((long long)kTileM, rows - r0);
 #pragma unroll
-    for (int j = 0; j < kPrefetch; j++) {
-      const int i = tid + j * kThreads;
-      pf[j] = i < total ? __ldg(src + i) : 0.0f;
+    for (int j = 0; j < kTasks; j++) {
+      const int wt = warp + 8 * (j + kTasks * batch);
+      const int g = wt / ncg, q = wt - g * ncg;
+      const int r = 8 * g + (lane & 7), c = 4 * q + (lane >> 3);
+      const bool on = (g < 16) && (c < nchunk) && (r < valid);
+      const float *src = obs + (r0 + r) * F + 8 * c;
+#pragma unroll
+      for (int i = 0; i < 8; i++) pf[8 * j + i] = (on && 8 * c + i < F) ? __ldg(src + i) : 0.0f;
+    }
+  };
+  auto store_batch = [&](int batch) {
+#pragma unroll
+    for (int j = 0; j < kTasks; j++) {
+      const int wt = warp + 8 * (j + kTasks * batch);
+      const int g = wt / ncg, q = wt - g * ncg;
+      const int c = 4 * q + (lane >> 3);
+      if (g < 16 && c < nchunk) {
+        uint4 o;
+        o.x = pack_bf16(pf[8 * j + 0], pf[8 * j + 1]);
+        o.y = pack_bf16(pf[8 * j + 2], pf[8 * j + 3]);
+        o.z = pack_bf16(pf[8 * j + 4], pf[8 * j + 5]);
+        o.w = pack_bf16(pf[8 * j + 6], pf[8 * j + 7]);
+        *reinterpret_cast<uint4 *>(s_a + g * (K1 / 8) * 128 + c * 128 + (lane & 7) * 16) = o;
+      }
     }
   };
   if (single_batch && (long long)blockIdx.x < n_tiles) load_batch(blockIdx.x, 0);
@@ -263,27 +291,15 @@ mlp_forward_kernel(const unsigned char *__restrict__ blob, const float *__restri
     const long long r0 = tile * kTileM;
     const int valid = (int)min((long long)kTileM, rows - r0);
 
-    // ---- obs tile -> bf16, canonical K-major layout
-    {
-      uint4 *z = reinterpret_cast<uint4 *>(s_a);          // K padding / missing rows = 0
-      for (int i = tid; i < kTileM * K1 * 2 / 16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
-      __syncthreads();
-      const int total = valid * F;
-      __nv_bfloat16 *a16 = reinterpret_cast<__nv_bfloat16 *>(s_a);
-      for (int base = 0; base < total; base += batch_elems) {
-        if (!single_batch) load_batch(tile, base);
-        int r = (base + tid) / F, k = (base + tid) - r * F;
-#pragma unroll
-        for (int j = 0; j < kPrefetch; j++) {
-          if (base + tid + j * kThreads < total) {
-            const int off = (r >> 3) * (int)(sbo_a / 2) + (k >> 3) * 64 + (r & 7) * 8 + (k & 7);
-            a16[off] = __float2bfloat16_rn(pf[j]);
-          }
-          r += dr; k += dk;
-          if (k >= F) { k -= F; r += 1; }
-        }
+    // ---- obs tile -> bf16, canonical K-major layout (K padding and missing rows = 0)
+    if (single_batch) {
+      store_batch(0);
+      if (tile + gridDim.x < n_tiles) load_batch(tile + gridDim.x, 0);   // prefetch
+    } else {
+      for (int batch = 0; batch * kTasks < tasks_per_warp; batch++) {
+        load_batch(tile, batch);
+        store_batch(batch);
       }
-      if (single_batch && tile + gridDim.x < n_tiles) load_batch(tile + gridDim.x, 0);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
@@ -336,25 +352,33 @@ mlp_forward_kernel(const unsigned char *__restrict__ blob, const float *__restri
       const int row = quad * 32 + lane;                    // TMEM lane == row of the tile
       uint32_t v[32];
       tmem_ld32(tmem_lane + kColD + cbase, v);             // columns past N3 hold stale data: unused
+      // logits pre-scaled by log2(e): softmax = 2^(l - max) / sum; loops stop at cnt
+      // (warp-uniform), so the registers stay statically indexed
+      constexpr float kLog2e = 1.4426950408889634f;
       float lg[32];
       float m = -CUDART_INF_F, value = 0.0f;
 #pragma unroll
       for (int i = 0; i < 32; i++) {
-        lg[i] = __uint_as_float(v[i]) + s_b3[min(cbase + i, N3 - 1)];
+        if (i > cnt) break;
+        const float x = __uint_as_float(v[i]) + s_b3[cbase + i];
+        lg[i] = x * kLog2e;
         if (i < cnt) m = fmaxf(m, lg[i]);
-        if (i == cnt) value = lg[i];
+        else value = x;
       }
       float z = 0.0f;
 #pragma unroll
       for (int i = 0; i < 32; i++) {
-        lg[i] = i < cnt ? __expf(lg[i] - m) : 0.0f;
+        if (i >= cnt) break;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(lg[i]) : "f"(lg[i] - m));
         z += lg[i];
       }
       const float inv = 1.0f / z;
       float *dst = (half ? s_p1 : s_p0) + row * cnt;
 #pragma unroll
-      for (int i = 0; i < 32; i++)
-        if (i < cnt) dst[i] = lg[i] * inv;
+      for (int i = 0; i < 32; i++) {
+        if (i >= cnt) break;
+        dst[i] = lg[i] * inv;
+      }
       if (half) s_v[row] = value;
     }
     fence_before();

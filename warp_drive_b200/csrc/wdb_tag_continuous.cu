@@ -238,6 +238,27 @@ __device__ __forceinline__ float div_by_const_f64(float d, double c, double inv_
   return (float)prod;
 }
 
+// Inclusive float32 prefix sum of one probability row (same left-to-right additions as
+// core/random.cu:62-72) followed by the reference's binary search.  Rows of <= 32 actions
+// are summed in registers (independent loads, one dependent FADD chain) instead of a
+// load-add-store chain through shared memory.
+__device__ __forceinline__ int sample_row(float *row, int A, float u) {
+  if (A <= 32) {
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = i < A ? row[i] : 0.0f;
+#pragma unroll
+    for (int i = 1; i < 32; i++) v[i] = v[i] + v[i - 1];
+#pragma unroll
+    for (int i = 1; i < 32; i++)
+      if (i < A) row[i] = v[i];
+  } else {
+    float c = row[0];
+    for (int i = 1; i < A; i++) { c = row[i] + c; row[i] = c; }
+  }
+  return search_index(row, 1, u, A - 1);
+}
+
 // Squared distance with a FIXED operation order (dx * dx rounded, then fused dy * dy + .):
 // the history scan (packed FMUL2 / FFMA2), its threshold tau, the sort keys and the exact
 // check must all see the same float for the same pair of agents.
@@ -535,18 +556,8 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
 #pragma unroll
       for (int p = 0; p < kMaxPolicies; p++)
         if (p == pol) { np = Q.policy_size[p]; o0 = p_off0[p]; o1 = p_off1[p]; }
-      {
-        float *row = s_tile + o0 + (le * np + slot) * Q.A0;
-        float c = row[0];
-        for (int i = 1; i < Q.A0; i++) { c = row[i] + c; row[i] = c; }
-        act0 = search_index(row, 1, u0, Q.A0 - 1);
-      }
-      {
-        float *row = s_tile + o1 + (le * np + slot) * Q.A1;
-        float c = row[0];
-        for (int i = 1; i < Q.A1; i++) { c = row[i] + c; row[i] = c; }
-        act1 = search_index(row, 1, u1, Q.A1 - 1);
-      }
+      act0 = sample_row(s_tile + o0 + (le * np + slot) * Q.A0, Q.A0, u0);
+      act1 = sample_row(s_tile + o1 + (le * np + slot) * Q.A1, Q.A1, u1);
       if (Q.actions_out) *reinterpret_cast<int2 *>(Q.actions_out + 2ll * gi) = make_int2(act0, act1);
       if (Q.actions_head0) Q.actions_head0[gi] = act0;
       if (Q.actions_head1) Q.actions_head1[gi] = act1;
@@ -987,6 +998,26 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
     }
   }
 
+  // bookkeeping words needed after the reward phase: requested now so that their latency
+  // hides behind it
+  int done_prev = 0, steps_prev = 0;
+  float run_prev = 0.0f;
+  long long pi_slot = 0;
+  if (FUSED && active) {
+    if (a == 0) {
+      done_prev = P.done[env];
+      if (Q.step_running_sum) steps_prev = Q.step_running_sum[env];
+    }
+    const int pol = Q.agent_policy[a], slot = Q.agent_slot[a];
+#pragma unroll
+    for (int p = 0; p < kMaxPolicies; p++) {
+      if (p == pol) {
+        pi_slot = (long long)env * Q.policy_size[p] + slot;
+        if (Q.reward_running_sum[p]) run_prev = Q.reward_running_sum[p][pi_slot];
+      }
+    }
+  }
+
   // ------------------------------------------------------------------ rewards / tags
   float r = active ? srew[li] : 0.0f;
   const bool is_runner = active && (stype[a] == 0);
@@ -1005,9 +1036,13 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
     }
     const float guard = P.margin * 1.001f;
     if (min_s <= guard * guard) {
+      // a tagger outside the guard band is farther than the margin, so it can only be the
+      // arg-min when nobody is within the margin -- and then the arg-min is not used
       for (int q = 0; q < ntag; q++) {
         const int b = stag[q];
         const float2 pb = epos[b];
+        const float dx = pa.x - pb.x, dy = pa.y - pb.y;
+        if (dx * dx + dy * dy > guard * guard) continue;
         const float dist = exact_distance(pa.x, pa.y, pb.x, pb.y);
         if (dist < min_dist) { min_dist = dist; nearest_tagger = b; }
       }
@@ -1034,14 +1069,14 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
       P.num_runners[env] = nr;
       if (FUSED) {
         // done is sticky in the reference (only the reset kernel clears it)
-        const int d = done_now | (P.done[env] > 0 ? 1 : 0);
+        const int d = done_now | (done_prev > 0 ? 1 : 0);
         s_done[le] = d;
         if (Q.done_batch) Q.done_batch[env] = d;
         const bool will_reset = d && Q.do_reset;
         if (!will_reset) { if (d) P.done[env] = 1; }
         else { P.done[env] = 0; P.timestep[env] = 0; }
         if (Q.step_running_sum) {
-          const int steps = Q.step_running_sum[env] + 1;
+          const int steps = steps_prev + 1;
           if (d) {
             if (Q.episodic_step_sum) atomicAdd(Q.episodic_step_sum, (unsigned long long)steps);
             if (Q.num_completed) atomicAdd(Q.num_completed, 1ull);
@@ -1058,15 +1093,15 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
   if (FUSED) {
     __syncthreads();   // s_done visible
     if (active) {
-      const int pol = Q.agent_policy[a], slot = Q.agent_slot[a];
+      const int pol = Q.agent_policy[a];
       const int d = s_done[le];
 #pragma unroll
       for (int p = 0; p < kMaxPolicies; p++) {
         if (p == pol) {
-          const long long pi = (long long)env * Q.policy_size[p] + slot;
+          const long long pi = pi_slot;
           if (Q.rewards_batch[p]) Q.rewards_batch[p][pi] = r;
           if (Q.reward_running_sum[p]) {
-            const float run = Q.reward_running_sum[p][pi] + r;
+            const float run = run_prev + r;
             if (d) {
               // one atomic per agent of a finished env (rare: once per episode)
               if (Q.episodic_reward_sum[p]) atomicAdd(Q.episodic_reward_sum[p], run);
@@ -1151,6 +1186,7 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
 }
 
 int g_tc_history = 1;   // wdb_set_option("tc_history", 0/1)
+int g_tc_threads = 320; // wdb_set_option("tc_cta_threads", n): thread budget of one CTA (<= 320)
 
 struct LaunchPlan {
   int epb, block, grid;
@@ -1160,7 +1196,7 @@ struct LaunchPlan {
 // shared-memory carve-up; must mirror the kernel prologue
 int plan_launch(TcParams &P, const FusedParams *Q, bool have_gscratch, LaunchPlan &plan) {
   const int N = P.N, K = P.K;
-  int epb = N >= 320 ? 1 : 320 / N;
+  int epb = N >= g_tc_threads ? 1 : g_tc_threads / N;
   if (epb > P.n_envs) epb = P.n_envs;
   const int block = round_up(epb * N, 32);
   const int nwarps = block / 32;
@@ -1278,12 +1314,18 @@ int fill_params(TcParams &P, int n_envs, int n_agents, float *loc_x, float *loc_
 
 WDB_API int wdb_set_option(const char *name, int value) {
   if (!name) return (int)cudaErrorInvalidValue;
-  const char *want = "tc_history";
-  int i = 0;
-  for (; want[i] && name[i] == want[i]; i++) {}
-  if (want[i] || name[i]) return (int)cudaErrorInvalidValue;
-  g_tc_history = value ? 1 : 0;
-  return 0;
+  auto is = [&](const char *want) {
+    int i = 0;
+    for (; want[i] && name[i] == want[i]; i++) {}
+    return !want[i] && !name[i];
+  };
+  if (is("tc_history")) { g_tc_history = value ? 1 : 0; return 0; }
+  if (is("tc_cta_threads")) {
+    if (value < 32 || value > 320) return (int)cudaErrorInvalidValue;
+    g_tc_threads = value;
+    return 0;
+  }
+  return (int)cudaErrorInvalidValue;
 }
 
 WDB_API int wdb_tag_continuous_step(
