@@ -15,7 +15,7 @@ try:
 except Exception as e:
     print("bench parse failed", e); print(open("gpurun_out/bench_$TAG.err").read()[-3000:])
 PY
-for CT in 224 128; do
+for CT in; do
   timeout 300 python bench.py --steps 100 --warmup 20 --skip-cpu-baseline --cta-threads $CT > gpurun_out/bench_${TAG}_ct$CT.json 2>/dev/null
   python -c "
 import json; d=json.loads(open('gpurun_out/bench_${TAG}_ct$CT.json').read().strip().splitlines()[-1]); print('CT$CT', d['value'], d['ms_per_step'], d['roofline']['kernel_ms'])"

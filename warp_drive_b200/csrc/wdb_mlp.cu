@@ -35,7 +35,7 @@ constexpr int kThreads = 256;
 constexpr int kTasks = 6;       // A-tile build tasks (8 fp32 obs values each) per thread held across a tile
 constexpr int kTmemCols = 512;
 constexpr int kColD = 0;      // accumulator columns [0, 256)
-constexpr int kColH = 256;    // packed bf16 hidden activations [256, 384)
+constexpr int kColH = 256;    // packed bf16 hidden activations: layer 1 -> [256, 384), layer 2 -> [384, 512)
 
 struct MlpHeader {            // start of the packed weight blob (device memory)
   int F, K1, H, A0, A1, N3;   // input features, padded K of layer 1, hidden width, heads, padded N3
@@ -144,6 +144,16 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<const uint32_t *>(&h);
 }
 
+// predicated read-only load (0 when off) -- written in PTX so that no select depends on the
+// loaded value: the prefetch must not wait for its own loads
+__device__ __forceinline__ float ldg_if(const float *p, bool on) {
+  float v;
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\tmov.f32 %0, 0f00000000;\n\t"
+               "@p ld.global.nc.f32 %0, [%1];\n\t}"
+               : "=f"(v) : "l"(p), "r"((int)on));
+  return v;
+}
+
 // (lo + b_lo, hi + b_hi) -> ReLU -> packed bf16x2: one FADD2 + one F2FP.RELU per 2 columns
 __device__ __forceinline__ uint32_t bias_relu_pack(uint32_t lo, uint32_t hi, float b_lo,
                                                    float b_hi) {
@@ -162,9 +172,9 @@ __device__ __forceinline__ uint32_t bias_relu_pack(uint32_t lo, uint32_t hi, flo
 }
 
 // hidden epilogue: D[lane, c0..c1) (+bias, ReLU) -> packed bf16 into TMEM columns kColH + c/2
-__device__ __forceinline__ void hidden_epilogue(uint32_t tmem_lane_base, const float *bias,
-                                                int c0, int c1) {
-  for (int c = c0; c < c1; c += 32) {
+__device__ __forceinline__ void hidden_epilogue(uint32_t tmem_lane_base, uint32_t col_h,
+                                                const float *bias, int c0, int c1) {
+  for (int c = c0; c < c1; c += 64) {      // the two column halves of a quadrant interleave
     uint32_t v[32];
     tmem_ld32(tmem_lane_base + kColD + c, v);
     uint32_t out[16];
@@ -174,7 +184,7 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t tmem_lane_base, const f
       out[2 * i] = bias_relu_pack(v[4 * i], v[4 * i + 1], b.x, b.y);
       out[2 * i + 1] = bias_relu_pack(v[4 * i + 2], v[4 * i + 3], b.z, b.w);
     }
-    tmem_st16(tmem_lane_base + kColH + c / 2, out);
+    tmem_st16(tmem_lane_base + col_h + c / 2, out);
   }
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
@@ -201,16 +211,17 @@ mlp_forward_kernel(const unsigned char *__restrict__ blob, const float *__restri
   unsigned char *s_a = s_w + ((w_bytes + 127) & ~127);   // A tile (layer 1) / output staging
   const int a_bytes = max(kTileM * K1 * 2, kTileM * (A0 + A1 + 1) * 4);
   unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(s_a + ((a_bytes + 15) & ~15));
-  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 2);
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 3);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quad = warp & 3, half = warp >> 2;
   const uint32_t bar_w = smem_addr(&s_bar[0]);           // weights landed
-  const uint32_t bar_mma = smem_addr(&s_bar[1]);         // MMA group done
+  const uint32_t bar_mma[2] = {smem_addr(&s_bar[1]), smem_addr(&s_bar[2])};   // MMA N-group done
 
   if (tid == 0) {
     mbar_init(bar_w, 1);
-    mbar_init(bar_mma, 1);
+    mbar_init(bar_mma[0], 1);
+    mbar_init(bar_mma[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -255,7 +266,7 @@ mlp_forward_kernel(const unsigned char *__restrict__ blob, const float *__restri
       const bool on = (g < 16) && (c < nchunk) && (r < valid);
       const float *src = obs + (r0 + r) * F + 8 * c;
 #pragma unroll
-      for (int i = 0; i < 8; i++) pf[8 * j + i] = (on && 8 * c + i < F) ? __ldg(src + i) : 0.0f;
+      for (int i = 0; i < 8; i++) pf[8 * j + i] = ldg_if(src + i, on && 8 * c + i < F);
     }
   };
   auto store_batch = [&](int batch) {
@@ -278,11 +289,17 @@ mlp_forward_kernel(const unsigned char *__restrict__ blob, const float *__restri
 
   mbar_wait(bar_w, 0);
 
-  const uint32_t idesc_h = make_idesc(kTileM, H);
+  // hidden layers run as `nsplit` N-groups of GW columns, each with its own commit barrier:
+  // the epilogue of group 0 overlaps the MMAs of group 1.  Layer 1 packs its activations into
+  // TMEM columns [256, 384), layer 2 into [384, 512), so layer 2's second group may still
+  // read layer 1's activations while the first group's epilogue writes layer 2's.
+  const int nsplit = (H % 128 == 0) ? 2 : 1;
+  const int GW = H / nsplit;
+  const uint32_t idesc_h = make_idesc(kTileM, GW);
   const uint32_t idesc_o = make_idesc(kTileM, N3);
   const uint32_t sbo_a = (uint32_t)(K1 / 8) * 128u;       // A tile / W1: K1/8 core matrices per row group
   const uint32_t sbo_h = (uint32_t)(H / 8) * 128u;        // W2 / W3: H/8 core matrices per row group
-  uint32_t mma_phase = 0;
+  uint32_t mma_phase[2] = {0, 0};
   float *s_p0 = reinterpret_cast<float *>(s_a);
   float *s_p1 = s_p0 + kTileM * A0;
   float *s_v = s_p1 + kTileM * A1;
@@ -294,7 +311,6 @@ mlp_forward_kernel(const unsigned char *__restrict__ blob, const float *__restri
     // ---- obs tile -> bf16, canonical K-major layout (K padding and missing rows = 0)
     if (single_batch) {
       store_batch(0);
-      if (tile + gridDim.x < n_tiles) load_batch(tile + gridDim.x, 0);   // prefetch
     } else {
       for (int batch = 0; batch * kTasks < tasks_per_warp; batch++) {
         load_batch(tile, batch);
@@ -308,14 +324,22 @@ mlp_forward_kernel(const unsigned char *__restrict__ blob, const float *__restri
     if (tid == 0) {
       fence_after();
       const uint32_t a0 = smem_addr(s_a), b0 = smem_addr(s_w);
-      for (int kk = 0; kk < K1 / 16; kk++)
-        mma_ss(tmem_base + kColD, make_desc(a0 + kk * 256, sbo_a), make_desc(b0 + kk * 256, sbo_a),
-               idesc_h, kk > 0);
-      mma_commit(bar_mma);
+      for (int g = 0; g < nsplit; g++) {
+        const uint32_t bg = b0 + (uint32_t)(g * GW / 8) * sbo_a;     // W1 rows g*GW ..
+        for (int kk = 0; kk < K1 / 16; kk++)
+          mma_ss(tmem_base + kColD + g * GW, make_desc(a0 + kk * 256, sbo_a),
+                 make_desc(bg + kk * 256, sbo_a), idesc_h, kk > 0);
+        mma_commit(bar_mma[g]);
+      }
     }
-    mbar_wait(bar_mma, mma_phase); mma_phase ^= 1;
-    fence_after();
-    hidden_epilogue(tmem_lane, s_b1, half * (H / 2), (half + 1) * (H / 2));
+    // prefetch the next tile's obs into registers (after the MMA issue, so that the queueing
+    // of ~12k loads per CTA does not delay the tensor core)
+    if (single_batch && tile + gridDim.x < n_tiles) load_batch(tile + gridDim.x, 0);
+    for (int g = 0; g < nsplit; g++) {
+      mbar_wait(bar_mma[g], mma_phase[g]); mma_phase[g] ^= 1;
+      fence_after();
+      hidden_epilogue(tmem_lane, kColH, s_b1, g * GW + 32 * half, (g + 1) * GW);
+    }
     fence_before();
     __syncthreads();
 
@@ -323,14 +347,19 @@ mlp_forward_kernel(const unsigned char *__restrict__ blob, const float *__restri
     if (tid == 0) {
       fence_after();
       const uint32_t b0 = smem_addr(s_w2);
-      for (int kk = 0; kk < H / 16; kk++)
-        mma_ts(tmem_base + kColD, tmem_base + kColH + kk * 8, make_desc(b0 + kk * 256, sbo_h),
-               idesc_h, kk > 0);
-      mma_commit(bar_mma);
+      for (int g = 0; g < nsplit; g++) {
+        const uint32_t bg = b0 + (uint32_t)(g * GW / 8) * sbo_h;
+        for (int kk = 0; kk < H / 16; kk++)
+          mma_ts(tmem_base + kColD + g * GW, tmem_base + kColH + kk * 8,
+                 make_desc(bg + kk * 256, sbo_h), idesc_h, kk > 0);
+        mma_commit(bar_mma[g]);
+      }
     }
-    mbar_wait(bar_mma, mma_phase); mma_phase ^= 1;
-    fence_after();
-    hidden_epilogue(tmem_lane, s_b2, half * (H / 2), (half + 1) * (H / 2));
+    for (int g = 0; g < nsplit; g++) {
+      mbar_wait(bar_mma[g], mma_phase[g]); mma_phase[g] ^= 1;
+      fence_after();
+      hidden_epilogue(tmem_lane, kColH + 128, s_b2, g * GW + 32 * half, (g + 1) * GW);
+    }
     fence_before();
     __syncthreads();
 
@@ -339,11 +368,11 @@ mlp_forward_kernel(const unsigned char *__restrict__ blob, const float *__restri
       fence_after();
       const uint32_t b0 = smem_addr(s_w3);
       for (int kk = 0; kk < H / 16; kk++)
-        mma_ts(tmem_base + kColD, tmem_base + kColH + kk * 8, make_desc(b0 + kk * 256, sbo_h),
+        mma_ts(tmem_base + kColD, tmem_base + kColH + 128 + kk * 8, make_desc(b0 + kk * 256, sbo_h),
                idesc_o, kk > 0);
-      mma_commit(bar_mma);
+      mma_commit(bar_mma[0]);
     }
-    mbar_wait(bar_mma, mma_phase); mma_phase ^= 1;
+    mbar_wait(bar_mma[0], mma_phase[0]); mma_phase[0] ^= 1;
     fence_after();
 
     // ---- output epilogue: bias, softmax of this half's head (+ value) -> staging
@@ -356,22 +385,25 @@ mlp_forward_kernel(const unsigned char *__restrict__ blob, const float *__restri
       // (warp-uniform), so the registers stay statically indexed
       constexpr float kLog2e = 1.4426950408889634f;
       float lg[32];
-      float m = -CUDART_INF_F, value = 0.0f;
+      float mx[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+      float value = 0.0f;
 #pragma unroll
       for (int i = 0; i < 32; i++) {
         if (i > cnt) break;
         const float x = __uint_as_float(v[i]) + s_b3[cbase + i];
         lg[i] = x * kLog2e;
-        if (i < cnt) m = fmaxf(m, lg[i]);
+        if (i < cnt) mx[i & 3] = fmaxf(mx[i & 3], lg[i]);
         else value = x;
       }
-      float z = 0.0f;
+      const float m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      float zz[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
       for (int i = 0; i < 32; i++) {
         if (i >= cnt) break;
         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(lg[i]) : "f"(lg[i] - m));
-        z += lg[i];
+        zz[i & 3] += lg[i];
       }
+      const float z = (zz[0] + zz[1]) + (zz[2] + zz[3]);
       const float inv = 1.0f / z;
       float *dst = (half ? s_p1 : s_p0) + row * cnt;
 #pragma unroll

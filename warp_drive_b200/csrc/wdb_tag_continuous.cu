@@ -242,19 +242,22 @@ __device__ __forceinline__ float div_by_const_f64(float d, double c, double inv_
 // core/random.cu:62-72) followed by the reference's binary search.  Rows of <= 32 actions
 // are summed in registers (independent loads, one dependent FADD chain) instead of a
 // load-add-store chain through shared memory.
-__device__ __forceinline__ int sample_row(float *row, int A, float u) {
+__device__ __forceinline__ int sample_row(float *row, const float *src, int A, float u) {
+  // src: where the probabilities are (the staged shared-memory row itself, or the global row
+  // of a block that could not travel by TMA); row: shared-memory row that receives the CDF
   if (A <= 32) {
     float v[32];
 #pragma unroll
-    for (int i = 0; i < 32; i++) v[i] = i < A ? row[i] : 0.0f;
+    for (int i = 0; i < 32; i++) v[i] = i < A ? src[i] : 0.0f;
 #pragma unroll
     for (int i = 1; i < 32; i++) v[i] = v[i] + v[i - 1];
 #pragma unroll
-    for (int i = 1; i < 32; i++)
+    for (int i = 0; i < 32; i++)
       if (i < A) row[i] = v[i];
   } else {
-    float c = row[0];
-    for (int i = 1; i < A; i++) { c = row[i] + c; row[i] = c; }
+    float c = src[0];
+    row[0] = c;
+    for (int i = 1; i < A; i++) { c = src[i] + c; row[i] = c; }
   }
   return search_index(row, 1, u, A - 1);
 }
@@ -450,6 +453,16 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
 #pragma unroll
   for (int p = 0; p < kListLen - 2; p++)
     pnr[p] = (P.use_history && active && p < K) ? P.nearest[(long long)gi * K + p] : 0;
+  // agent state: requested before the sampling phase so that the loads are in flight while
+  // the probabilities arrive and the random numbers are drawn
+  float st_x = 0.f, st_y = 0.f, st_sp = 0.f, st_dir = 0.f, st_acc = 0.f, st_skill = 0.f;
+  int st_alive = 0;
+  if (active) {
+    st_x = P.loc_x[gi]; st_y = P.loc_y[gi]; st_sp = P.speed[gi];
+    st_dir = P.direction[gi]; st_acc = P.acceleration[gi];
+    st_alive = P.alive[gi];
+    st_skill = P.skill[a];
+  }
   if (active && a == 0) {
     const int t = P.timestep[env] + 1;   // :391-393
     P.timestep[env] = t;
@@ -476,8 +489,8 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
     }
     // contiguous blocks whose global address, shared address and size are 16-byte aligned
     // go through the TMA (one elected thread issues cp.async.bulk, the bytes land while
-    // every thread draws its random numbers and loads its state); the rest is copied by
-    // the threads with unit-stride loads
+    // every thread draws its random numbers and loads its state); rows of the other blocks
+    // are read from global memory by their own thread
     const uint32_t mbar = smem_u32(s_mbar);
     if (tid == 0) mbar_init(mbar, 1);
     __syncthreads();
@@ -516,22 +529,6 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
         }
       }
     }
-#pragma unroll
-    for (int p = 0; p < kMaxPolicies; p++) {
-      if (p < Q.n_policies) {
-        const int np = Q.policy_size[p];
-        if (!(tma_mask & (1u << (2 * p)))) {
-          const int n = envs_here * np * Q.A0;
-          const float *src = Q.probs0[p] + (long long)env0 * np * Q.A0;
-          for (int i = tid; i < n; i += blockDim.x) s_tile[p_off0[p] + i] = src[i];
-        }
-        if (!(tma_mask & (2u << (2 * p)))) {
-          const int n = envs_here * np * Q.A1;
-          const float *src = Q.probs1[p] + (long long)env0 * np * Q.A1;
-          for (int i = tid; i < n; i += blockDim.x) s_tile[p_off1[p] + i] = src[i];
-        }
-      }
-    }
     // random draw for both heads (independent of the probabilities: overlaps the copies)
     float u0 = 0.f, u1 = 0.f;
     if (active) {
@@ -548,16 +545,24 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
         u1 = u32_to_uniform(d.y);
       }
     }
-    __syncthreads();                       // thread-copied blocks visible
     if (tma_mask) mbar_wait(mbar, 0);      // TMA blocks landed
     if (active) {
       const int pol = Q.agent_policy[a], slot = Q.agent_slot[a];
       int np = 0, o0 = 0, o1 = 0;
+      const float *g0 = nullptr, *g1 = nullptr;   // global rows of blocks that did not go by TMA
 #pragma unroll
-      for (int p = 0; p < kMaxPolicies; p++)
-        if (p == pol) { np = Q.policy_size[p]; o0 = p_off0[p]; o1 = p_off1[p]; }
-      act0 = sample_row(s_tile + o0 + (le * np + slot) * Q.A0, Q.A0, u0);
-      act1 = sample_row(s_tile + o1 + (le * np + slot) * Q.A1, Q.A1, u1);
+      for (int p = 0; p < kMaxPolicies; p++) {
+        if (p == pol) {
+          np = Q.policy_size[p]; o0 = p_off0[p]; o1 = p_off1[p];
+          const long long grow = (long long)env * np + slot;
+          if (!(tma_mask & (1u << (2 * p)))) g0 = Q.probs0[p] + grow * Q.A0;
+          if (!(tma_mask & (2u << (2 * p)))) g1 = Q.probs1[p] + grow * Q.A1;
+        }
+      }
+      float *row0 = s_tile + o0 + (le * np + slot) * Q.A0;
+      float *row1 = s_tile + o1 + (le * np + slot) * Q.A1;
+      act0 = sample_row(row0, g0 ? g0 : row0, Q.A0, u0);
+      act1 = sample_row(row1, g1 ? g1 : row1, Q.A1, u1);
       if (Q.actions_out) *reinterpret_cast<int2 *>(Q.actions_out + 2ll * gi) = make_int2(act0, act1);
       if (Q.actions_head0) Q.actions_head0[gi] = act0;
       if (Q.actions_head1) Q.actions_head1[gi] = act1;
@@ -578,13 +583,13 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
   float cap = 0.f;
   if (active) {
     // :402-465 kinematics, same float32 expression forms as the reference
-    float x = P.loc_x[gi], y = P.loc_y[gi], sp = P.speed[gi];
-    float dir = P.direction[gi], acc = P.acceleration[gi];
-    alive = P.alive[gi];
+    float x = st_x, y = st_y, sp = st_sp;
+    float dir = st_dir, acc = st_acc;
+    alive = st_alive;
     acc += P.acc_actions[act0];
     dir = fmod(dir + P.turn_actions[act1], kTwoPi) * alive;
     if (dir < 0) dir = kTwoPi + dir;
-    cap = P.max_speed * P.skill[a];
+    cap = P.max_speed * st_skill;
     sp = min(cap, max(0.0, sp + acc)) * alive;
     if ((sp <= 0.0) || (sp >= cap)) acc = 0.0;
     x += sp * cos(dir);
