@@ -135,7 +135,7 @@ def build_engine(n_envs, seed, graph_steps, use_graph=True, forward_dtype=None,
     wrapper.reset_all_envs()
     # the fused kernel hands observations straight to the per-policy forward buffers; the
     # [E, N, F] `observations` array is only materialised on demand
-    stats = torch.zeros(4, dtype=torch.int32, device="cuda")
+    stats = torch.zeros(64, dtype=torch.int32, device="cuda")
     engine = RolloutEngine(wrapper, models, policy_map, sampler, graph_steps,
                            use_cuda_graph=use_graph, forward_dtype=forward_dtype,
                            write_observations=False, stats=stats,
@@ -454,6 +454,8 @@ def main():
                                  "agents that needed the exact tie-resolution path"},
         "roofline": roofline,
     }
+    if any(stats_timed[8:32]):      # library built with -DWDB_PHASE_CLOCKS (profiling aid)
+        line["phase_clocks_cta0"] = stats_timed[8:32]
     if not args.skip_cpu_baseline:
         cores = os.cpu_count() or 1
         res = cpu_baseline(sample_steps=150, n_procs=cores)

@@ -38,7 +38,8 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + sources() + [
+    extra = os.environ.get("WDB_NVCC_EXTRA", "").split()   # e.g. -DWDB_PHASE_CLOCKS (profiling aid)
+    cmd = ["nvcc"] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + sources() + [
         "-o", LIB,
     ]
     if verbose:

@@ -58,6 +58,15 @@ constexpr int kMaxPolicies = 4;
 constexpr int kListLen = 16;   // sorted candidate list kept per agent (self + K+1 <= 16)
 constexpr int kHistCap = 32;   // history path: candidates one lane may collect
 
+// Profiling aid (-DWDB_PHASE_CLOCKS): thread 0 of CTA 0 records the SM clock at the phase
+// boundaries into stats[8 + i] (the stats buffer must then hold >= 32 ints).
+#ifdef WDB_PHASE_CLOCKS
+#define WDB_MARK(i)                                                                  \
+  if (P.stats && blockIdx.x == 0 && threadIdx.x == 0) P.stats[8 + (i)] = (int)(clock64() - wdb_t0);
+#else
+#define WDB_MARK(i)
+#endif
+
 struct TcParams {
   int n_envs, N, epb, K, episode_length;
   int use_full_obs, runner_exits, stage_obs, scratch_in_smem, id_bits;
@@ -373,6 +382,9 @@ template <bool FUSED, int MAXT>
 __global__ void __launch_bounds__(MAXT, MAXT == 320 ? 2 : 1)
 tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant__ FusedParams Q) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+#ifdef WDB_PHASE_CLOCKS
+  const long long wdb_t0 = clock64();
+#endif
   const int N = P.N, epb = P.epb, K = P.K;
   const int EN = epb * N;
   const int nwarps = blockDim.x / kWarp;
@@ -429,55 +441,17 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
     }
   }
 
-  // ------------------------------------------------------------------ phase 0
-  if (tid < N) {
-    stype[tid] = P.agent_types[tid];
-    int rb = tid * F, rs = N * F;
-    if (FUSED) {
-      const int pol = Q.agent_policy[tid], slot = Q.agent_slot[tid];
-#pragma unroll
-      for (int p = 0; p < kMaxPolicies; p++)
-        if (p == pol) { rb = tile_base[p] + slot * F; rs = Q.policy_size[p] * F; }
-    }
-    s_rowbase[tid] = rb;
-    s_rowstride[tid] = rs;
-  }
-  if (tid < epb) s_nalive[tid] = 0;
-  for (int i = tid; i < epb * (Ne - N); i += blockDim.x) {   // key padding: never a candidate
-    const int e = i / (Ne - N), j = N + (i - e * (Ne - N));
-    skx[e * Ne + j] = CUDART_INF_F;
-    sky[e * Ne + j] = CUDART_INF_F;
-  }
-  // last step's neighbour ids (history path): requested now, consumed after the kinematics
-  int pnr[kListLen - 2];
-#pragma unroll
-  for (int p = 0; p < kListLen - 2; p++)
-    pnr[p] = (P.use_history && active && p < K) ? P.nearest[(long long)gi * K + p] : 0;
-  // agent state: requested before the sampling phase so that the loads are in flight while
-  // the probabilities arrive and the random numbers are drawn
-  float st_x = 0.f, st_y = 0.f, st_sp = 0.f, st_dir = 0.f, st_acc = 0.f, st_skill = 0.f;
-  int st_alive = 0;
-  if (active) {
-    st_x = P.loc_x[gi]; st_y = P.loc_y[gi]; st_sp = P.speed[gi];
-    st_dir = P.direction[gi]; st_acc = P.acceleration[gi];
-    st_alive = P.alive[gi];
-    st_skill = P.skill[a];
-  }
-  if (active && a == 0) {
-    const int t = P.timestep[env] + 1;   // :391-393
-    P.timestep[env] = t;
-    s_t[le] = t;
-    s_nrun[le] = P.num_runners[env];
-  }
-
-  int act0 = 0, act1 = 0;
+  // ---- categorical sampling of both action heads (core/random.cu:51-85): the probability
+  // blocks are requested first thing (TMA), they land while the state loads fly ----
+  int p_off0[kMaxPolicies], p_off1[kMaxPolicies];
+  uint32_t tma_mask = 0;   // bit 2p / 2p+1: block (p, head) travels by TMA
+  const uint32_t mbar = smem_u32(s_mbar);
   if (FUSED) {
     // ---- categorical sampling of both action heads (core/random.cu:51-85) ----
     // stage every policy's [envs_here, Np, A] block (contiguous in global memory) with
     // unit-stride loads; rows keep their global layout (stride A is odd for A = 21, so a
     // thread walking its own row is bank-conflict free)
     // block offsets inside the tile (floats): [p0 head0][p0 head1][p1 head0]...
-    int p_off0[kMaxPolicies], p_off1[kMaxPolicies];
     {
       int off = 0;
 #pragma unroll
@@ -491,10 +465,6 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
     // go through the TMA (one elected thread issues cp.async.bulk, the bytes land while
     // every thread draws its random numbers and loads its state); rows of the other blocks
     // are read from global memory by their own thread
-    const uint32_t mbar = smem_u32(s_mbar);
-    if (tid == 0) mbar_init(mbar, 1);
-    __syncthreads();
-    uint32_t tma_mask = 0;   // bit 2p / 2p+1: block (p, head) travels by TMA
 #pragma unroll
     for (int p = 0; p < kMaxPolicies; p++) {
       if (p < Q.n_policies) {
@@ -505,6 +475,7 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
         if (tma_ok(g1, smem_u32(s_tile + p_off1[p]), 4ull * envs_here * np * Q.A1)) tma_mask |= 2u << (2 * p);
       }
     }
+    if (tid == 0) mbar_init(mbar, 1);      // (includes the init fence; waiters sync below)
     if (tid == 0 && tma_mask) {
       uint32_t total = 0;
 #pragma unroll
@@ -529,25 +500,94 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
         }
       }
     }
-    // random draw for both heads (independent of the probabilities: overlaps the copies)
-    float u0 = 0.f, u1 = 0.f;
-    if (active) {
-      if (Q.uniforms) {
-        u0 = Q.uniforms[2ll * gi];
-        u1 = Q.uniforms[2ll * gi + 1];
-      } else {
-        const RngHeader h = *reinterpret_cast<const RngHeader *>(Q.rng);
-        unsigned long long *offp = rng_offsets(Q.rng);
-        const unsigned long long o = offp[gi];
-        const uint4 d = rng_draw4(h, (unsigned long long)gi, o);
-        offp[gi] = o + 1;
-        u0 = u32_to_uniform(d.x);
-        u1 = u32_to_uniform(d.y);
-      }
+  }
+
+  // ------------------------------------------------------------------ phase 0
+  // Every global read of the prologue is issued here, back to back, BEFORE any global store
+  // (a store would pin the later loads behind it): one memory round trip instead of six.
+  int g_type = 0, g_pol = 0, g_slot = 0;           // per agent id (tid < N)
+  if (tid < N) {
+    g_type = P.agent_types[tid];
+    if (FUSED) { g_pol = Q.agent_policy[tid]; g_slot = Q.agent_slot[tid]; }
+  }
+  int my_pol = 0, my_slot = 0;                     // of this thread's agent
+  if (FUSED && active) { my_pol = Q.agent_policy[a]; my_slot = Q.agent_slot[a]; }
+  // last step's neighbour ids (history path), consumed after the kinematics
+  int pnr[kListLen - 2];
+#pragma unroll
+  for (int p = 0; p < kListLen - 2; p++)
+    pnr[p] = (P.use_history && active && p < K) ? P.nearest[(long long)gi * K + p] : 0;
+  float st_x = 0.f, st_y = 0.f, st_sp = 0.f, st_dir = 0.f, st_acc = 0.f, st_skill = 0.f;
+  int st_alive = 0;
+  if (active) {
+    st_x = P.loc_x[gi]; st_y = P.loc_y[gi]; st_sp = P.speed[gi];
+    st_dir = P.direction[gi]; st_acc = P.acceleration[gi];
+    st_alive = P.alive[gi];
+    st_skill = P.skill[a];
+  }
+  int g_t = 0, g_nrun = 0;
+  if (active && a == 0) { g_t = P.timestep[env]; g_nrun = P.num_runners[env]; }
+  unsigned long long rng_seed = 0, rng_off = 0;
+  float u0 = 0.f, u1 = 0.f;
+  if (FUSED && active) {
+    if (Q.uniforms) {
+      u0 = Q.uniforms[2ll * gi];
+      u1 = Q.uniforms[2ll * gi + 1];
+    } else {
+      rng_seed = reinterpret_cast<const RngHeader *>(Q.rng)->seed;
+      rng_off = rng_offsets(Q.rng)[gi];
     }
+  }
+  // action -> acceleration / turn tables, staged at the head of the per-warp scratch (free
+  // until the neighbour search) so that the kinematics do not wait on a dependent global load
+  float *s_tab = reinterpret_cast<float *>(s_scr);
+  const bool tab_ok = FUSED && (size_t)(Q.A0 + Q.A1) * 4 <= (size_t)nwarps * P.scr_warp_bytes;
+  float g_tab = 0.f;
+  if (tab_ok && tid < Q.A0 + Q.A1)
+    g_tab = tid < Q.A0 ? P.acc_actions[tid] : P.turn_actions[tid - Q.A0];
+
+  if (tid < N) {
+    stype[tid] = g_type;
+    int rb = tid * F, rs = N * F;
+    if (FUSED) {
+#pragma unroll
+      for (int p = 0; p < kMaxPolicies; p++)
+        if (p == g_pol) { rb = tile_base[p] + g_slot * F; rs = Q.policy_size[p] * F; }
+    }
+    s_rowbase[tid] = rb;
+    s_rowstride[tid] = rs;
+  }
+  if (tab_ok && tid < Q.A0 + Q.A1) s_tab[tid] = g_tab;
+  if (tid < epb) s_nalive[tid] = 0;
+  for (int i = tid; i < epb * (Ne - N); i += blockDim.x) {   // key padding: never a candidate
+    const int e = i / (Ne - N), j = N + (i - e * (Ne - N));
+    skx[e * Ne + j] = CUDART_INF_F;
+    sky[e * Ne + j] = CUDART_INF_F;
+  }
+  if (active && a == 0) {
+    const int t = g_t + 1;   // :391-393
+    P.timestep[env] = t;
+    s_t[le] = t;
+    s_nrun[le] = g_nrun;
+  }
+
+  int act0 = 0, act1 = 0;
+  if (FUSED) {
+    // random draw for both heads (independent of the probabilities: overlaps the copies)
+    if (active && !Q.uniforms) {
+      RngHeader h;
+      h.seed = rng_seed; h.n_streams = 0;
+      const uint4 d = rng_draw4(h, (unsigned long long)gi, rng_off);
+      rng_offsets(Q.rng)[gi] = rng_off + 1;
+      u0 = u32_to_uniform(d.x);
+      u1 = u32_to_uniform(d.y);
+    }
+    __syncthreads();                       // mbarrier initialised; tables / phase-0 arrays staged
+    WDB_MARK(0)   // rng drawn, state requested
     if (tma_mask) mbar_wait(mbar, 0);      // TMA blocks landed
+    WDB_MARK(1)   // probabilities landed
     if (active) {
-      const int pol = Q.agent_policy[a], slot = Q.agent_slot[a];
+      const int pol = my_pol, slot = my_slot;
       int np = 0, o0 = 0, o1 = 0;
       const float *g0 = nullptr, *g1 = nullptr;   // global rows of blocks that did not go by TMA
 #pragma unroll
@@ -579,6 +619,7 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
     act0 = act.x; act1 = act.y;
   }
 
+  WDB_MARK(2)   // actions sampled
   int alive = 0;
   float cap = 0.f;
   if (active) {
@@ -586,8 +627,8 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
     float x = st_x, y = st_y, sp = st_sp;
     float dir = st_dir, acc = st_acc;
     alive = st_alive;
-    acc += P.acc_actions[act0];
-    dir = fmod(dir + P.turn_actions[act1], kTwoPi) * alive;
+    acc += tab_ok ? s_tab[act0] : P.acc_actions[act0];
+    dir = fmod(dir + (tab_ok ? s_tab[Q.A0 + act1] : P.turn_actions[act1]), kTwoPi) * alive;
     if (dir < 0) dir = kTwoPi + dir;
     cap = P.max_speed * st_skill;
     sp = min(cap, max(0.0, sp + acc)) * alive;
@@ -615,7 +656,9 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
     if (alive) { r += ep; r += P.step_rewards[a]; }
     srew[li] = r;
   }
+  WDB_MARK(3)   // kinematics done
   __syncthreads();   // state staged; probability tile is dead from here on
+  WDB_MARK(4)
 
   // tagger id list in id order (agent_types is shared by all envs), built by warp 0
   if (warp == 0) {
@@ -682,6 +725,7 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
           // neighbours that left the game shrink the list: widen the disc accordingly
           if (seen < kk) tau *= 1.0f + 0.45f * (float)(kk - seen);
           if (seen == 0) tau = -1.0f;
+          WDB_MARK(5)   // tau known
           uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
           {
             unsigned long long pax2, pay2;
@@ -700,6 +744,7 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
 #undef WDB_SCAN_WORD
             m_out = fminf(mo_a, mo_b);
           }
+          WDB_MARK(6)   // scan done
           const int cnt = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
           const bool hist_ok = (cnt >= kk + 1) && (cnt <= kHistCap);   // self + >= kk others
           if (hist_ok) {
@@ -717,6 +762,7 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
               WDB_EXTRACT(m0, 0) WDB_EXTRACT(m1, 32) WDB_EXTRACT(m2, 64) WDB_EXTRACT(m3, 96)
 #undef WDB_EXTRACT
             }
+            WDB_MARK(7)   // ids extracted
 #define WDB_HKEY(i)                                                                 \
   uint32_t c##i;                                                                    \
   {                                                                                 \
@@ -764,6 +810,7 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
         R[0] = r0; R[1] = r1; R[2] = r2; R[3] = r3; R[4] = r4; R[5] = r5; R[6] = r6;
         R[7] = r7; R[8] = r8; R[9] = r9; R[10] = r10; R[11] = r11; R[12] = r12;
         R[13] = r13; R[14] = r14; R[15] = r15;
+        WDB_MARK(8)   // sorted
         // ---- verification on EXACT float32 squared distances of the K+1 nearest.
         // The network ranked keys whose low id_bits were replaced by the id, so (a) two
         // winners may be mis-ordered when their distances agree in the kept bits -> they
@@ -833,6 +880,7 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
         suspect = true;
       }
     }
+    WDB_MARK(9)   // verified
     // exact path: the warp resolves its suspect agents one at a time, cooperatively
     unsigned todo = __ballot_sync(0xffffffffu, suspect);
     while (todo) {
@@ -872,6 +920,7 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
         if (i <= kk) idcol[(i - 1) * kWarp] = (uint16_t)(R[i] & idmask);
     }
 
+    WDB_MARK(10)  // exact path done, ids stored
     if (active) {
       float *orow = P.stage_obs ? (s_tile + s_rowbase[a] + le * s_rowstride[a])
                                 : (P.obs + (long long)gi * F);
@@ -965,8 +1014,10 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
     }
   }
   // make the tile (written through the generic proxy) visible to the TMA engine
+  WDB_MARK(11)  // features written
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();   // obs tile complete; srew initialised; tagger list ready
+  WDB_MARK(12)
 
   // observation copy-out, part 1: every block of the tile whose shared / global addresses
   // and size are 16-byte aligned leaves through the TMA (cp.async.bulk), issued by one
@@ -988,6 +1039,7 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
         }
       }
     }
+    WDB_MARK(18)  // before the TMA store issue
     if (tid == 0 && out_mask) {
       if (out_mask & (1u << 8))
         tma_store_1d(P.obs + (long long)env0 * N * F, smem_u32(s_tile), 4u * envs_here * N * F);
@@ -1001,6 +1053,7 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
       }
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
+    WDB_MARK(19)  // TMA stores issued
   }
 
   // bookkeeping words needed after the reward phase: requested now so that their latency
@@ -1013,7 +1066,7 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
       done_prev = P.done[env];
       if (Q.step_running_sum) steps_prev = Q.step_running_sum[env];
     }
-    const int pol = Q.agent_policy[a], slot = Q.agent_slot[a];
+    const int pol = my_pol, slot = my_slot;
 #pragma unroll
     for (int p = 0; p < kMaxPolicies; p++) {
       if (p == pol) {
@@ -1023,6 +1076,7 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
     }
   }
 
+  WDB_MARK(20)  // bookkeeping loads requested
   // ------------------------------------------------------------------ rewards / tags
   float r = active ? srew[li] : 0.0f;
   const bool is_runner = active && (stype[a] == 0);
@@ -1063,7 +1117,9 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
     }
     if (t_env == P.episode_length) r += P.end_reward;        // :334-337
   }
+  WDB_MARK(13)  // reward phase done
   __syncthreads();
+  WDB_MARK(14)
   int done_now = 0;
   if (active) {
     r = (stype[a] == 1) ? srew[li] : r;
@@ -1098,7 +1154,7 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
   if (FUSED) {
     __syncthreads();   // s_done visible
     if (active) {
-      const int pol = Q.agent_policy[a];
+      const int pol = my_pol;
       const int d = s_done[le];
 #pragma unroll
       for (int p = 0; p < kMaxPolicies; p++) {
@@ -1155,7 +1211,9 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
 
   // the TMA stores must have read the tile (and, before the reset below overwrites the same
   // global rows for finished envs, must have completed) before the CTA goes on / exits
+  WDB_MARK(15)  // bookkeeping + thread copy-out done
   if (tid == 0 && out_mask) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  WDB_MARK(16)  // TMA stores complete
 
   if (FUSED && Q.do_reset) {
     // done-masked reset of this CTA's envs (core/reset.cu:9-75 for every registered array
@@ -1188,6 +1246,7 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
       }
     }
   }
+  WDB_MARK(17)  // reset done
 }
 
 int g_tc_history = 1;   // wdb_set_option("tc_history", 0/1)
