@@ -456,6 +456,12 @@ def main():
     }
     if any(stats_timed[8:32]):      # library built with -DWDB_PHASE_CLOCKS (profiling aid)
         line["phase_clocks_cta0"] = stats_timed[8:32]
+        import ctypes
+        raw = ctypes.CDLL(wlib.load()._name)
+        if hasattr(raw, "wdb_debug_mlp_clocks"):
+            buf = (ctypes.c_longlong * 96)()
+            raw.wdb_debug_mlp_clocks(buf)
+            line["mlp_clocks_cta0"] = list(buf)
     if not args.skip_cpu_baseline:
         cores = os.cpu_count() or 1
         res = cpu_baseline(sample_steps=150, n_procs=cores)

@@ -8,14 +8,14 @@
 //
 //   * all weights (bf16, pre-packed by wdb_mlp_pack_weights into the UMMA canonical K-major
 //     no-swizzle layout) are TMA-bulk-loaded into shared memory ONCE per CTA (192 KB);
-//   * per 128-row tile: obs (fp32, unit-stride loads) -> bf16 A tile in shared memory;
-//     layer 1 = tcgen05.mma (A from smem) into TMEM; epilogue (tcgen05.ld, +bias, ReLU,
+//   * per 128-row tile: obs (fp32) -> bf16 -> TMEM (through a shared-memory transpose);
+//     layer 1 = tcgen05.mma (A from TMEM) into TMEM; epilogue (tcgen05.ld, +bias, ReLU,
 //     bf16 pack) writes the hidden activations BACK INTO TMEM (tcgen05.st); layers 2 and 3
 //     take their A operand straight from TMEM (tcgen05.mma .ts form) -- hidden activations
 //     never touch shared or global memory; final epilogue = bias + two softmaxes + value,
 //     staged in shared memory and written with TMA bulk stores.
 //   * one elected thread issues the MMAs; completion is signalled through an mbarrier
-//     (tcgen05.commit); 8 warps run the epilogues (4 lane quadrants x 2 column halves);
+//     (tcgen05.commit); 16 warps run the epilogues (4 lane quadrants x 4 column parts);
 //   * the next tile's obs are prefetched into registers while the current tile computes.
 //
 // Numerics: bf16 operands, fp32 accumulation (the reference is fp32; SURVEY.md section 8
@@ -31,11 +31,30 @@ using namespace wdb;
 namespace {
 
 constexpr int kTileM = 128;
-constexpr int kThreads = 256;
-constexpr int kTasks = 6;       // A-tile build tasks (8 fp32 obs values each) per thread held across a tile
+#ifndef WDB_MLP_WORKERS
+#define WDB_MLP_WORKERS 384
+#endif
+constexpr int kWorkers = WDB_MLP_WORKERS;   // worker warps x 32 (obs path + epilogues); multiple of 128
+constexpr int kThreads = kWorkers + 32;  // + 1 warp whose lane 0 issues every tcgen05.mma
+constexpr int kWarps = kWorkers / 32;
+constexpr int kParts = kWarps / 4;       // worker warps per TMEM lane quadrant
+constexpr int kTasks = (48 + kWorkers / 32 - 1) / (kWorkers / 32);       // A-tile build tasks (8 fp32 obs values each) per thread held across a tile
 constexpr int kTmemCols = 512;
 constexpr int kColD = 0;      // accumulator columns [0, 256)
-constexpr int kColH = 256;    // packed bf16 hidden activations: layer 1 -> [256, 384), layer 2 -> [384, 512)
+constexpr int kColH = 256;    // packed bf16 hidden activations [256, 384)
+constexpr int kColA = 384;    // packed bf16 obs of the current / next tile [384, 384 + K1/2)
+// layer-3 accumulator: behind the obs columns when it fits (then layer 1 of the next tile may
+// run during the output epilogue), else on top of D
+
+// Profiling aid (-DWDB_PHASE_CLOCKS): thread 0 of CTA 0 records the SM clock at the phase
+// boundaries of its first tiles; read back with wdb_debug_mlp_clocks (debug builds only).
+#ifdef WDB_PHASE_CLOCKS
+__device__ long long g_mlp_clk[96];
+#define MLP_MARK(i)                                                                  \
+  if (blockIdx.x == 0 && threadIdx.x == 0 && mark_tile < 6) g_mlp_clk[mark_tile * 16 + (i)] = clock64() - mlp_t0;
+#else
+#define MLP_MARK(i)
+#endif
 
 struct MlpHeader {            // start of the packed weight blob (device memory)
   int F, K1, H, A0, A1, N3;   // input features, padded K of layer 1, hidden width, heads, padded N3
@@ -65,13 +84,6 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
          | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);   // K-major A and B
 }
 
-__device__ __forceinline__ void mma_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
-                                       uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
 __device__ __forceinline__ void mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc,
                                        uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -144,6 +156,14 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<const uint32_t *>(&h);
 }
 
+// named barriers: 1 = workers only, 2 = workers arrive / issuer warp waits
+__device__ __forceinline__ void bar_sync(int id, int n) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(int id, int n) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+
 // predicated read-only load (0 when off) -- written in PTX so that no select depends on the
 // loaded value: the prefetch must not wait for its own loads
 __device__ __forceinline__ float ldg_if(const float *p, bool on) {
@@ -174,7 +194,7 @@ __device__ __forceinline__ uint32_t bias_relu_pack(uint32_t lo, uint32_t hi, flo
 // hidden epilogue: D[lane, c0..c1) (+bias, ReLU) -> packed bf16 into TMEM columns kColH + c/2
 __device__ __forceinline__ void hidden_epilogue(uint32_t tmem_lane_base, uint32_t col_h,
                                                 const float *bias, int c0, int c1) {
-  for (int c = c0; c < c1; c += 64) {      // the two column halves of a quadrant interleave
+  for (int c = c0; c < c1; c += 32 * kParts) {   // the warps of a quadrant interleave 32-column chunks
     uint32_t v[32];
     tmem_ld32(tmem_lane_base + kColD + c, v);
     uint32_t out[16];
@@ -189,16 +209,21 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t tmem_lane_base, uint32_
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-// 8 warps: warp w owns TMEM lanes 32 (w & 3) .. +31 (= rows of the tile) and, in the hidden
-// epilogues, the column half (w >> 2); in the output epilogue half 0 does head 0 and half 1
-// does head 1 + the value.  The fp32 obs of the NEXT tile are prefetched into registers
-// (unit-stride loads issued right after the current A tile is built) so their latency hides
-// behind the three MMAs and epilogues of the current tile.
+// 16 warps: warp w owns TMEM lanes 32 (w & 3) .. +31 (= rows of the tile) and, in the hidden
+// epilogues, every kParts-th 32-column chunk (part = w >> 2); in the output epilogue part 0
+// does head 0 and part 1 head 1 + the value.  (Two warps per scheduler left every dependent
+// instruction latency exposed; four hide most of it.)  The A operand of layer 1 also lives in TMEM: the NEXT tile's obs
+// (prefetched into registers one tile ahead) are converted and copied there while the tensor
+// core runs layer 2 of the current tile, so the obs path never sits on the critical path.
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_forward_kernel(const unsigned char *__restrict__ blob, const float *__restrict__ obs,
                    long long rows, float *__restrict__ probs0, float *__restrict__ probs1,
                    float *__restrict__ values) {
   extern __shared__ __align__(128) unsigned char smem[];
+#ifdef WDB_PHASE_CLOCKS
+  const long long mlp_t0 = clock64();
+  int mark_tile = 0;
+#endif
   const MlpHeader hd = *reinterpret_cast<const MlpHeader *>(blob);
   const int F = hd.F, K1 = hd.K1, H = hd.H, A0 = hd.A0, A1 = hd.A1, N3 = hd.N3;
   const int w_bytes = hd.total_bytes - hd.off_w1;        // W1 | W2 | W3 | biases, contiguous
@@ -211,17 +236,20 @@ mlp_forward_kernel(const unsigned char *__restrict__ blob, const float *__restri
   unsigned char *s_a = s_w + ((w_bytes + 127) & ~127);   // A tile (layer 1) / output staging
   const int a_bytes = max(kTileM * K1 * 2, kTileM * (A0 + A1 + 1) * 4);
   unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(s_a + ((a_bytes + 15) & ~15));
-  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 3);
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int quad = warp & 3, half = warp >> 2;
+  const int quad = warp & 3, part = warp >> 2;
   const uint32_t bar_w = smem_addr(&s_bar[0]);           // weights landed
-  const uint32_t bar_mma[2] = {smem_addr(&s_bar[1]), smem_addr(&s_bar[2])};   // MMA N-group done
+  const uint32_t bar_l1 = smem_addr(&s_bar[1]);          // layer-1 / 2 / 3 accumulators complete
+  const uint32_t bar_l2 = smem_addr(&s_bar[2]);
+  const uint32_t bar_l3 = smem_addr(&s_bar[3]);
 
   if (tid == 0) {
     mbar_init(bar_w, 1);
-    mbar_init(bar_mma[0], 1);
-    mbar_init(bar_mma[1], 1);
+    mbar_init(bar_l1, 1);
+    mbar_init(bar_l2, 1);
+    mbar_init(bar_l3, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -250,9 +278,9 @@ mlp_forward_kernel(const unsigned char *__restrict__ blob, const float *__restri
   // row of a core matrix): lane -> (row = 8 g + lane % 8, chunk = 4 q + lane / 8), so the 8
   // global loads of a task read 128 contiguous bytes of each of 8 obs rows and the one
   // 16-byte shared store per lane is bank-conflict free.  16 * ncg tasks per tile, dealt
-  // round-robin to the 8 warps; up to kTasks per thread live in registers (pf).
+  // round-robin to the warps; up to kTasks per thread live in registers (pf).
   const int nchunk = K1 / 8, ncg = (nchunk + 3) / 4;
-  const int tasks_per_warp = (16 * ncg + 7) / 8;
+  const int tasks_per_warp = (16 * ncg + kWarps - 1) / kWarps;
   const bool single_batch = tasks_per_warp <= kTasks;     // whole tile fits the register prefetch
   float pf[kTasks * 8];
   auto load_batch = [&](long long tile, int batch) {
@@ -260,7 +288,7 @@ mlp_forward_kernel(const unsigned char *__restrict__ blob, const float *__restri
     const int valid = (int)min((long long)kTileM, rows - r0);
 #pragma unroll
     for (int j = 0; j < kTasks; j++) {
-      const int wt = warp + 8 * (j + kTasks * batch);
+      const int wt = warp + kWarps * (j + kTasks * batch);
       const int g = wt / ncg, q = wt - g * ncg;
       const int r = 8 * g + (lane & 7), c = 4 * q + (lane >> 3);
       const bool on = (g < 16) && (c < nchunk) && (r < valid);
@@ -272,7 +300,7 @@ mlp_forward_kernel(const unsigned char *__restrict__ blob, const float *__restri
   auto store_batch = [&](int batch) {
 #pragma unroll
     for (int j = 0; j < kTasks; j++) {
-      const int wt = warp + 8 * (j + kTasks * batch);
+      const int wt = warp + kWarps * (j + kTasks * batch);
       const int g = wt / ncg, q = wt - g * ncg;
       const int c = 4 * q + (lane >> 3);
       if (g < 16 && c < nchunk) {
@@ -285,159 +313,204 @@ mlp_forward_kernel(const unsigned char *__restrict__ blob, const float *__restri
       }
     }
   };
-  if (single_batch && (long long)blockIdx.x < n_tiles) load_batch(blockIdx.x, 0);
+  if (single_batch && warp < kWarps && (long long)blockIdx.x < n_tiles) load_batch(blockIdx.x, 0);
 
-  mbar_wait(bar_w, 0);
-
-  // hidden layers run as `nsplit` N-groups of GW columns, each with its own commit barrier:
-  // the epilogue of group 0 overlaps the MMAs of group 1.  Layer 1 packs its activations into
-  // TMEM columns [256, 384), layer 2 into [384, 512), so layer 2's second group may still
-  // read layer 1's activations while the first group's epilogue writes layer 2's.
-  const int nsplit = (H % 128 == 0) ? 2 : 1;
-  const int GW = H / nsplit;
-  const uint32_t idesc_h = make_idesc(kTileM, GW);
+  const uint32_t idesc_h = make_idesc(kTileM, H);
   const uint32_t idesc_o = make_idesc(kTileM, N3);
-  const uint32_t sbo_a = (uint32_t)(K1 / 8) * 128u;       // A tile / W1: K1/8 core matrices per row group
+  const uint32_t sbo_a = (uint32_t)(K1 / 8) * 128u;       // W1: K1/8 core matrices per row group
   const uint32_t sbo_h = (uint32_t)(H / 8) * 128u;        // W2 / W3: H/8 core matrices per row group
-  uint32_t mma_phase[2] = {0, 0};
+  const bool overlap_l1 = K1 / 2 + N3 <= kTmemCols - kColA;   // room for a separate layer-3 accumulator
+  const int col_d3 = overlap_l1 ? kColA + K1 / 2 : kColD;
   float *s_p0 = reinterpret_cast<float *>(s_a);
   float *s_p1 = s_p0 + kTileM * A0;
   float *s_v = s_p1 + kTileM * A1;
 
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long long r0 = tile * kTileM;
-    const int valid = (int)min((long long)kTileM, rows - r0);
-
-    // ---- obs tile -> bf16, canonical K-major layout (K padding and missing rows = 0)
-    if (single_batch) {
-      store_batch(0);
-    } else {
-      for (int batch = 0; batch * kTasks < tasks_per_warp; batch++) {
-        load_batch(tile, batch);
-        store_batch(batch);
-      }
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-
-    // ---- layer 1: D[128, H] = A[128, K1] * W1^T          (A, B from shared memory)
-    if (tid == 0) {
+  if (warp == kWarps) {
+    // ================= MMA issuer warp =================
+    // Waits (named barrier 2) until the workers have produced an operand in TMEM, then lane 0
+    // issues the layer's MMAs and commits them to that layer's mbarrier.  Issuing is
+    // back-pressured by the tensor core (~100+ cycles per instruction), which is why it has
+    // its own warp: the workers build the next tile's operand meanwhile.
+    auto issue_l1 = [&]() {
+      const uint32_t b0 = smem_addr(s_w);
+      for (int kk = 0; kk < K1 / 16; kk++)
+        mma_ts(tmem_base + kColD, tmem_base + kColA + kk * 8, make_desc(b0 + kk * 256, sbo_a),
+               idesc_h, kk > 0);
+      mma_commit(bar_l1);
+    };
+    mbar_wait(bar_w, 0);
+    bar_sync(2, kThreads);                                // first A operand in TMEM
+    fence_after();
+    if (lane == 0 && (long long)blockIdx.x < n_tiles) issue_l1();
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const bool has_next = tile + gridDim.x < n_tiles;
+      bar_sync(2, kThreads);                              // hidden activations of layer 1 packed
       fence_after();
-      const uint32_t a0 = smem_addr(s_a), b0 = smem_addr(s_w);
-      for (int g = 0; g < nsplit; g++) {
-        const uint32_t bg = b0 + (uint32_t)(g * GW / 8) * sbo_a;     // W1 rows g*GW ..
-        for (int kk = 0; kk < K1 / 16; kk++)
-          mma_ss(tmem_base + kColD + g * GW, make_desc(a0 + kk * 256, sbo_a),
-                 make_desc(bg + kk * 256, sbo_a), idesc_h, kk > 0);
-        mma_commit(bar_mma[g]);
-      }
-    }
-    // prefetch the next tile's obs into registers (after the MMA issue, so that the queueing
-    // of ~12k loads per CTA does not delay the tensor core)
-    if (single_batch && tile + gridDim.x < n_tiles) load_batch(tile + gridDim.x, 0);
-    for (int g = 0; g < nsplit; g++) {
-      mbar_wait(bar_mma[g], mma_phase[g]); mma_phase[g] ^= 1;
-      fence_after();
-      hidden_epilogue(tmem_lane, kColH, s_b1, g * GW + 32 * half, (g + 1) * GW);
-    }
-    fence_before();
-    __syncthreads();
-
-    // ---- layer 2: D[128, H] = H1[128, H] * W2^T           (A from TMEM)
-    if (tid == 0) {
-      fence_after();
-      const uint32_t b0 = smem_addr(s_w2);
-      for (int g = 0; g < nsplit; g++) {
-        const uint32_t bg = b0 + (uint32_t)(g * GW / 8) * sbo_h;
+      if (lane == 0) {
+        const uint32_t b0 = smem_addr(s_w2);
         for (int kk = 0; kk < H / 16; kk++)
-          mma_ts(tmem_base + kColD + g * GW, tmem_base + kColH + kk * 8,
-                 make_desc(bg + kk * 256, sbo_h), idesc_h, kk > 0);
-        mma_commit(bar_mma[g]);
+          mma_ts(tmem_base + kColD, tmem_base + kColH + kk * 8, make_desc(b0 + kk * 256, sbo_h),
+                 idesc_h, kk > 0);
+        mma_commit(bar_l2);
       }
-    }
-    for (int g = 0; g < nsplit; g++) {
-      mbar_wait(bar_mma[g], mma_phase[g]); mma_phase[g] ^= 1;
+      bar_sync(2, kThreads);                              // layer 2 packed; next A operand built
       fence_after();
-      hidden_epilogue(tmem_lane, kColH + 128, s_b2, g * GW + 32 * half, (g + 1) * GW);
-    }
-    fence_before();
-    __syncthreads();
-
-    // ---- layer 3: D[128, N3] = H2[128, H] * W3^T          (heads + value)
-    if (tid == 0) {
-      fence_after();
-      const uint32_t b0 = smem_addr(s_w3);
-      for (int kk = 0; kk < H / 16; kk++)
-        mma_ts(tmem_base + kColD, tmem_base + kColH + 128 + kk * 8, make_desc(b0 + kk * 256, sbo_h),
-               idesc_o, kk > 0);
-      mma_commit(bar_mma[0]);
-    }
-    mbar_wait(bar_mma[0], mma_phase[0]); mma_phase[0] ^= 1;
-    fence_after();
-
-    // ---- output epilogue: bias, softmax of this half's head (+ value) -> staging
-    {
-      const int cbase = half ? A0 : 0, cnt = half ? A1 : A0;
-      const int row = quad * 32 + lane;                    // TMEM lane == row of the tile
-      uint32_t v[32];
-      tmem_ld32(tmem_lane + kColD + cbase, v);             // columns past N3 hold stale data: unused
-      // logits pre-scaled by log2(e): softmax = 2^(l - max) / sum; loops stop at cnt
-      // (warp-uniform), so the registers stay statically indexed
-      constexpr float kLog2e = 1.4426950408889634f;
-      float lg[32];
-      float mx[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
-      float value = 0.0f;
-#pragma unroll
-      for (int i = 0; i < 32; i++) {
-        if (i > cnt) break;
-        const float x = __uint_as_float(v[i]) + s_b3[cbase + i];
-        lg[i] = x * kLog2e;
-        if (i < cnt) mx[i & 3] = fmaxf(mx[i & 3], lg[i]);
-        else value = x;
+      if (lane == 0) {
+        const uint32_t b0 = smem_addr(s_w3);
+        for (int kk = 0; kk < H / 16; kk++)
+          mma_ts(tmem_base + col_d3, tmem_base + kColH + kk * 8, make_desc(b0 + kk * 256, sbo_h),
+                 idesc_o, kk > 0);
+        mma_commit(bar_l3);
       }
-      const float m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-      float zz[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll
-      for (int i = 0; i < 32; i++) {
-        if (i >= cnt) break;
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(lg[i]) : "f"(lg[i] - m));
-        zz[i & 3] += lg[i];
+      if (!overlap_l1) {
+        bar_sync(2, kThreads);                            // output epilogue has read D
+        fence_after();
       }
-      const float z = (zz[0] + zz[1]) + (zz[2] + zz[3]);
-      const float inv = 1.0f / z;
-      float *dst = (half ? s_p1 : s_p0) + row * cnt;
-#pragma unroll
-      for (int i = 0; i < 32; i++) {
-        if (i >= cnt) break;
-        dst[i] = lg[i] * inv;
-      }
-      if (half) s_v[row] = value;
+      if (lane == 0 && has_next) issue_l1();              // runs during the output epilogue
     }
-    fence_before();
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    {
-      float *g0 = probs0 + r0 * A0, *g1 = probs1 + r0 * A1;
-      const uint32_t n0 = (uint32_t)valid * A0 * 4, n1 = (uint32_t)valid * A1 * 4;
-      const bool tma_ok = (((uintptr_t)g0 | (uintptr_t)g1 | n0 | n1) & 15) == 0 &&
-                          ((smem_addr(s_p0) | smem_addr(s_p1)) & 15) == 0;
-      if (tma_ok) {
-        if (tid == 0) {
-          tma_store(g0, smem_addr(s_p0), n0);
-          tma_store(g1, smem_addr(s_p1), n1);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        }
+  } else {
+    // ================= worker warps =================
+    // A operand of layer 1 = packed bf16 obs in TMEM columns kColA.. (lane = row): registers
+    // (fp32 obs prefetched one tile ahead) -> bf16 canonical tile in the shared staging buffer
+    // -> each thread copies its row's 16-byte chunks into TMEM (tcgen05.st).
+    auto build_a = [&](long long tile) {
+      // the staging buffer may still be read by the previous tile's output TMA store
+      if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      bar_sync(1, kWorkers);
+      if (single_batch) {
+        store_batch(0);
       } else {
-        for (int i = tid; i < valid * A0; i += kThreads) g0[i] = s_p0[i];
-        for (int i = tid; i < valid * A1; i += kThreads) g1[i] = s_p1[i];
+        for (int batch = 0; batch * kTasks < tasks_per_warp; batch++) {
+          load_batch(tile, batch);
+          store_batch(batch);
+        }
       }
-      if (values && tid < valid) values[r0 + tid] = s_v[tid];
+      bar_sync(1, kWorkers);
+      const int row = quad * 32 + lane;
+      const unsigned char *rp = s_a + (row >> 3) * (K1 / 8) * 128 + (row & 7) * 16;
+      for (int c = part; c < nchunk; c += kParts) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(rp + c * 128);
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                     ::"r"(tmem_lane + kColA + 4 * c), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                     : "memory");
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    };
+
+    if ((long long)blockIdx.x < n_tiles) {
+      build_a(blockIdx.x);
+      if (single_batch && (long long)blockIdx.x + gridDim.x < n_tiles)
+        load_batch((long long)blockIdx.x + gridDim.x, 0);
     }
-    fence_after();
-    __syncthreads();      // staging (aliases the A tile) free again; TMEM D free
+    fence_before();
+    bar_arrive(2, kThreads);                              // first A operand ready
+    mbar_wait(bar_w, 0);                                  // biases live in the weight blob
+
+    uint32_t phase = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, phase ^= 1) {
+      const long long r0 = tile * kTileM;
+      const int valid = (int)min((long long)kTileM, rows - r0);
+      const bool has_next = tile + gridDim.x < n_tiles;
+      MLP_MARK(0)   // tile start
+
+      // ---- layer 1 epilogue
+      mbar_wait(bar_l1, phase);
+      fence_after();
+      MLP_MARK(1)
+      hidden_epilogue(tmem_lane, kColH, s_b1, 32 * part, H);
+      fence_before();
+      bar_arrive(2, kThreads);
+      MLP_MARK(2)
+
+      // ---- while the tensor core runs layer 2: next tile's A operand
+      if (has_next) build_a(tile + gridDim.x);
+      MLP_MARK(3)
+
+      // ---- layer 2 epilogue (layer 2 is done with H1: packed in place)
+      mbar_wait(bar_l2, phase);
+      fence_after();
+      MLP_MARK(5)
+      hidden_epilogue(tmem_lane, kColH, s_b2, 32 * part, H);
+      fence_before();
+      bar_arrive(2, kThreads);
+      MLP_MARK(6)
+      // (the ~12k loads of a tile take a while to queue: do it while layer 3 runs)
+      if (has_next && single_batch && tile + 2 * (long long)gridDim.x < n_tiles)
+        load_batch(tile + 2 * (long long)gridDim.x, 0);
+      MLP_MARK(4)
+
+      // ---- output epilogue: bias, softmax of this part's head (+ value) -> staging
+      mbar_wait(bar_l3, phase);
+      fence_after();
+      MLP_MARK(7)
+      if (!has_next && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      if (!has_next) bar_sync(1, kWorkers);               // (build_a did this when there is a next tile)
+      if (part < 2) {
+        const int cbase = part ? A0 : 0, cnt = part ? A1 : A0;
+        const int row = quad * 32 + lane;                  // TMEM lane == row of the tile
+        uint32_t v[32];
+        tmem_ld32(tmem_lane + col_d3 + cbase, v);          // columns past N3 hold stale data: unused
+        // logits pre-scaled by log2(e): softmax = 2^(l - max) / sum.  Branch-free over 32
+        // statically indexed registers (predicated), four independent max / sum chains.
+        constexpr float kLog2e = 1.4426950408889634f;
+        float lg[32];
+        float mx[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+        float value = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+          const float x = __uint_as_float(v[i]) + s_b3[min(cbase + i, N3 - 1)];
+          lg[i] = i < cnt ? x * kLog2e : -CUDART_INF_F;
+          mx[i & 3] = fmaxf(mx[i & 3], lg[i]);
+          value = (i == cnt) ? x : value;
+        }
+        const float m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+        float zz[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(lg[i]) : "f"(lg[i] - m));   // 2^-inf = 0
+          zz[i & 3] += lg[i];
+        }
+        const float inv = 1.0f / ((zz[0] + zz[1]) + (zz[2] + zz[3]));
+        float *dst = (part ? s_p1 : s_p0) + row * cnt;
+#pragma unroll
+        for (int i = 0; i < 32; i++)
+          if (i < cnt) dst[i] = lg[i] * inv;
+        if (part) s_v[row] = value;
+      }
+      if (!overlap_l1) {
+        fence_before();
+        bar_arrive(2, kThreads);                           // D may be overwritten by the next layer 1
+      }
+      MLP_MARK(8)
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      bar_sync(1, kWorkers);
+      MLP_MARK(9)
+      {
+        float *g0 = probs0 + r0 * A0, *g1 = probs1 + r0 * A1;
+        const uint32_t n0 = (uint32_t)valid * A0 * 4, n1 = (uint32_t)valid * A1 * 4;
+        const bool tma_ok = (((uintptr_t)g0 | (uintptr_t)g1 | n0 | n1) & 15) == 0 &&
+                            ((smem_addr(s_p0) | smem_addr(s_p1)) & 15) == 0;
+        if (tma_ok) {
+          if (tid == 0) {                                  // completion is awaited in build_a
+            tma_store(g0, smem_addr(s_p0), n0);
+            tma_store(g1, smem_addr(s_p1), n1);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        } else {
+          for (int i = tid; i < valid * A0; i += kWorkers) g0[i] = s_p0[i];
+          for (int i = tid; i < valid * A1; i += kWorkers) g1[i] = s_p1[i];
+        }
+        if (values && tid < valid) values[r0 + tid] = s_v[tid];
+      }
+      MLP_MARK(10)
+#ifdef WDB_PHASE_CLOCKS
+      mark_tile++;
+#endif
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
 
+  fence_before();
   __syncthreads();
   if (warp == 0)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
@@ -506,6 +579,12 @@ bool mlp_shape_ok(int F, int H, int A0, int A1) {
 }
 
 }  // namespace
+
+#ifdef WDB_PHASE_CLOCKS
+WDB_API int wdb_debug_mlp_clocks(long long *host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, g_mlp_clk, sizeof(long long) * 96);
+}
+#endif
 
 WDB_API long long wdb_mlp_blob_bytes(int F, int H, int A0, int A1) {
   if (!mlp_shape_ok(F, H, A0, A1)) return -1;

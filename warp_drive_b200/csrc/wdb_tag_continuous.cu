@@ -1057,7 +1057,7 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
   }
 
   // bookkeeping words needed after the reward phase: requested now so that their latency
-  // hides behind it
+  // hides behind it (kept out of the prologue: four more live registers there cost more)
   int done_prev = 0, steps_prev = 0;
   float run_prev = 0.0f;
   long long pi_slot = 0;
