@@ -570,6 +570,9 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
     s_t[le] = t;
     s_nrun[le] = g_nrun;
   }
+  // s_nalive must be zero before the first atomicAdd of the kinematics (the fused variant
+  // has its barrier in the sampling phase)
+  if (!FUSED) __syncthreads();
 
   int act0 = 0, act1 = 0;
   if (FUSED) {
