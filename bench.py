@@ -193,38 +193,33 @@ def time_dominant_kernel(wrapper, engine, iters=30):
             "bytes_per_agent_step": nbytes}
 
 
-def time_e2e_host_buffers(wrapper, n_steps, warmup=3):
-    """Public-API env.step() with host buffers: H2D actions, step, D2H obs/rewards/done."""
+def time_e2e_host_buffers(wrapper, n_steps, warmup=3, n_copy_streams=4):
+    """Public-API env.step() with host buffers (EnvWrapper.step_with_host_buffers): H2D
+    actions, step, D2H obs/rewards/done, every step, the host waits for each result."""
     import torch
 
     dm = wrapper.cuda_data_manager
     actions_d = dm.data_on_device_via_torch("sampled_actions")
-    obs_d = dm.data_on_device_via_torch("observations")
-    rew_d = dm.data_on_device_via_torch("rewards")
-    done_d = dm.data_on_device_via_torch("_done_")
+    names = ("observations", "rewards", "_done_")
     rs = np.random.RandomState(0)
     host_actions = [torch.from_numpy(rs.randint(0, 21, tuple(actions_d.shape)).astype(np.int32)
                                      ).pin_memory() for _ in range(4)]
-    obs_h = torch.empty(obs_d.shape, dtype=obs_d.dtype).pin_memory()
-    rew_h = torch.empty(rew_d.shape, dtype=rew_d.dtype).pin_memory()
-    done_h = torch.empty(done_d.shape, dtype=done_d.dtype).pin_memory()
+    host_out = {}
+    for k in names:
+        dev = dm.data_on_device_via_torch(k)
+        host_out[k] = torch.empty(dev.shape, dtype=dev.dtype).pin_memory()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for i in range(warmup + n_steps):
         if i == warmup:
             torch.cuda.synchronize()
             start.record()
-        actions_d.copy_(host_actions[i % 4], non_blocking=True)
-        wrapper.step_all_envs()
-        obs_h.copy_(obs_d, non_blocking=True)
-        rew_h.copy_(rew_d, non_blocking=True)
-        done_h.copy_(done_d, non_blocking=True)
-        torch.cuda.current_stream().synchronize()   # the host consumes this step's result
+        wrapper.step_with_host_buffers(host_actions[i % 4], host_out, n_copy_streams)
         wrapper.reset_only_done_envs()
     end.record()
     torch.cuda.synchronize()
     ms = start.elapsed_time(end) / n_steps
     h2d = actions_d.numel() * 4
-    d2h = obs_d.numel() * 4 + rew_d.numel() * 4 + done_d.numel() * 4
+    d2h = sum(t.numel() * t.element_size() for t in host_out.values())
     return ms, h2d, d2h
 
 
@@ -328,6 +323,8 @@ def main():
                     help="run the policy forward through torch/cuBLAS instead of the fused "
                          "tcgen05 kernel (wdb_mlp_policy_forward)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--copy-streams", type=int, default=4,
+                    help="streams the e2e observation D2H copy is split over")
     ap.add_argument("--cta-threads", type=int, default=0,
                     help="A/B switch: thread budget of one tag_continuous CTA (wdb_set_option)")
     args = ap.parse_args()
@@ -403,7 +400,8 @@ def main():
     value = world * E * N * K / (elapsed_ms / 1000.0)
 
     # ---- e2e through the public API with host buffers (max over ranks)
-    e2e_ms, h2d, d2h = time_e2e_host_buffers(wrapper, n_steps=min(K, 50))
+    e2e_ms, h2d, d2h = time_e2e_host_buffers(wrapper, n_steps=min(K, 50),
+                                             n_copy_streams=args.copy_streams)
     t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -444,8 +442,9 @@ def main():
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
-                "path": "EnvWrapper.step_all_envs with pinned host actions in and "
-                        "observations/rewards/done out every step"},
+                "path": "EnvWrapper.step_with_host_buffers: pinned host actions in, "
+                        "observations/rewards/done out to pinned host memory every step "
+                        f"(obs copy split over {args.copy_streams} streams), host waits per step"},
         "gpu_launches": int(my_launches),
         "kernel_stats": {"exact_tie_path_agents": stats_timed[0], "tags": stats_timed[1],
                          "history_path_fallbacks": stats_timed[2],
@@ -462,7 +461,10 @@ def main():
             buf = (ctypes.c_longlong * 96)()
             raw.wdb_debug_mlp_clocks(buf)
             line["mlp_clocks_cta0"] = list(buf)
-    if not args.skip_cpu_baseline:
+    if world > 1:
+        line["cpu_baseline"] = {"value": None, "unit": "agent-steps/s", "cores": 0, "kind": "port",
+                                "sample": "measured at N=1 only (rank 0)"}
+    elif not args.skip_cpu_baseline:
         cores = os.cpu_count() or 1
         res = cpu_baseline(sample_steps=150, n_procs=cores)
         line["cpu_baseline"] = {

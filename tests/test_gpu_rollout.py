@@ -203,3 +203,26 @@ def test_engine_fused_matches_unfused_batches():
                            dm.data_on_device_via_torch("rewards")[:, i])
     assert int(e.num_completed_episodes) >= E      # 64 steps > one 40-step episode
     assert float(e.episodic_step_sum) / float(e.num_completed_episodes) <= 40
+
+
+def test_step_with_host_buffers_matches_pull():
+    """EnvWrapper.step_with_host_buffers (pinned host actions in; observations / rewards /
+    done out over several copy streams) returns exactly what step_all_envs followed by
+    pull_data_from_device returns."""
+    E = 64
+    wa, _, _ = _setup(E, 2)
+    wb, _, _ = _setup(E, 2)
+    rs = np.random.RandomState(5)
+    dma, dmb = wa.cuda_data_manager, wb.cuda_data_manager
+    names = ("observations", "rewards", "_done_")
+    host_out = {k: torch.empty(dma.data_on_device_via_torch(k).shape,
+                               dtype=dma.data_on_device_via_torch(k).dtype).pin_memory()
+                for k in names}
+    for _ in range(4):
+        acts = rs.randint(0, 21, tuple(dma.get_shape("sampled_actions"))).astype(np.int32)
+        wa.step_with_host_buffers(torch.from_numpy(acts).pin_memory(), host_out, n_copy_streams=3,
+                                  min_split_bytes=1024)   # force the split-copy path
+        dmb.data_on_device_via_torch("sampled_actions").copy_(torch.from_numpy(acts))
+        wb.step_all_envs()
+        for k in names:
+            assert np.array_equal(host_out[k].numpy(), dmb.pull_data_from_device(k)), k

@@ -441,6 +441,26 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
     }
   }
 
+  // which blocks of the observation tile can leave through the TMA (16-byte aligned shared /
+  // global addresses and size); decided here, used after the tile is complete
+  uint32_t out_mask = 0;   // bit p: policy block p goes by TMA;  bit 8: the [E,N,F] array
+  if (!P.use_full_obs && P.stage_obs) {
+    if (!FUSED) {
+      if (tma_ok(P.obs + (long long)env0 * N * F, smem_u32(s_tile), 4ull * envs_here * N * F))
+        out_mask |= 1u << 8;
+    } else {
+#pragma unroll
+      for (int p = 0; p < kMaxPolicies; p++) {
+        if (p < Q.n_policies && Q.obs_next[p]) {
+          const int np = Q.policy_size[p];
+          if (tma_ok(Q.obs_next[p] + (long long)env0 * np * F, smem_u32(s_tile + tile_base[p]),
+                     4ull * envs_here * np * F))
+            out_mask |= 1u << p;
+        }
+      }
+    }
+  }
+
   // ---- categorical sampling of both action heads (core/random.cu:51-85): the probability
   // blocks are requested first thing (TMA), they land while the state loads fly ----
   int p_off0[kMaxPolicies], p_off1[kMaxPolicies];
@@ -685,6 +705,23 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
   const float2 *epos = spos + le * N;
   const int *ealive = salive + le * N;
 
+  // bookkeeping words needed after the reward phase (loaded just before the feature phase)
+  int done_prev = 0, steps_prev = 0;
+  float run_prev = 0.0f;
+  long long pi_slot = 0;
+  auto load_bookkeeping = [&]() {
+    if (FUSED && active) {
+      done_prev = P.done[env];          // every thread: it derives the env's done flag itself
+      if (a == 0 && Q.step_running_sum) steps_prev = Q.step_running_sum[env];
+#pragma unroll
+      for (int p = 0; p < kMaxPolicies; p++) {
+        if (p == my_pol) {
+          pi_slot = (long long)env * Q.policy_size[p] + my_slot;
+          if (Q.reward_running_sum[p]) run_prev = Q.reward_running_sum[p][pi_slot];
+        }
+      }
+    }
+  };
   if (!P.use_full_obs) {
     uint32_t R[kListLen];
     int kk = 0;
@@ -924,6 +961,10 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
     }
 
     WDB_MARK(10)  // exact path done, ids stored
+    // bookkeeping words needed after the reward phase: requested here, so that they are not
+    // queued behind the burst of observation stores (kept out of the prologue: more live
+    // registers across the neighbour search cost more than they save)
+    load_bookkeeping();
     if (active) {
       float *orow = P.stage_obs ? (s_tile + s_rowbase[a] + le * s_rowstride[a])
                                 : (P.obs + (long long)gi * F);
@@ -967,6 +1008,7 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
       }
     }
   } else {
+    load_bookkeeping();
     // full observation (:55-113): one warp per row, lanes over the other agents, so every
     // feature plane of a row is written with unit-stride stores
     const int M = N - 1;
@@ -1026,22 +1068,7 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
   // and size are 16-byte aligned leaves through the TMA (cp.async.bulk), issued by one
   // thread now so that it overlaps the reward phase; the rest is copied by the threads at
   // the end of the kernel.
-  uint32_t out_mask = 0;   // bit p: policy block p went by TMA;  bit 8: the [E,N,F] array
   if (!P.use_full_obs && P.stage_obs) {
-    if (!FUSED) {
-      if (tma_ok(P.obs + (long long)env0 * N * F, smem_u32(s_tile), 4ull * envs_here * N * F))
-        out_mask |= 1u << 8;
-    } else {
-#pragma unroll
-      for (int p = 0; p < kMaxPolicies; p++) {
-        if (p < Q.n_policies && Q.obs_next[p]) {
-          const int np = Q.policy_size[p];
-          if (tma_ok(Q.obs_next[p] + (long long)env0 * np * F, smem_u32(s_tile + tile_base[p]),
-                     4ull * envs_here * np * F))
-            out_mask |= 1u << p;
-        }
-      }
-    }
     WDB_MARK(18)  // before the TMA store issue
     if (tid == 0 && out_mask) {
       if (out_mask & (1u << 8))
@@ -1057,26 +1084,6 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
     WDB_MARK(19)  // TMA stores issued
-  }
-
-  // bookkeeping words needed after the reward phase: requested now so that their latency
-  // hides behind it (kept out of the prologue: four more live registers there cost more)
-  int done_prev = 0, steps_prev = 0;
-  float run_prev = 0.0f;
-  long long pi_slot = 0;
-  if (FUSED && active) {
-    if (a == 0) {
-      done_prev = P.done[env];
-      if (Q.step_running_sum) steps_prev = Q.step_running_sum[env];
-    }
-    const int pol = my_pol, slot = my_slot;
-#pragma unroll
-    for (int p = 0; p < kMaxPolicies; p++) {
-      if (p == pol) {
-        pi_slot = (long long)env * Q.policy_size[p] + slot;
-        if (Q.reward_running_sum[p]) run_prev = Q.reward_running_sum[p][pi_slot];
-      }
-    }
   }
 
   WDB_MARK(20)  // bookkeeping loads requested
@@ -1155,10 +1162,11 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
     }
   }
   if (FUSED) {
-    __syncthreads();   // s_done visible
     if (active) {
       const int pol = my_pol;
-      const int d = s_done[le];
+      // done is sticky in the reference; every thread derives it (no barrier: s_done is only
+      // for the reset phase, which synchronises first)
+      const int d = done_now | (done_prev > 0 ? 1 : 0);
 #pragma unroll
       for (int p = 0; p < kMaxPolicies; p++) {
         if (p == pol) {

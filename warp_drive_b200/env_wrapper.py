@@ -158,6 +158,45 @@ class EnvWrapper:
         assert actions is not None, "Please provide actions to step with."
         return self.env.step(actions)
 
+    def step_with_host_buffers(self, host_actions, host_out, n_copy_streams=4,
+                               min_split_bytes=8 << 20):
+        """One env.step() for a HOST-side policy: pinned `host_actions` -> device, step,
+        then `observations` / `rewards` / `_done_` -> the pinned tensors in `host_out`
+        ({name: pinned CPU tensor}).  The large observation copy is split over
+        `n_copy_streams` CUDA streams (several copy engines in flight saturate the PCIe link
+        better than one); returns after everything has landed on the host.  The reference
+        has no such call: its users combine `push_data_to_device` / `step_all_envs` /
+        `pull_data_from_device` (data_manager.py:270-330), one blocking copy per array."""
+        import torch
+
+        assert self.env_backend != "cpu"
+        dm = self.cuda_data_manager
+        cur = torch.cuda.current_stream()
+        dm.data_on_device_via_torch("sampled_actions").copy_(host_actions, non_blocking=True)
+        self.env.step()
+        if not hasattr(self, "_copy_streams") or len(self._copy_streams) < n_copy_streams:
+            self._copy_streams = [torch.cuda.Stream() for _ in range(n_copy_streams)]
+            self._copy_events = [torch.cuda.Event() for _ in range(n_copy_streams)]
+        stepped = torch.cuda.Event()
+        stepped.record(cur)
+        for name, host in host_out.items():
+            dev = dm.data_on_device_via_torch(name)
+            if dev.numel() * dev.element_size() < min_split_bytes or n_copy_streams <= 1:
+                host.copy_(dev, non_blocking=True)
+                continue
+            d, h = dev.reshape(-1), host.reshape(-1)
+            chunk = (d.numel() + n_copy_streams - 1) // n_copy_streams
+            for i in range(n_copy_streams):
+                st = self._copy_streams[i]
+                st.wait_event(stepped)
+                with torch.cuda.stream(st):
+                    h[i * chunk:(i + 1) * chunk].copy_(d[i * chunk:(i + 1) * chunk],
+                                                       non_blocking=True)
+                self._copy_events[i].record(st)
+        for ev in getattr(self, "_copy_events", [])[:n_copy_streams]:
+            cur.wait_event(ev)
+        cur.synchronize()
+
     def obs_at_reset(self):
         return self.env.reset()
 
