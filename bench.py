@@ -416,8 +416,20 @@ def main():
     peaks, peak_src = measured_peaks()
     dk = time_dominant_kernel(wrapper, engine)
     achieved = dk["bytes_per_agent_step"] * E * N / (dk["ms_median"] * 1e-3) / 1e9
+    traffic = None      # DRAM bytes per launch from the committed ncu capture (same config only)
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles",
+                               "ncu_traffic.json")) as fh:
+            tr = json.load(fh).get(dk["kernel"])
+        if tr and tr["envs"] == E and tr["agents"] == N:
+            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+    except (OSError, ValueError, KeyError):
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
+                "traffic_note": "ncu dram bytes per launch (profiles/ncu_traffic.json); "
+                                "algorithmic bytes per launch = "
+                                f"{dk['bytes_per_agent_step'] * E * N}",
                 "kernel": dk["kernel"], "kernel_ms": dk["ms_median"],
                 "algorithmic_bytes_per_agent_step": dk["bytes_per_agent_step"],
                 "peak_source": peak_src, "l2": "flushed before every launch"}

@@ -43,7 +43,9 @@ long long wdb_launch_count(void);
 /* Tuning / A-B switches (results are identical either way).  "tc_history": use last step's
  * neighbour lists as a distance threshold in the tag_continuous k-nearest search (1, default)
  * or always run the full sorting network (0).  "tc_cta_threads": thread budget of one
- * tag_continuous CTA (32..320, default 320); a CTA takes floor(budget / agents) envs. */
+ * tag_continuous CTA (32..320, default 320); a CTA takes floor(budget / agents) envs.
+ * "mlp_max_ctas": persistent CTAs (= SMs) the following wdb_mlp_policy_forward launches may
+ * use (0 = all): two policies' forwards can then run concurrently on disjoint SMs. */
 int wdb_set_option(const char *name, int value);
 
 /* ------------------------------------------------------------------ RNG ------ */

@@ -4,7 +4,7 @@
 TAG=${1:-x}
 mkdir -p gpurun_out
 if [ "$2" != "notests" ]; then
-  timeout 600 python -m pytest tests -m gpu -x -q --tb=short 2>&1 | tail -25
+  timeout 900 python -m pytest tests -m gpu -x -q --tb=short --durations=6 2>&1 | tail -30
 fi
 timeout 300 python bench.py --steps 100 --warmup 20 --skip-cpu-baseline > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
 python - <<PY

@@ -586,6 +586,10 @@ WDB_API int wdb_debug_mlp_clocks(long long *host_out) {
 }
 #endif
 
+// wdb_set_option("mlp_max_ctas", n): CTAs (= SMs, one persistent CTA each) the NEXT forward
+// launches may use; 0 = all.  Lets two policies' forwards run side by side on disjoint SMs.
+int g_mlp_max_ctas = 0;
+
 WDB_API long long wdb_mlp_blob_bytes(int F, int H, int A0, int A1) {
   if (!mlp_shape_ok(F, H, A0, A1)) return -1;
   const MlpHeader hd = make_header(F, H, A0, A1);
@@ -635,7 +639,8 @@ WDB_API int wdb_mlp_policy_forward(void *stream, const void *blob, int F, int H,
     configured = smem;
   }
   const long long n_tiles = (rows + kTileM - 1) / kTileM;
-  const int grid = (int)min((long long)kNumSMs, n_tiles);
+  const int sm_budget = (g_mlp_max_ctas > 0 && g_mlp_max_ctas < kNumSMs) ? g_mlp_max_ctas : kNumSMs;
+  const int grid = (int)min((long long)sm_budget, n_tiles);
   mlp_forward_kernel<<<grid, kThreads, smem, as_stream(stream)>>>(
       reinterpret_cast<const unsigned char *>(blob), obs, rows, probs0, probs1, values);
   return finish_launch();

@@ -1335,6 +1335,9 @@ int launch_t(const TcParams &P, const FusedParams &Q, const LaunchPlan &plan, cu
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)plan.smem);
     if (e != cudaSuccess) return (int)e;
+    // all of the SM's unified L1 as shared memory: the CTAs are sized to fill it
+    cudaFuncSetAttribute(tag_continuous_kernel<FUSED, MAXT>,
+                         cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     configured = plan.smem;
   }
   tag_continuous_kernel<FUSED, MAXT><<<plan.grid, plan.block, plan.smem, st>>>(P, Q);
@@ -1387,6 +1390,8 @@ int fill_params(TcParams &P, int n_envs, int n_agents, float *loc_x, float *loc_
 
 }  // namespace
 
+extern int g_mlp_max_ctas;   // wdb_mlp.cu
+
 WDB_API int wdb_set_option(const char *name, int value) {
   if (!name) return (int)cudaErrorInvalidValue;
   auto is = [&](const char *want) {
@@ -1395,6 +1400,11 @@ WDB_API int wdb_set_option(const char *name, int value) {
     return !want[i] && !name[i];
   };
   if (is("tc_history")) { g_tc_history = value ? 1 : 0; return 0; }
+  if (is("mlp_max_ctas")) {
+    if (value < 0) return (int)cudaErrorInvalidValue;
+    g_mlp_max_ctas = value;
+    return 0;
+  }
   if (is("tc_cta_threads")) {
     if (value < 32 || value > 320) return (int)cudaErrorInvalidValue;
     g_tc_threads = value;

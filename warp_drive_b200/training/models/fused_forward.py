@@ -51,9 +51,11 @@ class FusedPolicyForward:
             self.F, self.H, self.A0, self.A1), "mlp_pack_weights")
         self._keep = ts
 
-    def __call__(self, obs, probs0, probs1, values=None):
-        """obs [..., F] float32 contiguous -> probs0 [..., A0], probs1 [..., A1] (written)."""
+    def __call__(self, obs, probs0, probs1, values=None, max_ctas=0):
+        """obs [..., F] float32 contiguous -> probs0 [..., A0], probs1 [..., A1] (written).
+        max_ctas > 0 restricts the launch to that many SMs (side-by-side forwards)."""
         rows = obs.numel() // self.F
+        _lib.check(self.lib.wdb_set_option(b"mlp_max_ctas", int(max_ctas)), "set_option")
         _lib.check(self.lib.wdb_mlp_policy_forward(
             _lib.stream_ptr(), _lib.ptr(self.blob), self.F, self.H, self.A0, self.A1,
             _lib.ptr(obs), rows, _lib.ptr(probs0), _lib.ptr(probs1), _lib.ptr(values)),

@@ -130,6 +130,42 @@ class RolloutEngine:
         probs, _ = model(obs_p)
         return [q.contiguous() for q in probs]
 
+    def _forward_side_by_side(self, obs_in, probs):
+        """Every policy's fused forward, concurrently: the persistent MLP kernel uses one CTA
+        per SM, so the SMs are split between the policies in proportion to their rows and the
+        smaller policies run on side streams (fork/join by events, also under graph capture).
+        Sequential launches would each pay the 195 KB weight load and leave most SMs idle
+        during the small policy's single wave."""
+        if len(self.policies) == 1:
+            p = self.policies[0]
+            self.fused_forward[p](obs_in[p], probs[p][0], probs[p][1])
+            return
+        if not hasattr(self, "_fwd_plan"):
+            n_sm = torch.cuda.get_device_properties(self.dm.device).multi_processor_count
+            rows = {p: obs_in[p].numel() // obs_in[p].shape[-1] for p in self.policies}
+            total = sum(rows.values())
+            order = sorted(self.policies, key=lambda p: -rows[p])
+            share = {p: max(1, min(n_sm - 1, -(-n_sm * rows[p] // total))) for p in order[1:]}
+            share[order[0]] = max(1, n_sm - sum(share.values()))
+            self._fwd_plan = (order, share)
+            self._fwd_streams = [torch.cuda.Stream() for _ in order[1:]]
+        order, share = self._fwd_plan
+        cur = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        joins = []
+        for p, st in zip(order[1:], self._fwd_streams):
+            st.wait_event(fork)
+            with torch.cuda.stream(st):
+                self.fused_forward[p](obs_in[p], probs[p][0], probs[p][1], max_ctas=share[p])
+                ev = torch.cuda.Event()
+                ev.record(st)
+            joins.append(ev)
+        p = order[0]
+        self.fused_forward[p](obs_in[p], probs[p][0], probs[p][1], max_ctas=share[p])
+        for ev in joins:
+            cur.wait_event(ev)
+
     def step_fused(self, t, uniforms=None):
         """One timestep = policy forwards + ONE libwdb200 launch."""
         with torch.no_grad():
@@ -157,8 +193,7 @@ class RolloutEngine:
                 actions_batch = rewards_batch = done_batch = None
             if self.fused_forward:
                 probs = self._probs
-                for p in self.policies:
-                    self.fused_forward[p](obs_in[p], probs[p][0], probs[p][1])
+                self._forward_side_by_side(obs_in, probs)
             else:
                 probs = {p: self._forward(self.models[p], obs_in[p]) for p in self.policies}
             self.fused.launch(probs, actions_batch=actions_batch, rewards_batch=rewards_batch,
