@@ -110,7 +110,7 @@ class ClockSampler:
 
 
 def build_engine(n_envs, seed, graph_steps, use_graph=True, forward_dtype=None,
-                 fused_forward=True):
+                 fused_forward=True, obs_tiles=False):
     import torch
 
     from warp_drive_b200.env_wrapper import EnvWrapper
@@ -139,7 +139,7 @@ def build_engine(n_envs, seed, graph_steps, use_graph=True, forward_dtype=None,
     engine = RolloutEngine(wrapper, models, policy_map, sampler, graph_steps,
                            use_cuda_graph=use_graph, forward_dtype=forward_dtype,
                            write_observations=False, stats=stats,
-                           use_fused_forward=fused_forward)
+                           use_fused_forward=fused_forward, use_obs_tiles=obs_tiles)
     engine.stats = stats
     return wrapper, engine, sampler, policy_map
 
@@ -183,7 +183,8 @@ def time_dominant_kernel(wrapper, engine, iters=30):
                 ev[i - 3][0].record()
             engine.fused.launch(probs, actions_batch=slots["sampled_actions"],
                                 rewards_batch=slots["rewards"],
-                                obs_next=slots["processed_observations"], done_batch=done_b)
+                                obs_next=slots["processed_observations"], done_batch=done_b,
+                                obs_next_tiles=engine.obs_tiles or None)
             if i >= 3:
                 ev[i - 3][1].record()
         name, nbytes = "tag_continuous_kernel<true> (fused sample+step+push+reset)", BYTES_FUSED
@@ -323,6 +324,9 @@ def main():
                     help="run the policy forward through torch/cuBLAS instead of the fused "
                          "tcgen05 kernel (wdb_mlp_policy_forward)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--obs-tiles", action="store_true",
+                    help="A/B switch: the env step also emits the bf16 MMA-ready copy of the "
+                         "observations and the forward reads that (wdb_mlp_policy_forward_tiles)")
     ap.add_argument("--copy-streams", type=int, default=4,
                     help="streams the e2e observation D2H copy is split over")
     ap.add_argument("--cta-threads", type=int, default=0,
@@ -357,7 +361,7 @@ def main():
     wrapper, engine, sampler, policy_map = build_engine(
         args.envs, seed=1234 + rank, graph_steps=T, use_graph=not args.no_graph,
         forward_dtype=torch.bfloat16 if args.forward_precision == "bf16" else None,
-        fused_forward=not args.torch_forward)
+        fused_forward=not args.torch_forward, obs_tiles=args.obs_tiles)
     E, N = wrapper.n_envs, wrapper.n_agents
 
     def barrier():

@@ -190,6 +190,9 @@ typedef struct wdb_tc_policy_io {    /* per policy; agents of a policy are [E, N
   float *obs_next;                   /* [E, Np, F]  where the next forward reads, or NULL */
   float *reward_running_sum;         /* [E, Np] or NULL */
   float *episodic_reward_sum;        /* scalar or NULL */
+  void *obs_next_tiles;              /* optional bf16 copy of obs_next in the A-operand tile
+                                      * layout of wdb_mlp_policy_forward_tiles
+                                      * (wdb_mlp_obs_tiles_bytes bytes, 16-byte aligned), or NULL */
 } wdb_tc_policy_io;
 
 typedef struct wdb_tc_rollout {
@@ -240,6 +243,17 @@ int wdb_mlp_pack_weights(void *stream, void *blob, const float *w1, const float 
 int wdb_mlp_policy_forward(void *stream, const void *blob, int F, int H, int A0, int A1,
                            const float *obs, long long rows, float *probs0, float *probs1,
                            float *values /* may be NULL */);
+/* The same forward fed from the bf16 copy of the observations in A-operand layout: 128-row
+ * tiles, each one contiguous block (canonical K-major layout, K padded to a multiple of 16
+ * with zeros) that the kernel fetches with one TMA bulk copy.  wdb_mlp_pack_obs builds it
+ * from fp32 obs [rows, F]; the fused tag_continuous step writes it directly
+ * (wdb_tc_policy_io.obs_next_tiles).  No reference counterpart: the reference always runs
+ * the torch forward on the fp32 batch slice (trainer_base.py:437-464). */
+long long wdb_mlp_obs_tiles_bytes(int F, long long rows);
+int wdb_mlp_pack_obs(void *stream, const float *obs, long long rows, int F, void *tiles);
+int wdb_mlp_policy_forward_tiles(void *stream, const void *blob, int F, int H, int A0, int A1,
+                                 const void *obs_tiles, long long rows, float *probs0,
+                                 float *probs1, float *values /* may be NULL */);
 
 /* ------------------------------------------------------------------ update ---- */
 /* Bootstrapped discounted returns of the A2C/PPO update, backwards in time with done

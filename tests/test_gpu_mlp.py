@@ -59,3 +59,32 @@ def test_fused_mlp_matches_torch(F, H, A0, A1, rows):
     with torch.no_grad():
         (q0, _), _ = model(obs)
     assert (p0 - q0).abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize("F,H,A0,A1,rows", [(71, 256, 21, 21, 2000 * 100), (71, 256, 21, 21, 10000),
+                                            (71, 256, 21, 21, 77), (36, 64, 21, 21, 333),
+                                            (200, 128, 30, 10, 5000)])
+def test_fused_mlp_from_tiles_equals_fp32_path(F, H, A0, A1, rows):
+    """wdb_mlp_pack_obs + wdb_mlp_policy_forward_tiles: the same bf16 A operand reaches the
+    tensor cores as on the fp32-obs path, so the outputs are IDENTICAL bit for bit."""
+    from warp_drive_b200.training.models.fused_forward import FusedPolicyForward
+
+    torch.manual_seed(7 * F + H)
+    model = _Model(F, H, A0, A1).cuda()
+    fwd = FusedPolicyForward(model)
+    obs = torch.randn(rows, F, device="cuda")
+    outs = []
+    for use_tiles in (False, True):
+        p0 = torch.full((rows, A0), -1.0, device="cuda")
+        p1 = torch.full((rows, A1), -1.0, device="cuda")
+        v = torch.full((rows,), -1.0, device="cuda")
+        if use_tiles:
+            tiles = torch.full((fwd.tiles_bytes(rows),), 0xFF, dtype=torch.uint8, device="cuda")
+            fwd.pack_obs(obs, tiles)          # must overwrite every byte it later reads
+            fwd.forward_tiles(tiles, rows, p0, p1, v)
+        else:
+            fwd(obs, p0, p1, v)
+        outs.append((p0, p1, v))
+    torch.cuda.synchronize()
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)

@@ -140,7 +140,7 @@ def test_fused_step_without_reset_keeps_done_set():
                        dm.data_on_device_via_torch("loc_x_at_reset"))
 
 
-def _engine(E, T, use_graph, fused, seed=3):
+def _engine(E, T, use_graph, fused, seed=3, **engine_kw):
     from warp_drive_b200.training.models.fully_connected import FullyConnected
     from warp_drive_b200.training.rollout import RolloutEngine
 
@@ -149,7 +149,8 @@ def _engine(E, T, use_graph, fused, seed=3):
     cfg = {"type": "fully_connected", "fc_dims": [32, 32], "model_ckpt_filepath": ""}
     models = {p: FullyConnected(w, cfg, p, pm).cuda().eval() for p in pm}
     w.reset_all_envs()
-    eng = RolloutEngine(w, models, pm, s, T, use_cuda_graph=use_graph, use_fused_step=fused)
+    eng = RolloutEngine(w, models, pm, s, T, use_cuda_graph=use_graph, use_fused_step=fused,
+                        **engine_kw)
     return w, eng, pm
 
 
@@ -226,3 +227,26 @@ def test_step_with_host_buffers_matches_pull():
         wb.step_all_envs()
         for k in names:
             assert np.array_equal(host_out[k].numpy(), dmb.pull_data_from_device(k)), k
+
+
+def test_engine_obs_tiles_matches_fp32_forward():
+    """use_obs_tiles=True: the fused env step also emits the bf16 MMA-ready copy of the next
+    observations (incl. the rows of envs that reset) and the forward reads that copy through
+    the TMA.  The A operand is the same bf16 data either way, so whole rollouts -- several
+    episodes, with resets -- fill identical training batches."""
+    E, T = 40, 16                                   # 40 x 20 runners = 800 rows: partial last tile
+    wa, ea, pm = _engine(E, T, True, True, use_obs_tiles=True)
+    wb, eb, _ = _engine(E, T, True, True, use_obs_tiles=False)
+    assert ea.obs_tiles and not eb.obs_tiles
+    for _ in range(6):                              # 96 steps > 2 episodes of 40 steps
+        ea.rollout()
+        eb.rollout()
+    torch.cuda.synchronize()
+    for p in pm:
+        for name in (f"processed_observations_batch_{p}", f"sampled_actions_batch_{p}",
+                     f"rewards_batch_{p}"):
+            ta = wa.cuda_data_manager.data_on_device_via_torch(name)
+            tb = wb.cuda_data_manager.data_on_device_via_torch(name)
+            assert torch.equal(ta, tb), name
+    assert int(ea.num_completed_episodes) == int(eb.num_completed_episodes) > 0
+

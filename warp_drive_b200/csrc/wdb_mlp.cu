@@ -215,10 +215,18 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t tmem_lane_base, uint32_
 // instruction latency exposed; four hide most of it.)  The A operand of layer 1 also lives in TMEM: the NEXT tile's obs
 // (prefetched into registers one tile ahead) are converted and copied there while the tensor
 // core runs layer 2 of the current tile, so the obs path never sits on the critical path.
+// TILES = false: `input` is the fp32 obs [rows, F]; TILES = true: `input` is the bf16 copy of
+// the obs already in A-operand layout (128-row tiles of the canonical K-major layout, K
+// padded with zeros -- written by wdb_mlp_pack_obs or by the env-step kernel's epilogue): a
+// tile is then ONE 16-byte-aligned contiguous block that the TMA drops into the staging
+// buffer, and the whole fp32 obs path (4-byte loads, conversion, scatter) disappears.
+template <bool TILES>
 __global__ void __launch_bounds__(kThreads, 1)
-mlp_forward_kernel(const unsigned char *__restrict__ blob, const float *__restrict__ obs,
+mlp_forward_kernel(const unsigned char *__restrict__ blob, const void *__restrict__ input,
                    long long rows, float *__restrict__ probs0, float *__restrict__ probs1,
                    float *__restrict__ values) {
+  const float *obs = reinterpret_cast<const float *>(input);
+  const unsigned char *tiles = reinterpret_cast<const unsigned char *>(input);
   extern __shared__ __align__(128) unsigned char smem[];
 #ifdef WDB_PHASE_CLOCKS
   const long long mlp_t0 = clock64();
@@ -236,7 +244,7 @@ mlp_forward_kernel(const unsigned char *__restrict__ blob, const float *__restri
   unsigned char *s_a = s_w + ((w_bytes + 127) & ~127);   // A tile (layer 1) / output staging
   const int a_bytes = max(kTileM * K1 * 2, kTileM * (A0 + A1 + 1) * 4);
   unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(s_a + ((a_bytes + 15) & ~15));
-  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 4);
+  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(s_bar + 5);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quad = warp & 3, part = warp >> 2;
@@ -244,12 +252,14 @@ mlp_forward_kernel(const unsigned char *__restrict__ blob, const float *__restri
   const uint32_t bar_l1 = smem_addr(&s_bar[1]);          // layer-1 / 2 / 3 accumulators complete
   const uint32_t bar_l2 = smem_addr(&s_bar[2]);
   const uint32_t bar_l3 = smem_addr(&s_bar[3]);
+  const uint32_t bar_a = smem_addr(&s_bar[4]);           // TILES: next A tile landed in the staging buffer
 
   if (tid == 0) {
     mbar_init(bar_w, 1);
     mbar_init(bar_l1, 1);
     mbar_init(bar_l2, 1);
     mbar_init(bar_l3, 1);
+    mbar_init(bar_a, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -313,7 +323,7 @@ mlp_forward_kernel(const unsigned char *__restrict__ blob, const float *__restri
       }
     }
   };
-  if (single_batch && warp < kWarps && (long long)blockIdx.x < n_tiles) load_batch(blockIdx.x, 0);
+  if (!TILES && single_batch && warp < kWarps && (long long)blockIdx.x < n_tiles) load_batch(blockIdx.x, 0);
 
   const uint32_t idesc_h = make_idesc(kTileM, H);
   const uint32_t idesc_o = make_idesc(kTileM, N3);
@@ -373,7 +383,31 @@ mlp_forward_kernel(const unsigned char *__restrict__ blob, const float *__restri
     // A operand of layer 1 = packed bf16 obs in TMEM columns kColA.. (lane = row): registers
     // (fp32 obs prefetched one tile ahead) -> bf16 canonical tile in the shared staging buffer
     // -> each thread copies its row's 16-byte chunks into TMEM (tcgen05.st).
+    const uint32_t tile_bytes = (uint32_t)kTileM * K1 * 2;
+    uint32_t a_phase = 0;
+    // TILES: thread 0 requests tile `t` (the staging buffer must be free: the previous output
+    // store has read it, and every worker is past its reads -- see the end of the tile loop)
+    auto request_tile = [&](long long t) {
+      if (tid == 0) {
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        mbar_expect_tx(bar_a, tile_bytes);
+        tma_load(smem_addr(s_a), tiles + t * tile_bytes, tile_bytes, bar_a);
+      }
+    };
     auto build_a = [&](long long tile) {
+      if (TILES) {
+        mbar_wait(bar_a, a_phase); a_phase ^= 1;          // the TMA wrote the canonical tile
+        const int row = quad * 32 + lane;
+        const unsigned char *rp = s_a + (row >> 3) * (K1 / 8) * 128 + (row & 7) * 16;
+        for (int c = part; c < nchunk; c += kParts) {
+          const uint4 v = *reinterpret_cast<const uint4 *>(rp + c * 128);
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                       ::"r"(tmem_lane + kColA + 4 * c), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                       : "memory");
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        return;
+      }
       // the staging buffer may still be read by the previous tile's output TMA store
       if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       bar_sync(1, kWorkers);
@@ -398,53 +432,24 @@ mlp_forward_kernel(const unsigned char *__restrict__ blob, const float *__restri
     };
 
     if ((long long)blockIdx.x < n_tiles) {
+      if (TILES) request_tile(blockIdx.x);
       build_a(blockIdx.x);
-      if (single_batch && (long long)blockIdx.x + gridDim.x < n_tiles)
+      if (!TILES && single_batch && (long long)blockIdx.x + gridDim.x < n_tiles)
         load_batch((long long)blockIdx.x + gridDim.x, 0);
     }
     fence_before();
     bar_arrive(2, kThreads);                              // first A operand ready
     mbar_wait(bar_w, 0);                                  // biases live in the weight blob
 
-    uint32_t phase = 0;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, phase ^= 1) {
-      const long long r0 = tile * kTileM;
+    // ---- output epilogue of tile `tl` (mbarrier parity `ph`): bias, softmax of this part's
+    // head (+ value) -> staging -> TMA bulk store.  The caller guarantees that the staging
+    // buffer is free (previous store read, no worker still reading it).
+    auto output_epilogue = [&](long long tl, uint32_t ph) {
+      const long long r0 = tl * kTileM;
       const int valid = (int)min((long long)kTileM, rows - r0);
-      const bool has_next = tile + gridDim.x < n_tiles;
-      MLP_MARK(0)   // tile start
-
-      // ---- layer 1 epilogue
-      mbar_wait(bar_l1, phase);
-      fence_after();
-      MLP_MARK(1)
-      hidden_epilogue(tmem_lane, kColH, s_b1, 32 * part, H);
-      fence_before();
-      bar_arrive(2, kThreads);
-      MLP_MARK(2)
-
-      // ---- while the tensor core runs layer 2: next tile's A operand
-      if (has_next) build_a(tile + gridDim.x);
-      MLP_MARK(3)
-
-      // ---- layer 2 epilogue (layer 2 is done with H1: packed in place)
-      mbar_wait(bar_l2, phase);
-      fence_after();
-      MLP_MARK(5)
-      hidden_epilogue(tmem_lane, kColH, s_b2, 32 * part, H);
-      fence_before();
-      bar_arrive(2, kThreads);
-      MLP_MARK(6)
-      // (the ~12k loads of a tile take a while to queue: do it while layer 3 runs)
-      if (has_next && single_batch && tile + 2 * (long long)gridDim.x < n_tiles)
-        load_batch(tile + 2 * (long long)gridDim.x, 0);
-      MLP_MARK(4)
-
-      // ---- output epilogue: bias, softmax of this part's head (+ value) -> staging
-      mbar_wait(bar_l3, phase);
+      mbar_wait(bar_l3, ph);
       fence_after();
       MLP_MARK(7)
-      if (!has_next && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      if (!has_next) bar_sync(1, kWorkers);               // (build_a did this when there is a next tile)
       if (part < 2) {
         const int cbase = part ? A0 : 0, cnt = part ? A1 : A0;
         const int row = quad * 32 + lane;                  // TMEM lane == row of the tile
@@ -484,28 +489,83 @@ mlp_forward_kernel(const unsigned char *__restrict__ blob, const float *__restri
       MLP_MARK(8)
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       bar_sync(1, kWorkers);
-      MLP_MARK(9)
-      {
-        float *g0 = probs0 + r0 * A0, *g1 = probs1 + r0 * A1;
-        const uint32_t n0 = (uint32_t)valid * A0 * 4, n1 = (uint32_t)valid * A1 * 4;
-        const bool tma_ok = (((uintptr_t)g0 | (uintptr_t)g1 | n0 | n1) & 15) == 0 &&
-                            ((smem_addr(s_p0) | smem_addr(s_p1)) & 15) == 0;
-        if (tma_ok) {
-          if (tid == 0) {                                  // completion is awaited in build_a
-            tma_store(g0, smem_addr(s_p0), n0);
-            tma_store(g1, smem_addr(s_p1), n1);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          }
-        } else {
-          for (int i = tid; i < valid * A0; i += kWorkers) g0[i] = s_p0[i];
-          for (int i = tid; i < valid * A1; i += kWorkers) g1[i] = s_p1[i];
+      float *g0 = probs0 + r0 * A0, *g1 = probs1 + r0 * A1;
+      const uint32_t n0 = (uint32_t)valid * A0 * 4, n1 = (uint32_t)valid * A1 * 4;
+      const bool tma_ok = (((uintptr_t)g0 | (uintptr_t)g1 | n0 | n1) & 15) == 0 &&
+                          ((smem_addr(s_p0) | smem_addr(s_p1)) & 15) == 0;
+      if (tma_ok) {
+        if (tid == 0) {                                    // its completion is awaited before the
+          tma_store(g0, smem_addr(s_p0), n0);              // staging buffer is written again
+          tma_store(g1, smem_addr(s_p1), n1);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
-        if (values && tid < valid) values[r0 + tid] = s_v[tid];
+      } else {
+        for (int i = tid; i < valid * A0; i += kWorkers) g0[i] = s_p0[i];
+        for (int i = tid; i < valid * A1; i += kWorkers) g1[i] = s_p1[i];
       }
+      if (values && tid < valid) values[r0 + tid] = s_v[tid];
       MLP_MARK(10)
+    };
+
+    // With a separate layer-3 accumulator the output epilogue of tile t is DEFERRED into the
+    // layer-2 window of tile t+1: the long softmax runs while the tensor core is busy with the
+    // 16 biggest MMAs instead of extending the critical path.
+    const bool deferred = overlap_l1;
+    uint32_t phase = 0;
+    long long prev_tile = -1;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, phase ^= 1) {
+      const bool has_next = tile + gridDim.x < n_tiles;
+      MLP_MARK(0)   // tile start
+      if (TILES && has_next) {
+        bar_sync(1, kWorkers);                             // everyone is done with the staging buffer
+        request_tile(tile + gridDim.x);                    // lands during epilogue 1 / layer 2
+      }
+
+      // ---- layer 1 epilogue
+      mbar_wait(bar_l1, phase);
+      fence_after();
+      MLP_MARK(1)
+      hidden_epilogue(tmem_lane, kColH, s_b1, 32 * part, H);
+      fence_before();
+      bar_arrive(2, kThreads);
+      MLP_MARK(2)
+
+      // ---- while the tensor core runs layer 2: next tile's A operand, previous tile's output
+      if (has_next) build_a(tile + gridDim.x);
+      MLP_MARK(3)
+      if (deferred && prev_tile >= 0) {
+        if (!has_next && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        bar_sync(1, kWorkers);                             // staging: store read, A copy finished
+        output_epilogue(prev_tile, phase ^ 1);
+      }
+
+      // ---- layer 2 epilogue (layer 2 is done with H1: packed in place)
+      mbar_wait(bar_l2, phase);
+      fence_after();
+      MLP_MARK(5)
+      hidden_epilogue(tmem_lane, kColH, s_b2, 32 * part, H);
+      fence_before();
+      bar_arrive(2, kThreads);
+      MLP_MARK(6)
+      // (the ~12k loads of a tile take a while to queue: do it while layer 3 runs)
+      if (!TILES && has_next && single_batch && tile + 2 * (long long)gridDim.x < n_tiles)
+        load_batch(tile + 2 * (long long)gridDim.x, 0);
+      MLP_MARK(4)
+
+      if (!deferred) {
+        if (!has_next && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (!has_next) bar_sync(1, kWorkers);             // (build_a did this when there is a next tile)
+        output_epilogue(tile, phase);
+      }
+      prev_tile = tile;
 #ifdef WDB_PHASE_CLOCKS
       mark_tile++;
 #endif
+    }
+    if (deferred && prev_tile >= 0) {
+      if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      bar_sync(1, kWorkers);
+      output_epilogue(prev_tile, phase ^ 1);
     }
     if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
@@ -623,17 +683,21 @@ WDB_API int wdb_mlp_pack_weights(void *stream, void *blob, const float *w1, cons
   return finish_launch();
 }
 
-WDB_API int wdb_mlp_policy_forward(void *stream, const void *blob, int F, int H, int A0, int A1,
-                                   const float *obs, long long rows, float *probs0,
-                                   float *probs1, float *values) {
-  if (!blob || !obs || !probs0 || !probs1 || rows <= 0) return (int)cudaErrorInvalidValue;
+namespace {
+
+template <bool TILES>
+int launch_forward(void *stream, const void *blob, int F, int H, int A0, int A1,
+                   const void *input, long long rows, float *probs0, float *probs1,
+                   float *values) {
+  if (!blob || !input || !probs0 || !probs1 || rows <= 0) return (int)cudaErrorInvalidValue;
   if (!mlp_shape_ok(F, H, A0, A1)) return (int)cudaErrorInvalidValue;
+  if (TILES && (reinterpret_cast<uintptr_t>(input) & 15)) return (int)cudaErrorInvalidValue;
   const MlpHeader hd = make_header(F, H, A0, A1);
   const size_t smem = mlp_smem_bytes(hd);
   if (smem > 227 * 1024) return (int)cudaErrorInvalidValue;
   static size_t configured = 0;
   if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(mlp_forward_kernel,
+    cudaError_t e = cudaFuncSetAttribute(mlp_forward_kernel<TILES>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     configured = smem;
@@ -641,7 +705,64 @@ WDB_API int wdb_mlp_policy_forward(void *stream, const void *blob, int F, int H,
   const long long n_tiles = (rows + kTileM - 1) / kTileM;
   const int sm_budget = (g_mlp_max_ctas > 0 && g_mlp_max_ctas < kNumSMs) ? g_mlp_max_ctas : kNumSMs;
   const int grid = (int)min((long long)sm_budget, n_tiles);
-  mlp_forward_kernel<<<grid, kThreads, smem, as_stream(stream)>>>(
-      reinterpret_cast<const unsigned char *>(blob), obs, rows, probs0, probs1, values);
+  mlp_forward_kernel<TILES><<<grid, kThreads, smem, as_stream(stream)>>>(
+      reinterpret_cast<const unsigned char *>(blob), input, rows, probs0, probs1, values);
   return finish_launch();
+}
+
+// fp32 obs [rows, F] -> bf16 A-operand tiles (128 rows x K1, canonical K-major layout, K
+// padding and the rows of the last tile beyond `rows` = 0): one thread per 16-byte chunk
+__global__ void pack_obs_kernel(const float *__restrict__ obs, long long rows, int F, int K1,
+                                unsigned char *__restrict__ tiles) {
+  const int nchunk = K1 / 8;
+  const long long n_tiles = (rows + kTileM - 1) / kTileM;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_tiles * kTileM * nchunk) return;
+  // consecutive threads: the 8 rows of a core matrix, then the next chunk of the same rows
+  const long long grp = i / (8 * nchunk);                 // 8-row group (global)
+  const int in = (int)(i - grp * 8 * nchunk);
+  const int c = in >> 3, rr = in & 7;
+  const long long row = grp * 8 + rr;
+  float v[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++)
+    v[k] = (row < rows && 8 * c + k < F) ? obs[row * F + 8 * c + k] : 0.0f;
+  uint4 o;
+  o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+  const long long t = row >> 7;
+  const int r = (int)(row & 127);
+  *reinterpret_cast<uint4 *>(tiles + t * ((long long)kTileM * K1 * 2) + (r >> 3) * (K1 * 16) +
+                             c * 128 + (r & 7) * 16) = o;
+}
+
+}  // namespace
+
+WDB_API long long wdb_mlp_obs_tiles_bytes(int F, long long rows) {
+  if (F < 1 || F > 256 || rows <= 0) return -1;
+  const long long n_tiles = (rows + kTileM - 1) / kTileM;
+  return n_tiles * kTileM * round_up(F, 16) * 2;
+}
+
+WDB_API int wdb_mlp_pack_obs(void *stream, const float *obs, long long rows, int F,
+                             void *tiles) {
+  if (!obs || !tiles || rows <= 0 || F < 1 || F > 256) return (int)cudaErrorInvalidValue;
+  const int K1 = round_up(F, 16);
+  const long long n = ((rows + kTileM - 1) / kTileM) * kTileM * (K1 / 8);
+  const int T = 256;
+  pack_obs_kernel<<<(unsigned)((n + T - 1) / T), T, 0, as_stream(stream)>>>(
+      obs, rows, F, K1, reinterpret_cast<unsigned char *>(tiles));
+  return finish_launch();
+}
+
+WDB_API int wdb_mlp_policy_forward(void *stream, const void *blob, int F, int H, int A0, int A1,
+                                   const float *obs, long long rows, float *probs0,
+                                   float *probs1, float *values) {
+  return launch_forward<false>(stream, blob, F, H, A0, A1, obs, rows, probs0, probs1, values);
+}
+
+WDB_API int wdb_mlp_policy_forward_tiles(void *stream, const void *blob, int F, int H, int A0,
+                                         int A1, const void *obs_tiles, long long rows,
+                                         float *probs0, float *probs1, float *values) {
+  return launch_forward<true>(stream, blob, F, H, A0, A1, obs_tiles, rows, probs0, probs1,
+                              values);
 }

@@ -43,6 +43,8 @@
 //     NumPy semantics (tag_continuous.py:660-672).
 #include <math_constants.h>
 
+#include <cuda_bf16.h>
+
 #include "wdb_common.cuh"
 #include "wdb_sortnet.cuh"
 
@@ -108,6 +110,8 @@ struct FusedParams {
   int *actions_batch[kMaxPolicies];     // [E, Np, 2]
   float *rewards_batch[kMaxPolicies];   // [E, Np]
   float *obs_next[kMaxPolicies];        // [E, Np, F] : post-step (post-reset) observations
+  unsigned char *obs_tiles[kMaxPolicies];  // optional bf16 copy of obs_next in the A-operand tile
+                                           // layout of wdb_mlp_policy_forward_tiles
   int *done_batch;                      // [E]
   // episodic bookkeeping (optional)
   float *reward_running_sum[kMaxPolicies];   // [E, Np]
@@ -269,6 +273,28 @@ __device__ __forceinline__ int sample_row(float *row, const float *src, int A, f
     for (int i = 1; i < A; i++) { c = src[i] + c; row[i] = c; }
   }
   return search_index(row, 1, u, A - 1);
+}
+
+// 8 consecutive features of one observation row -> one 16-byte chunk of the bf16 A-operand
+// tiles read by wdb_mlp_policy_forward_tiles (canonical K-major layout of 128-row tiles:
+// element (r, k) at (r / 8) * K1 * 16 + (k / 8) * 128 + (r % 8) * 16 + (k % 8) * 2 bytes;
+// K padding = 0).  `grow` = row index inside the policy's [E * Np] rows.
+__device__ __forceinline__ void store_obs_chunk(unsigned char *tiles, long long grow, int c,
+                                                int K1, const float *src, int F) {
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) v[i] = (8 * c + i < F) ? src[8 * c + i] : 0.0f;
+  uint4 o;
+  {
+    const __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+    o.x = *reinterpret_cast<const uint32_t *>(&h0); o.y = *reinterpret_cast<const uint32_t *>(&h1);
+    o.z = *reinterpret_cast<const uint32_t *>(&h2); o.w = *reinterpret_cast<const uint32_t *>(&h3);
+  }
+  const long long t = grow >> 7;
+  const int r = (int)(grow & 127);
+  *reinterpret_cast<uint4 *>(tiles + t * (128ll * K1 * 2) + (r >> 3) * (K1 * 16) + c * 128 +
+                             (r & 7) * 16) = o;
 }
 
 // Squared distance with a FIXED operation order (dx * dx rounded, then fused dy * dy + .):
@@ -1085,6 +1111,31 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
     }
     WDB_MARK(19)  // TMA stores issued
   }
+  // bf16 copy of the tile in the layout the next policy forward feeds to the tensor cores
+  // (its fp32 obs path -- 4-byte loads of 284-byte rows, conversion, transposition -- is
+  // the largest cost of that kernel; here the tile is in shared memory anyway).  Consecutive
+  // threads take consecutive rows: conflict-free reads, 128-byte store segments.
+  if (FUSED && !P.use_full_obs && P.stage_obs) {
+    const int K1 = (F + 15) & ~15, nchunk = K1 / 8;
+#pragma unroll
+    for (int p = 0; p < kMaxPolicies; p++) {
+      if (p < Q.n_policies && Q.obs_tiles[p]) {
+        const int np = Q.policy_size[p], rows_p = envs_here * np;
+        const float *blk = s_tile + tile_base[p];
+        const long long grow0 = (long long)env0 * np;
+        // (chunks that are all K padding stay zero from the allocation: never written)
+        const int nreal = (F + 7) / 8;
+        int c = tid / rows_p, lr = tid - c * rows_p;
+        const int dc = blockDim.x / rows_p, dl = blockDim.x - dc * rows_p;
+        for (int it = tid; it < rows_p * nreal; it += blockDim.x) {
+          store_obs_chunk(Q.obs_tiles[p], grow0 + lr, c, K1, blk + lr * F, F);
+          c += dc; lr += dl;
+          if (lr >= rows_p) { lr -= rows_p; c++; }
+        }
+        (void)nchunk;
+      }
+    }
+  }
 
   WDB_MARK(20)  // bookkeeping loads requested
   // ------------------------------------------------------------------ rewards / tags
@@ -1253,6 +1304,16 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
               dst = Q.obs_next[p] + ((long long)renv * Q.policy_size[p] + Q.agent_slot[row]) * F;
           if (dst)
             for (int f = lane; f < F; f += kWarp) dst[f] = src[(long long)row * F + f];
+#pragma unroll
+          for (int p = 0; p < kMaxPolicies; p++) {
+            if (p == pol && Q.obs_tiles[p]) {
+              const int K1 = (F + 15) & ~15;
+              if (lane < K1 / 8)
+                store_obs_chunk(Q.obs_tiles[p],
+                                (long long)renv * Q.policy_size[p] + Q.agent_slot[row], lane, K1,
+                                src + (long long)row * F, F);
+            }
+          }
         }
       }
     }
@@ -1486,6 +1547,9 @@ WDB_API int wdb_tag_continuous_rollout_step(void *stream, const wdb_tc_env *env,
     Q.probs0[p] = io.probs0; Q.probs1[p] = io.probs1;
     Q.actions_batch[p] = io.actions_batch; Q.rewards_batch[p] = io.rewards_batch;
     Q.obs_next[p] = io.obs_next; Q.reward_running_sum[p] = io.reward_running_sum;
+    Q.obs_tiles[p] = reinterpret_cast<unsigned char *>(io.obs_next_tiles);
+    if (io.obs_next_tiles && ((uintptr_t)io.obs_next_tiles & 15))
+      return (int)cudaErrorMisalignedAddress;
     Q.episodic_reward_sum[p] = io.episodic_reward_sum;
     total += io.n_agents;
   }
@@ -1505,7 +1569,10 @@ WDB_API int wdb_tag_continuous_rollout_step(void *stream, const wdb_tc_env *env,
   if (!P.stage_obs && !P.use_full_obs) {
     // the per-policy observation push needs the shared-memory tile
     for (int p = 0; p < Q.n_policies; p++)
-      if (Q.obs_next[p]) return (int)cudaErrorInvalidValue;
+      if (Q.obs_next[p] || Q.obs_tiles[p]) return (int)cudaErrorInvalidValue;
   }
+  if (P.use_full_obs)
+    for (int p = 0; p < Q.n_policies; p++)
+      if (Q.obs_tiles[p]) return (int)cudaErrorInvalidValue;   // tiles come from the staged tile
   return launch<true>(P, Q, plan, as_stream(stream));
 }

@@ -53,7 +53,7 @@ class TcPolicyIO(ctypes.Structure):
     _fields_ = [
         ("n_agents", _i), ("probs0", _fp), ("probs1", _fp), ("actions_batch", _fp),
         ("rewards_batch", _fp), ("obs_next", _fp), ("reward_running_sum", _fp),
-        ("episodic_reward_sum", _fp),
+        ("episodic_reward_sum", _fp), ("obs_next_tiles", _fp),
     ]
 
 
@@ -103,6 +103,9 @@ _SIGNATURES = {
     "wdb_mlp_blob_bytes": (_ll, [_i, _i, _i, _i]),
     "wdb_mlp_pack_weights": (_i, [_vp] * 12 + [_i, _i, _i, _i]),
     "wdb_mlp_policy_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _ll, _vp, _vp, _vp]),
+    "wdb_mlp_obs_tiles_bytes": (_ll, [_i, _ll]),
+    "wdb_mlp_pack_obs": (_i, [_vp, _vp, _ll, _i, _vp]),
+    "wdb_mlp_policy_forward_tiles": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _ll, _vp, _vp, _vp]),
     "wdb_discounted_returns": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f]),
     "wdb_cartpole_step": (
         _i,

@@ -106,7 +106,7 @@ class FusedTagContinuousStep:
         self.ro.num_completed_episodes = _p(num_completed)
 
     def launch(self, probs, actions_batch=None, rewards_batch=None, obs_next=None,
-               done_batch=None, uniforms=None, reset_done_envs=True):
+               done_batch=None, uniforms=None, reset_done_envs=True, obs_next_tiles=None):
         """probs: {policy: [probs_head0 [E,Np,A0], probs_head1 [E,Np,A1]]}; the *_batch /
         obs_next dicts hold this timestep's slots (tensors) per policy, or None."""
         ro = self.ro
@@ -116,6 +116,7 @@ class FusedTagContinuousStep:
             io.actions_batch = _p(actions_batch[p]) if actions_batch else None
             io.rewards_batch = _p(rewards_batch[p]) if rewards_batch else None
             io.obs_next = _p(obs_next[p]) if obs_next else None
+            io.obs_next_tiles = _p(obs_next_tiles[p]) if obs_next_tiles else None
         ro.done_batch = _p(done_batch)
         ro.uniforms = _p(uniforms)
         ro.reset_done_envs = int(bool(reset_done_envs))

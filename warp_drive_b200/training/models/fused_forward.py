@@ -60,3 +60,22 @@ class FusedPolicyForward:
             _lib.stream_ptr(), _lib.ptr(self.blob), self.F, self.H, self.A0, self.A1,
             _lib.ptr(obs), rows, _lib.ptr(probs0), _lib.ptr(probs1), _lib.ptr(values)),
             "mlp_policy_forward")
+
+    # ---- bf16 A-operand tiles (the MMA-ready copy of the observations) ----------------
+    def tiles_bytes(self, rows):
+        return int(self.lib.wdb_mlp_obs_tiles_bytes(self.F, int(rows)))
+
+    def pack_obs(self, obs, tiles):
+        """fp32 obs [..., F] -> `tiles` (uint8 tensor of tiles_bytes(rows) bytes)."""
+        rows = obs.numel() // self.F
+        _lib.check(self.lib.wdb_mlp_pack_obs(_lib.stream_ptr(), _lib.ptr(obs), rows, self.F,
+                                             _lib.ptr(tiles)), "mlp_pack_obs")
+
+    def forward_tiles(self, tiles, rows, probs0, probs1, values=None, max_ctas=0):
+        """The forward fed from the bf16 tiles (written by pack_obs or by the fused env step)."""
+        _lib.check(self.lib.wdb_set_option(b"mlp_max_ctas", int(max_ctas)), "set_option")
+        _lib.check(self.lib.wdb_mlp_policy_forward_tiles(
+            _lib.stream_ptr(), _lib.ptr(self.blob), self.F, self.H, self.A0, self.A1,
+            _lib.ptr(tiles), int(rows), _lib.ptr(probs0), _lib.ptr(probs1), _lib.ptr(values)),
+            "mlp_policy_forward_tiles")
+

@@ -23,7 +23,7 @@ class RolloutEngine:
     def __init__(self, env_wrapper, models, policy_tag_to_agent_id_map, sampler,
                  batch_size_per_env, use_cuda_graph=True, forward_dtype=None,
                  use_fused_step=True, write_observations=True, stats=None,
-                 use_fused_forward=True):
+                 use_fused_forward=True, use_obs_tiles=False):
         self.env_wrapper = env_wrapper
         self.dm = env_wrapper.cuda_data_manager
         self.models = models
@@ -75,6 +75,7 @@ class RolloutEngine:
 
         # ---- tensor-core forward (tcgen05 MLP kernel) for the fused path
         self.fused_forward = {}
+        self.obs_tiles = {}
         if self.fused is not None and use_fused_forward and forward_dtype is None:
             from warp_drive_b200.training.models.fused_forward import FusedPolicyForward
 
@@ -82,6 +83,15 @@ class RolloutEngine:
                 self.fused_forward = {p: FusedPolicyForward(self.models[p]) for p in self.policies}
                 self._probs = {p: [torch.empty((self.E, len(self.policy_map[p]), h), device=dev)
                                    for h in self.heads] for p in self.policies}
+                # bf16 MMA-ready mirror of the observations the next forward reads: written by
+                # the fused env step itself (and by pack_obs whenever cur_obs changes outside it)
+                # (off by default: measured at config 2, the env step's extra pass costs what
+                #  the forward saves -- see DESIGN.md 3.2)
+                if use_obs_tiles and not getattr(env_wrapper.env, "use_full_observation", False):
+                    self.obs_tiles = {
+                        p: torch.zeros(self.fused_forward[p].tiles_bytes(
+                            self.E * len(self.policy_map[p])), dtype=torch.uint8, device=dev)
+                        for p in self.policies}
 
     def refresh_forward_weights(self):
         """Re-pack the policies' parameters for the tensor-core forward (after every
@@ -112,6 +122,12 @@ class RolloutEngine:
             obs = self._tensor(_OBSERVATIONS).view(self.E, self.N, -1)
             for p in self.policies:
                 self.cur_obs[p].copy_(obs.index_select(1, self.ids[p]))
+            self._repack_obs_tiles()
+
+    def _repack_obs_tiles(self):
+        if self.obs_tiles:
+            for p in self.policies:
+                self.fused_forward[p].pack_obs(self.cur_obs[p], self.obs_tiles[p])
 
     def materialize_observations(self):
         """Scatter the per-policy observation buffers back into the [E, N, F]
@@ -137,16 +153,29 @@ class RolloutEngine:
         Sequential launches would each pay the 195 KB weight load and leave most SMs idle
         during the small policy's single wave."""
         if len(self.policies) == 1:
-            p = self.policies[0]
-            self.fused_forward[p](obs_in[p], probs[p][0], probs[p][1])
+            self._one_forward(self.policies[0], obs_in, probs)
             return
         if not hasattr(self, "_fwd_plan"):
             n_sm = torch.cuda.get_device_properties(self.dm.device).multi_processor_count
             rows = {p: obs_in[p].numel() // obs_in[p].shape[-1] for p in self.policies}
             total = sum(rows.values())
             order = sorted(self.policies, key=lambda p: -rows[p])
-            share = {p: max(1, min(n_sm - 1, -(-n_sm * rows[p] // total))) for p in order[1:]}
-            share[order[0]] = max(1, n_sm - sum(share.values()))
+            if len(order) == 2:
+                # cost model in tile-times: ceil(tiles / SMs) + ~1.5 for the weight load;
+                # pick the split that minimises the slower of the two
+                tiles = {p: -(-rows[p] // 128) for p in order}
+                best = None
+                for k in range(1, n_sm // 2 + 1):
+                    # (measured: the small policy's tiles run ~1.3x slower -- fewer CTAs share
+                    #  its weights in L2 -- and a launch pays ~1.5 tile-times up front)
+                    cost = max(-(-tiles[order[0]] // (n_sm - k)),
+                               1.3 * -(-tiles[order[1]] // k)) + 1.5
+                    if best is None or cost < best[0]:
+                        best = (cost, k)
+                share = {order[1]: best[1], order[0]: n_sm - best[1]}
+            else:
+                share = {p: max(1, min(n_sm - 1, -(-n_sm * rows[p] // total))) for p in order[1:]}
+                share[order[0]] = max(1, n_sm - sum(share.values()))
             self._fwd_plan = (order, share)
             self._fwd_streams = [torch.cuda.Stream() for _ in order[1:]]
         order, share = self._fwd_plan
@@ -157,14 +186,22 @@ class RolloutEngine:
         for p, st in zip(order[1:], self._fwd_streams):
             st.wait_event(fork)
             with torch.cuda.stream(st):
-                self.fused_forward[p](obs_in[p], probs[p][0], probs[p][1], max_ctas=share[p])
+                self._one_forward(p, obs_in, probs, share[p])
                 ev = torch.cuda.Event()
                 ev.record(st)
             joins.append(ev)
         p = order[0]
-        self.fused_forward[p](obs_in[p], probs[p][0], probs[p][1], max_ctas=share[p])
+        self._one_forward(p, obs_in, probs, share[p])
         for ev in joins:
             cur.wait_event(ev)
+
+    def _one_forward(self, p, obs_in, probs, max_ctas=0):
+        if self.obs_tiles:
+            rows = obs_in[p].numel() // obs_in[p].shape[-1]
+            self.fused_forward[p].forward_tiles(self.obs_tiles[p], rows, probs[p][0], probs[p][1],
+                                                max_ctas=max_ctas)
+        else:
+            self.fused_forward[p](obs_in[p], probs[p][0], probs[p][1], max_ctas=max_ctas)
 
     def step_fused(self, t, uniforms=None):
         """One timestep = policy forwards + ONE libwdb200 launch."""
@@ -197,7 +234,8 @@ class RolloutEngine:
             else:
                 probs = {p: self._forward(self.models[p], obs_in[p]) for p in self.policies}
             self.fused.launch(probs, actions_batch=actions_batch, rewards_batch=rewards_batch,
-                              obs_next=obs_next, done_batch=done_batch, uniforms=uniforms)
+                              obs_next=obs_next, done_batch=done_batch, uniforms=uniforms,
+                              obs_next_tiles=self.obs_tiles or None)
             if t < 0:
                 for p in self.policies:
                     self.cur_obs[p].copy_(self._scratch_obs[p])
