@@ -42,7 +42,9 @@ long long wdb_launch_count(void);
 
 /* Tuning / A-B switches (results are identical either way).  "tc_history": use last step's
  * neighbour lists as a distance threshold in the tag_continuous k-nearest search (1, default)
- * or always run the full sorting network (0).  "tc_cta_threads": thread budget of one
+ * or always run the full sorting network (0).  "tc_force_exact": resolve every agent's
+ * neighbours with the reference's literal selection (1) instead of only the ambiguous ones
+ * (0, default).  "tc_cta_threads": thread budget of one
  * tag_continuous CTA (32..320, default 320); a CTA takes floor(budget / agents) envs.
  * "mlp_max_ctas": persistent CTAs (= SMs) the following wdb_mlp_policy_forward launches may
  * use (0 = all): two policies' forwards can then run concurrently on disjoint SMs. */

@@ -250,3 +250,47 @@ def test_engine_obs_tiles_matches_fp32_forward():
             assert torch.equal(ta, tb), name
     assert int(ea.num_completed_episodes) == int(eb.num_completed_episodes) > 0
 
+
+
+def test_config4_agent_count_through_wrapper_and_engine():
+    """BASELINE config 4 territory (1024 agents per env): EnvWrapper allocates the reference's
+    global neighbour scratch by itself, the env steps through the managers, and the
+    RolloutEngine falls back to the generic multi-launch timestep (the fused step's
+    observation tile does not fit shared memory at this size)."""
+    from warp_drive_b200.env_wrapper import EnvWrapper
+    from warp_drive_b200.envs.tag_continuous import TagContinuous
+    from warp_drive_b200.managers.function_manager import CUDASampler
+    from warp_drive_b200.training.models.fully_connected import FullyConnected
+    from warp_drive_b200.training.rollout import RolloutEngine
+    from warp_drive_b200.training.utils.data_loader import create_and_push_data_placeholders
+
+    kw = dict(ENV_KW, num_taggers=24, num_runners=1000, grid_length=64.0,
+              num_other_agents_observed=10, tagging_distance=0.3)
+    env = TagContinuous(**kw)
+    E, T = 2, 4
+    w = EnvWrapper(env, num_envs=E, env_backend="b200")
+    w.reset_all_envs()
+    assert env.allocate_reference_scratch          # decided when the data is registered
+    pm = {"runner": sorted(env.runners), "tagger": sorted(env.taggers)}
+    s = CUDASampler(w.cuda_function_manager)
+    create_and_push_data_placeholders(env_wrapper=w, action_sampler=s,
+                                      policy_tag_to_agent_id_map=pm,
+                                      training_batch_size_per_env=T)
+    s.init_random(3)
+    torch.manual_seed(0)
+    cfg = {"type": "fully_connected", "fc_dims": [32, 32], "model_ckpt_filepath": ""}
+    models = {p: FullyConnected(w, cfg, p, pm).cuda().eval() for p in pm}
+    eng = RolloutEngine(w, models, pm, s, T, use_cuda_graph=False)
+    assert eng.fused is None
+    for _ in range(3):
+        eng.rollout()
+    torch.cuda.synchronize()
+    dm = w.cuda_data_manager
+    x, y = dm.pull_data_from_device("loc_x"), dm.pull_data_from_device("loc_y")
+    assert ((x >= 0) & (x <= 64.0) & (y >= 0) & (y <= 64.0)).all()
+    assert (dm.pull_data_from_device("_timestep_") == 12).all()
+    nn = dm.pull_data_from_device("nearest_neighbor_ids")
+    alive = dm.pull_data_from_device("still_in_the_game")
+    assert nn.min() >= 0 and nn.max() < 1024
+    obs = dm.pull_data_from_device("observations")
+    assert np.isfinite(obs).all() and (obs[alive == 0] == 0).all()

@@ -73,6 +73,7 @@ struct TcParams {
   int n_envs, N, epb, K, episode_length;
   int use_full_obs, runner_exits, stage_obs, scratch_in_smem, id_bits;
   int use_history, scr_warp_bytes;   // per-warp scratch: history candidate list / exact path
+  int force_exact;                   // A/B switch: every agent takes the exact (reference-literal) path
   float *loc_x, *loc_y, *speed, *direction, *acceleration;
   const int *agent_types;
   float *edge_pen;
@@ -947,6 +948,7 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
       }
     }
     WDB_MARK(9)   // verified
+    if (P.force_exact && active && alive) suspect = true;
     // exact path: the warp resolves its suspect agents one at a time, cooperatively
     unsigned todo = __ballot_sync(0xffffffffu, suspect);
     while (todo) {
@@ -1323,6 +1325,7 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
 
 int g_tc_history = 1;   // wdb_set_option("tc_history", 0/1)
 int g_tc_threads = 320; // wdb_set_option("tc_cta_threads", n): thread budget of one CTA (<= 320)
+int g_tc_force_exact = 0;  // wdb_set_option("tc_force_exact", 0/1)
 
 struct LaunchPlan {
   int epb, block, grid;
@@ -1340,6 +1343,7 @@ int plan_launch(TcParams &P, const FusedParams *Q, bool have_gscratch, LaunchPla
   const size_t base = tc_small_bytes(epb, N);
   // per-warp scratch: exact-path lists (8 B per agent) and/or the history byte list
   P.use_history = (g_tc_history && !P.use_full_obs && N <= 128 && K + 2 <= kListLen) ? 1 : 0;
+  P.force_exact = g_tc_force_exact;
   size_t warp_bytes = 8ull * N;
   const size_t hist_bytes = (size_t)(kHistCap + 1) * kWarp;
   if (P.use_history && hist_bytes > warp_bytes) warp_bytes = hist_bytes;
@@ -1461,6 +1465,7 @@ WDB_API int wdb_set_option(const char *name, int value) {
     return !want[i] && !name[i];
   };
   if (is("tc_history")) { g_tc_history = value ? 1 : 0; return 0; }
+  if (is("tc_force_exact")) { g_tc_force_exact = value ? 1 : 0; return 0; }
   if (is("mlp_max_ctas")) {
     if (value < 0) return (int)cudaErrorInvalidValue;
     g_mlp_max_ctas = value;

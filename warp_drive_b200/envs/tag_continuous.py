@@ -136,6 +136,11 @@ class TagContinuous(CUDAEnvironmentContext):
         self.env_backend = env_backend
         # the reference env allocates 2 x [E, N, N-1] global scratch for its kNN sort;
         # the B200 kernel keeps the sweep on chip, so by default they are 1-element stubs
+        # The reference always allocates two [E, N, N-1] scratch arrays for the neighbour
+        # search; here they are only needed when the exact-tie path's per-warp lists
+        # (8 N bytes per warp) do not fit next to the staged state in shared memory (>~400
+        # agents), or when the observation dimension K + 2 exceeds the sorting network
+        self._scratch_requested = allocate_reference_scratch
         self.allocate_reference_scratch = allocate_reference_scratch
         self.runners_at_reset = dict(self.runners)
 
@@ -312,6 +317,9 @@ class TagContinuous(CUDAEnvironmentContext):
         d.add_data(name="tag_penalty_for_runner", data=self.tag_penalty_for_runner)
         d.add_data(name="end_of_game_reward_for_runner",
                    data=self.end_of_game_reward_for_runner)
+        n_warps = (N + 31) // 32
+        if 36 * N + 8 * N * n_warps > 60000 or K + 2 > 16:
+            self.allocate_reference_scratch = True
         if self.allocate_reference_scratch:
             d.add_data(name="neighbor_distances",
                        data=np.zeros((N, N - 1), dtype=np.float32),

@@ -113,6 +113,16 @@ class RolloutEngine:
             return False
         if self.T < 1 or self.dm.reset_target_to_pool:
             return False
+        if not getattr(env, "use_full_observation", False):
+            # the fused step pushes the per-policy observations from its shared-memory tile
+            # (same sizing rule as plan_launch in wdb_tag_continuous.cu); envs too large for
+            # that (e.g. 1024 agents) take the generic multi-launch path
+            n, f = self.N, 7 * int(env.num_other_agents_observed) + 1
+            epb = max(1, 320 // n)
+            n_warps = (epb * n + 31) // 32
+            small = 36 * epb * n + 16 * n + max(8 * n, 1056) * n_warps
+            if small + 4 * epb * n * f > 113 * 1024:
+                return False
         return all(getattr(m, "action_mask", None) is None for m in self.models.values())
 
     def resync_observations(self):
