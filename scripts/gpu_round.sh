@@ -22,7 +22,7 @@ import json; d=json.loads(open('gpurun_out/bench_${TAG}_ct$CT.json').read().stri
 done
 timeout 300 ncu --set full --import-source on --clock-control none -k regex:tag_continuous_kernel -s 30 -c 1 \
   -o gpurun_out/prof_fused_$TAG -f python bench.py --steps 3 --warmup 3 --skip-cpu-baseline > gpurun_out/ncu_fused_$TAG.log 2>&1
-timeout 300 ncu --set full --import-source on --clock-control none -k regex:mlp_forward_kernel -s 4 -c 1 \
+timeout 300 ncu --set full --import-source on --clock-control none -k regex:mlp_forward_kernel -s 4 -c 2 \
   -o gpurun_out/prof_mlp_$TAG -f python bench.py --steps 3 --warmup 3 --skip-cpu-baseline > gpurun_out/ncu_mlp_$TAG.log 2>&1
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv \
   --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 3 --warmup 3 --skip-cpu-baseline --no-graph > gpurun_out/ncu_list_$TAG.log 2>&1
