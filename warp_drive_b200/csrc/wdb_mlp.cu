@@ -14,9 +14,17 @@
 //     take their A operand straight from TMEM (tcgen05.mma .ts form) -- hidden activations
 //     never touch shared or global memory; final epilogue = bias + two softmaxes + value,
 //     staged in shared memory and written with TMA bulk stores.
-//   * one elected thread issues the MMAs; completion is signalled through an mbarrier
-//     (tcgen05.commit); 16 warps run the epilogues (4 lane quadrants x 4 column parts);
-//   * the next tile's obs are prefetched into registers while the current tile computes.
+//   * warp-specialised: lane 0 of a dedicated warp issues every tcgen05.mma (issue is
+//     back-pressured by the tensor core, ~100 cycles per instruction); 12 worker warps
+//     (4 TMEM lane quadrants x 3 column parts) run the obs path and the epilogues.
+//     Workers -> issuer: named barriers (bar.arrive / bar.sync); issuer -> workers:
+//     tcgen05.commit onto one mbarrier per layer;
+//   * software pipeline: layer 1 of tile t+1 is issued right behind layer 3 of tile t; the
+//     next tile's A operand is built, and the PREVIOUS tile's softmax epilogue runs, while
+//     the tensor core executes layer 2; the obs of tile t+2 are prefetched into registers
+//     while it executes layer 3;
+//   * optional TILES mode: the A operand arrives as ready-made bf16 tiles (one TMA bulk
+//     copy per tile) instead of fp32 obs rows.
 //
 // Numerics: bf16 operands, fp32 accumulation (the reference is fp32; SURVEY.md section 8
 // row a3 allows TF32/BF16 for the forward that feeds the sampler).  Tested against a
