@@ -16,19 +16,24 @@
 //     updated in registers, written back once, and staged in shared memory; the O(N^2)
 //     neighbour sweep and the tagger scan read only shared memory.  The reference re-reads
 //     global memory per pair and keeps N*(N-1) distances and ids per env in global scratch.
-//   * action probabilities are staged through shared memory with unit-stride loads (the
-//     reference reads rows with an A*4-byte stride per thread and round-trips the CDF
-//     through global memory); observations are assembled in a shared-memory tile and
-//     written out with unit-stride stores.
+//   * action probabilities arrive in shared memory by TMA bulk copies (cp.async.bulk +
+//     mbarrier) issued first thing (the reference reads rows with an A*4-byte stride per
+//     thread and round-trips the CDF through global memory); observations are assembled in
+//     a shared-memory tile laid out like their destination and leave by TMA bulk stores
+//     that overlap the reward phase.
+//   * every global read of the prologue is issued back to back before the first global
+//     store (one memory round trip); see DESIGN.md 3.1 for the phase timeline.
 //
 // Exactness (what "parity" means here; tests/test_gpu_envs.py compares against the
 // reference kernels compiled from the reference sources, bit for bit)
 //   * kinematics use the same float32 expressions as the reference.
 //   * k-nearest selection: the reference orders neighbours by
 //     d = (float)sqrt(pow((double)dx,2)+pow((double)dy,2)) through a swap-based partial
-//     selection sort whose tie order is NOT id order (:179-199).  The fast path ranks all
-//     candidates with a branch-free sorting network on packed (float32 squared distance |
-//     id) keys and accepts the result only when the exact float32 squared distances of the
+//     selection sort whose tie order is NOT id order (:179-199).  The fast paths -- a
+//     temporal-coherence threshold scan on packed float32x2 arithmetic that keeps a bit
+//     mask of the ~K+2 candidates inside last step's neighbour radius, or a branch-free
+//     sorting network over all candidates -- rank packed (float32 squared distance | id)
+//     keys and accept the result only when the exact float32 squared distances of the
 //     K+1 nearest are strictly increasing with relative gaps > 2^-19 (2^-15 for the last
 //     pair, which also covers the key truncation) -- then the ranking provably equals the
 //     ranking by d and no tie exists.  Otherwise the agent takes the exact path: the
