@@ -495,60 +495,60 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
 
   // ---- categorical sampling of both action heads (core/random.cu:51-85): the probability
   // blocks are requested first thing (TMA), they land while the state loads fly ----
-  int p_off0[kMaxPolicies], p_off1[kMaxPolicies];
+  // Block (p, head) = the [envs_here, Np, A] probabilities of this CTA's envs, contiguous in
+  // global memory but in general NOT 16-byte aligned (taggers: 1260 bytes at a 1260 c byte
+  // offset).  The TMA therefore fetches the 16-byte-aligned SUPERSET of each block (up to 15
+  // bytes of neighbouring rows of the same tensor on either side) into a 16-byte-aligned
+  // slot, and the rows are addressed `lead` bytes into the slot.  Slots are padded so that
+  // supersets never overlap.  A block falls back to per-thread global reads only when the
+  // superset would leave the tensor (unaligned tensor base / end).
+  int p_off0[kMaxPolicies], p_off1[kMaxPolicies];   // float offset of the block's first row
   uint32_t tma_mask = 0;   // bit 2p / 2p+1: block (p, head) travels by TMA
   const uint32_t mbar = smem_u32(s_mbar);
   if (FUSED) {
-    // ---- categorical sampling of both action heads (core/random.cu:51-85) ----
-    // stage every policy's [envs_here, Np, A] block (contiguous in global memory) with
-    // unit-stride loads; rows keep their global layout (stride A is odd for A = 21, so a
-    // thread walking its own row is bank-conflict free)
-    // block offsets inside the tile (floats): [p0 head0][p0 head1][p1 head0]...
-    {
-      int off = 0;
-#pragma unroll
-      for (int p = 0; p < kMaxPolicies; p++) {
-        const int np = (p < Q.n_policies) ? Q.policy_size[p] : 0;
-        p_off0[p] = off; off += epb * np * Q.A0;
-        p_off1[p] = off; off += epb * np * Q.A1;
-      }
-    }
-    // contiguous blocks whose global address, shared address and size are 16-byte aligned
-    // go through the TMA (one elected thread issues cp.async.bulk, the bytes land while
-    // every thread draws its random numbers and loads its state); rows of the other blocks
-    // are read from global memory by their own thread
+    uint32_t slot = 0;                                // byte offset of the next slot in s_tile
+    uint32_t t_src_lead[2 * kMaxPolicies], t_dst[2 * kMaxPolicies], t_span[2 * kMaxPolicies];
 #pragma unroll
     for (int p = 0; p < kMaxPolicies; p++) {
-      if (p < Q.n_policies) {
-        const int np = Q.policy_size[p];
-        const float *g0 = Q.probs0[p] + (long long)env0 * np * Q.A0;
-        const float *g1 = Q.probs1[p] + (long long)env0 * np * Q.A1;
-        if (tma_ok(g0, smem_u32(s_tile + p_off0[p]), 4ull * envs_here * np * Q.A0)) tma_mask |= 1u << (2 * p);
-        if (tma_ok(g1, smem_u32(s_tile + p_off1[p]), 4ull * envs_here * np * Q.A1)) tma_mask |= 2u << (2 * p);
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int np = (p < Q.n_policies) ? Q.policy_size[p] : 0;
+        const int A = h ? Q.A1 : Q.A0;
+        const float *base = (p < Q.n_policies) ? (h ? Q.probs1[p] : Q.probs0[p]) : nullptr;
+        const uint32_t bytes = 4u * envs_here * np * A;
+        const unsigned long long tensor_bytes = 4ull * P.n_envs * np * A;
+        const uintptr_t ga = reinterpret_cast<uintptr_t>(base) + 4ull * env0 * np * A;
+        const uint32_t lead = (uint32_t)(ga & 15);
+        const uint32_t span = (lead + bytes + 15u) & ~15u;
+        // with a 16-byte-aligned tensor base the superset starts inside the tensor; it must
+        // also end inside it
+        const bool inside = ((reinterpret_cast<uintptr_t>(base) & 15) == 0) &&
+                            (4ull * env0 * np * A - lead + span <= tensor_bytes);
+        if (np > 0 && bytes > 0 && inside) tma_mask |= 1u << (2 * p + h);
+        (h ? p_off1[p] : p_off0[p]) = (int)((slot + lead) >> 2);
+        t_src_lead[2 * p + h] = lead; t_dst[2 * p + h] = slot; t_span[2 * p + h] = span;
+        slot += ((4u * epb * np * A + 15u) & ~15u) + 32u;   // room for lead + tail padding
       }
     }
     if (tid == 0) mbar_init(mbar, 1);      // (includes the init fence; waiters sync below)
     if (tid == 0 && tma_mask) {
       uint32_t total = 0;
 #pragma unroll
-      for (int p = 0; p < kMaxPolicies; p++) {
-        if (p < Q.n_policies) {
-          const int np = Q.policy_size[p];
-          if (tma_mask & (1u << (2 * p))) total += 4u * envs_here * np * Q.A0;
-          if (tma_mask & (2u << (2 * p))) total += 4u * envs_here * np * Q.A1;
-        }
-      }
+      for (int q = 0; q < 2 * kMaxPolicies; q++)
+        if (tma_mask & (1u << q)) total += t_span[q];
       mbar_expect_tx(mbar, total);
 #pragma unroll
       for (int p = 0; p < kMaxPolicies; p++) {
-        if (p < Q.n_policies) {
-          const int np = Q.policy_size[p];
-          if (tma_mask & (1u << (2 * p)))
-            tma_load_1d(smem_u32(s_tile + p_off0[p]), Q.probs0[p] + (long long)env0 * np * Q.A0,
-                        4u * envs_here * np * Q.A0, mbar);
-          if (tma_mask & (2u << (2 * p)))
-            tma_load_1d(smem_u32(s_tile + p_off1[p]), Q.probs1[p] + (long long)env0 * np * Q.A1,
-                        4u * envs_here * np * Q.A1, mbar);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int q = 2 * p + h;
+          if (tma_mask & (1u << q)) {
+            const int np = Q.policy_size[p];
+            const int A = h ? Q.A1 : Q.A0;
+            const char *g = reinterpret_cast<const char *>(h ? Q.probs1[p] : Q.probs0[p]) +
+                            4ll * env0 * np * A - t_src_lead[q];
+            tma_load_1d(smem_u32(s_tile) + t_dst[q], g, t_span[q], mbar);
+          }
         }
       }
     }
@@ -1361,7 +1361,8 @@ int plan_launch(TcParams &P, const FusedParams *Q, bool have_gscratch, LaunchPla
   size_t tile_probs = 0;
   if (Q) {
     for (int p = 0; p < Q->n_policies; p++)
-      tile_probs += sizeof(float) * (size_t)epb * Q->policy_size[p] * (Q->A0 + Q->A1);
+      tile_probs += ((sizeof(float) * (size_t)epb * Q->policy_size[p] * Q->A0 + 15) & ~(size_t)15) +
+                    ((sizeof(float) * (size_t)epb * Q->policy_size[p] * Q->A1 + 15) & ~(size_t)15) + 64;
   }
   const size_t kMaxSmem = 200 * 1024;
   P.scratch_in_smem = (base + scr <= 64 * 1024) || !have_gscratch;
