@@ -250,10 +250,13 @@ __device__ __noinline__ int exact_select_warp(const float2 *pos, const int *sali
 // differ from the float64 quotient by a few ulp(53), which changes the float32 rounding
 // only if the product sits within those few ulp of a float32 rounding boundary (the 29
 // discarded mantissa bits ~ 0x10000000).  Those (probability ~2^-26) take the real divide.
+// (rare paths are kept out of line: the kernel is larger than the instruction cache, every
+//  inlined copy of a ~90-instruction float64 division costs the hot path fetch stalls)
+__device__ __noinline__ float true_div_f64(float d, double c) { return (float)((double)d / c); }
 __device__ __forceinline__ float div_by_const_f64(float d, double c, double inv_c) {
   const double prod = (double)d * inv_c;
   const uint32_t lo = (uint32_t)__double2loint(prod) & 0x1FFFFFFFu;
-  if (__builtin_expect(lo - 0x0FFFFFF8u <= 0x10u, 0)) return (float)((double)d / c);
+  if (__builtin_expect(lo - 0x0FFFFFF8u <= 0x10u, 0)) return true_div_f64(d, c);
   return (float)prod;
 }
 
@@ -261,6 +264,11 @@ __device__ __forceinline__ float div_by_const_f64(float d, double c, double inv_
 // core/random.cu:62-72) followed by the reference's binary search.  Rows of <= 32 actions
 // are summed in registers (independent loads, one dependent FADD chain) instead of a
 // load-add-store chain through shared memory.
+__device__ __noinline__ void cdf_long_row(float *row, const float *src, int A) {
+  float c = src[0];
+  row[0] = c;
+  for (int i = 1; i < A; i++) { c = src[i] + c; row[i] = c; }
+}
 __device__ __forceinline__ int sample_row(float *row, const float *src, int A, float u) {
   // src: where the probabilities are (the staged shared-memory row itself, or the global row
   // of a block that could not travel by TMA); row: shared-memory row that receives the CDF
@@ -274,9 +282,7 @@ __device__ __forceinline__ int sample_row(float *row, const float *src, int A, f
     for (int i = 0; i < 32; i++)
       if (i < A) row[i] = v[i];
   } else {
-    float c = src[0];
-    row[0] = c;
-    for (int i = 1; i < A; i++) { c = src[i] + c; row[i] = c; }
+    cdf_long_row(row, src, A);
   }
   return search_index(row, 1, u, A - 1);
 }
@@ -285,7 +291,7 @@ __device__ __forceinline__ int sample_row(float *row, const float *src, int A, f
 // tiles read by wdb_mlp_policy_forward_tiles (canonical K-major layout of 128-row tiles:
 // element (r, k) at (r / 8) * K1 * 16 + (k / 8) * 128 + (r % 8) * 16 + (k % 8) * 2 bytes;
 // K padding = 0).  `grow` = row index inside the policy's [E * Np] rows.
-__device__ __forceinline__ void store_obs_chunk(unsigned char *tiles, long long grow, int c,
+__device__ __noinline__ void store_obs_chunk(unsigned char *tiles, long long grow, int c,
                                                 int K1, const float *src, int F) {
   float v[8];
 #pragma unroll
@@ -914,7 +920,9 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
         for (int i = 1; i < kListLen; i++) last_key = (i == K + 1) ? R[i] : last_key;
         const float floor_out = __uint_as_float(last_key & ~idmask);
         if (misordered) {
-          // rare: exact odd-even transposition sort of the (<= 15) winners
+          // rare: exact odd-even transposition sort of the (<= 15) winners (not unrolled over
+          // the passes: code size)
+#pragma unroll 1
           for (int pass = 0; pass < kListLen - 1; pass++) {
 #pragma unroll
             for (int i = 1; i + 1 < kListLen; i++) {
@@ -1019,8 +1027,8 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
                               ? P.g_nid + (long long)gi * (N - 1) : nullptr;
         // (x / vnorm with vnorm == 1.0f -- max_speed 1 -- is the identity: skipping the
         //  IEEE division also avoids its slow path, which a zero numerator always takes)
-#define WDB_FEATURES(UNIT)                                                          \
-        _Pragma("unroll 2")                                                         \
+#define WDB_FEATURES(UNIT, UNROLL)                                                  \
+        _Pragma(UNROLL)                                                             \
         for (int p = 0; p < kk; p++) {                                              \
           const int b = net_ok ? (int)idcol[p * kWarp] : gids[p];                   \
           nn[p] = b;                                            /* :202-211 */      \
@@ -1035,7 +1043,7 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
           orow[5 * K + p] = stype[b];                                               \
           orow[6 * K + p] = ealive[b];                                              \
         }
-        if (unit_v) { WDB_FEATURES(true) } else { WDB_FEATURES(false) }
+        if (unit_v) { WDB_FEATURES(true, "unroll 2") } else { WDB_FEATURES(false, "unroll 1") }
 #undef WDB_FEATURES
         orow[7 * K] = static_cast<float>(t_env) / P.episode_length;   // :251-253
       }
