@@ -459,9 +459,11 @@ def main():
     peaks, peak_src = measured_peaks()
     dk = time_dominant_kernel(wrapper, engine)
     in_loop = time_dominant_kernel_in_rollout(engine) if engine.fused is not None else None
-    # the roofline uses the launch duration inside the rollout loop (median over 60 launches);
-    # the L2-flushed stand-alone timing is reported next to it
-    kernel_ms = in_loop["ms_median"] if in_loop else dk["ms_median"]
+    # The roofline uses the stand-alone timing (L2 flushed, the launch is enqueued while the
+    # flush kernel still runs, so no host launch latency can leak into the interval).  The
+    # in-rollout timing is reported next to it: in eager mode the host sometimes falls behind
+    # the GPU and the interval then includes the launch latency (median 90-107 us, min 82 us).
+    kernel_ms = dk["ms_median"]
     achieved = dk["bytes_per_agent_step"] * E * N / (kernel_ms * 1e-3) / 1e9
     traffic = None      # DRAM bytes per launch from the committed ncu capture (same config only)
     try:
@@ -482,9 +484,10 @@ def main():
                 "kernel_ms_in_rollout": in_loop,
                 "algorithmic_bytes_per_agent_step": dk["bytes_per_agent_step"],
                 "peak_source": peak_src,
-                "l2": "kernel_ms: CUDA events around the launch inside eager rollout steps "
-                      "(working set > L2); kernel_ms_l2_flushed_standalone: L2 flushed before "
-                      "every launch"}
+                "l2": "kernel_ms = kernel_ms_l2_flushed_standalone: CUDA events around the "
+                      "launch, L2 flushed before every launch; kernel_ms_in_rollout: events "
+                      "around the launch inside eager rollout steps (may include host launch "
+                      "latency)"}
 
     line = {
         "metric": "agent_steps_per_sec", "value": value, "unit": "agent-steps/s",
