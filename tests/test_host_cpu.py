@@ -306,3 +306,24 @@ def test_param_scheduler_and_config_merge():
     assert merged["num_envs"] == 7 and merged["train_batch_size"] == 10000
     for name in ("tag_gridworld", "single_cartpole"):
         assert load_run_config(name)["name"] == name
+
+
+def test_forward_sm_split_cost_model():
+    """RolloutEngine._forward_side_by_side splits the SMs between two policies so that the
+    slower launch is as short as possible (cost in tile-times: tiles per CTA, 1.3x for the
+    small policy, +1.5 for the weight load).  Config 2: 1563 runner tiles vs 79 tagger tiles
+    on 148 SMs -> the taggers get 9 SMs."""
+    n_sm, tiles = 148, {"runner": 1563, "tagger": 79}
+    best = None
+    for k in range(1, n_sm // 2 + 1):
+        cost = max(-(-tiles["runner"] // (n_sm - k)), 1.3 * -(-tiles["tagger"] // k)) + 1.5
+        if best is None or cost < best[0]:
+            best = (cost, k)
+    assert best[1] == 9
+    # and the engine source uses exactly this rule
+    import inspect
+
+    from warp_drive_b200.training import rollout
+
+    src = inspect.getsource(rollout.RolloutEngine._forward_side_by_side)
+    assert "1.3 * -(-tiles[order[1]] // k)" in src and "+ 1.5" in src
