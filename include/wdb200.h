@@ -228,6 +228,41 @@ int wdb_cartpole_step(void *stream, int n_envs, float *state, const int *action,
                       float theta_threshold_radians, float x_threshold,
                       int *env_timestep, int episode_length);
 
+/* ------------------------------------------------- classic control ---- */
+/* The four remaining single-agent envs of example_envs/single_agent/classic_control/.
+ * The reference has them only as numba kernels launched as one 1-thread block per env;
+ * argument order below = the kernel signatures (and the `args` lists of the env classes'
+ * step()), with n_envs made explicit.  state/obs rows are [n_envs, 1, k] float32. */
+
+/* Replaces NumbaClassicControlMountainCarEnvStep (mountain_car/mountain_car_step_numba.py:
+ * 14-70; args of mountain_car.py:104-119).  state/obs k = 2, action int32 [E,1,1].
+ * done = 1 at the episode end, 2 when the goal is reached (as the reference). */
+int wdb_mountain_car_step(void *stream, int n_envs, float *state, const int *action,
+                          int *done, float *reward, float *obs, float min_position,
+                          float max_position, float max_speed, float goal_position,
+                          float goal_velocity, float force, float gravity,
+                          int *env_timestep, int episode_length);
+
+/* Replaces NumbaClassicControlContinuousMountainCarEnvStep (continuous_mountain_car/
+ * continuous_mountain_car_step_numba.py:14-71; args of continuous_mountain_car.py:105-121).
+ * action float32 [E,1,1]. */
+int wdb_continuous_mountain_car_step(void *stream, int n_envs, float *state,
+                                     const float *action, int *done, float *reward,
+                                     float *obs, float min_action, float max_action,
+                                     float min_position, float max_position, float max_speed,
+                                     float goal_position, float goal_velocity, float power,
+                                     int *env_timestep, int episode_length);
+
+/* Replaces NumbaClassicControlPendulumEnvStep (pendulum/pendulum_step_numba.py:30-72; args
+ * of pendulum.py:92-100).  state k = 2 (theta, theta_dot), obs k = 3, action float32. */
+int wdb_pendulum_step(void *stream, int n_envs, float *state, const float *action, int *done,
+                      float *reward, float *obs, int *env_timestep, int episode_length);
+
+/* Replaces NumbaClassicControlAcrobotEnvStep (acrobot/acrobot_step_numba.py:24-168; args of
+ * acrobot.py:91-99).  state k = 4 (16-byte aligned), obs k = 6, action int32 in {0,1,2}. */
+int wdb_acrobot_step(void *stream, int n_envs, float *state, const int *action, int *done,
+                     float *reward, float *obs, int *env_timestep, int episode_length);
+
 /* ------------------------------------------------------------- policy forward ---- */
 /* Fused policy/value MLP forward on the tensor cores (tcgen05 + TMEM), replacing the
  * rollout-time FullyConnected.forward (warp_drive/training/models/fully_connected.py:51-89):

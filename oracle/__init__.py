@@ -82,6 +82,18 @@ def lib():
         _c_int, _c_int, _i32p, _i32p, _i32p, _i32p, _f32p, _f32p, _c_float, _c_float,
         _c_float, _c_float, _c_int, _c_int, _i32p, _c_int, _i32p,
     ]
+    L.wd_oracle_mountain_car_step.restype = None
+    L.wd_oracle_mountain_car_step.argtypes = (
+        [_c_int, _f32p, _i32p, _i32p, _f32p, _f32p] + [_c_float] * 7 + [_i32p, _c_int])
+    L.wd_oracle_continuous_mountain_car_step.restype = None
+    L.wd_oracle_continuous_mountain_car_step.argtypes = (
+        [_c_int, _f32p, _f32p, _i32p, _f32p, _f32p] + [_c_float] * 8 + [_i32p, _c_int])
+    L.wd_oracle_pendulum_step.restype = None
+    L.wd_oracle_pendulum_step.argtypes = [
+        _c_int, _f32p, _f32p, _i32p, _f32p, _f32p, _i32p, _c_int]
+    L.wd_oracle_acrobot_step.restype = None
+    L.wd_oracle_acrobot_step.argtypes = [
+        _c_int, _f32p, _i32p, _i32p, _f32p, _f32p, _i32p, _c_int]
     L.wd_oracle_cartpole_step.restype = None
     L.wd_oracle_cartpole_step.argtypes = [
         _c_int, _f32p, _i32p, _i32p, _f32p, _f32p, _c_float, _c_float, _c_float,

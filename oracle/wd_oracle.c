@@ -376,14 +376,16 @@ WD_EXPORT void wd_oracle_cartpole_step(
     float x = s[0], x_dot = s[1], theta = s[2], theta_dot = s[3];
     float force = (action[env] > 0.5) ? force_mag : -force_mag;
     float costheta = cosf(theta), sintheta = sinf(theta);
-    float temp = (force + polemass_length * (theta_dot * theta_dot) * sintheta) / total_mass;
-    double thetaacc = (double)(gravity * sintheta - costheta * temp) /
-                      ((double)length * (4.0 / 3.0 - (double)(masspole * (costheta * costheta) / total_mass)));
+    /* fmaf()/fma() where the reference binary (ptxas on numba's PTX) fuses */
+    float temp = fmaf(polemass_length * (theta_dot * theta_dot), sintheta, force) / total_mass;
+    float c2m = masspole * (costheta * costheta) / total_mass;
+    float torque = fmaf(gravity, sintheta, -(costheta * temp));
+    double thetaacc = (double)torque / ((double)length * (4.0 / 3.0 - (double)c2m));
     double xacc = (double)temp - (double)polemass_length * thetaacc * (double)costheta / (double)total_mass;
-    float nx = x + tau * x_dot;
-    float nx_dot = (float)((double)x_dot + (double)tau * xacc);
-    float ntheta = theta + tau * theta_dot;
-    float ntheta_dot = (float)((double)theta_dot + (double)tau * thetaacc);
+    float nx = fmaf(tau, x_dot, x);
+    float nx_dot = (float)fma((double)tau, xacc, (double)x_dot);
+    float ntheta = fmaf(tau, theta_dot, theta);
+    float ntheta_dot = (float)fma((double)tau, thetaacc, (double)theta_dot);
     s[0] = nx; s[1] = nx_dot; s[2] = ntheta; s[3] = ntheta_dot;
     float *o = obs + (size_t)env * 4;
     o[0] = s[0]; o[1] = s[1]; o[2] = s[2]; o[3] = s[3];
@@ -496,4 +498,185 @@ WD_EXPORT void wd_oracle_philox4x32_10(const uint32_t ctr[4],
     k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
   }
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+/* ------------------------------------------------------------------------ */
+/* Classic control: the reference has these only    */
+/* as numba kernels under example_envs/single_agent/classic_control/.        */
+/* Arithmetic types follow numba's type inference of that Python source      */
+/* (float32 arrays and np.float32 scalar arguments; int * float32 and every  */
+/* expression with a Python float literal are float64; math.sin/cos pick the */
+/* float32 routine for float32 arguments), read off numba's own type         */
+/* annotations; fma() is written where the reference binary (ptxas on        */
+/* numba's PTX, oracle/build_ref_numba.py) fuses.  Pinning: on the GPU box    */
+/* against those reference binaries (tests/test_gpu_classic_control.py) and  */
+/* through the fixtures they produced there (tests/golden/                   */
+/* classic_control_numba_golden.npz); on CPU against float64 restatements of */
+/* the gym physics the reference's CPU envs delegate to.                     */
+/* ------------------------------------------------------------------------ */
+static double wd_clip(double v, double lo, double hi) {
+  if (v < lo) return lo;                 /* mountain_car_step_numba.py:5-11 */
+  if (v > hi) return hi;
+  return v;
+}
+
+/* NumbaClassicControlMountainCarEnvStep, mountain_car/mountain_car_step_numba.py:14-70 */
+WD_EXPORT void wd_oracle_mountain_car_step(
+    int n_envs, float *state /*[E,1,2]*/, const int *action /*[E,1,1]*/, int *done,
+    float *reward /*[E,1]*/, float *obs /*[E,1,2]*/, float min_position,
+    float max_position, float max_speed, float goal_position, float goal_velocity,
+    float force, float gravity, int *env_timestep, int episode_length) {
+  for (int env = 0; env < n_envs; env++) {
+    env_timestep[env] += 1;                                          /* :35 */
+    float *s = state + (size_t)env * 2;
+    double position = (double)s[0], velocity = (double)s[1];
+    /* :46  velocity += (action - 1) * force + math.cos(3 * position) * (-gravity) */
+    double c = cos(3.0 * position);
+    velocity = fma((double)force, (double)(long)(action[env] - 1), -((double)gravity * c)) +
+               velocity;
+    velocity = wd_clip(velocity, (double)(-max_speed), (double)max_speed);   /* :47 */
+    position = position + velocity;                                          /* :48 */
+    position = wd_clip(position, (double)min_position, (double)max_position);
+    if (position == (double)min_position && velocity < 0.0) velocity = 0.0;  /* :50-51 */
+    s[0] = (float)position; s[1] = (float)velocity;                          /* :53-54 */
+    obs[(size_t)env * 2] = s[0]; obs[(size_t)env * 2 + 1] = s[1];
+    int terminated = position >= (double)goal_position &&
+                     velocity >= (double)goal_velocity;                      /* :59-61 */
+    reward[env] = -1.0f;                                                     /* :64 */
+    if (env_timestep[env] == episode_length) done[env] = 1;                  /* :66-69 */
+    else if (terminated) done[env] = 2;
+  }
+}
+
+/* NumbaClassicControlContinuousMountainCarEnvStep,
+ * continuous_mountain_car/continuous_mountain_car_step_numba.py:14-71 */
+WD_EXPORT void wd_oracle_continuous_mountain_car_step(
+    int n_envs, float *state, const float *action /*[E,1,1] float32*/, int *done,
+    float *reward, float *obs, float min_action, float max_action, float min_position,
+    float max_position, float max_speed, float goal_position, float goal_velocity,
+    float power, int *env_timestep, int episode_length) {
+  for (int env = 0; env < n_envs; env++) {
+    env_timestep[env] += 1;
+    float *s = state + (size_t)env * 2;
+    float a = action[env];
+    float f = a;                                      /* :44 _clip on float32 values */
+    if (a < min_action) f = min_action; else if (a > max_action) f = max_action;
+    float fp = f * power;                             /* float32 product */
+    double position = (double)s[0], velocity = (double)s[1];
+    double c = cos(3.0 * position);
+    velocity = fma(c, -0.0025, (double)fp) + velocity;                       /* :46 */
+    velocity = wd_clip(velocity, (double)(-max_speed), (double)max_speed);
+    position = position + velocity;
+    position = wd_clip(position, (double)min_position, (double)max_position);
+    if (position == (double)min_position && velocity < 0.0) velocity = 0.0;
+    s[0] = (float)position; s[1] = (float)velocity;
+    obs[(size_t)env * 2] = s[0]; obs[(size_t)env * 2 + 1] = s[1];
+    int terminated = position >= (double)goal_position &&
+                     velocity >= (double)goal_velocity;
+    double rew = terminated ? 100.0 : 0.0;                                   /* :64-66 */
+    rew -= pow((double)a, 2.0) * 0.1;                                        /* :67 */
+    reward[env] = (float)rew;
+    if (env_timestep[env] == episode_length || terminated) done[env] = 1;    /* :70-71 */
+  }
+}
+
+/* `x % (2*pi)` as NVVM lowers Python's float modulo: a - floor(|a|/b)*b (one fma), sign of
+ * the dividend restored, then "result takes the divisor's sign". */
+static double wd_python_mod_2pi(double a) {
+  const double b = 2.0 * 3.141592653589793;
+  double q = floor(fabs(a) / b);
+  double r = fma(-q, b, fabs(a));
+  if (!(a >= 0.0)) r = -r;
+  if (r < 0.0) r = r + b;
+  return r;
+}
+
+/* NumbaClassicControlPendulumEnvStep, pendulum/pendulum_step_numba.py:30-72
+ * (module constants :9-14: max_speed 8, max_torque 2, dt 0.05, g 9.81, m = l = 1) */
+WD_EXPORT void wd_oracle_pendulum_step(
+    int n_envs, float *state /*[E,1,2]*/, const float *action /*[E,1,1]*/, int *done,
+    float *reward, float *obs /*[E,1,3]*/, int *env_timestep, int episode_length) {
+  const double kPi = 3.141592653589793, dt = 0.05;
+  const double gain = 3 * 9.81 / (2 * 1.0);
+  for (int env = 0; env < n_envs; env++) {
+    env_timestep[env] += 1;
+    float *s = state + (size_t)env * 2;
+    double u = wd_clip((double)action[env], -2.0, 2.0);                     /* :51 */
+    double th = (double)s[0], thdot = (double)s[1];
+    double an = wd_python_mod_2pi(th + kPi) - kPi;                           /* :26-27 */
+    double td2 = (double)(s[1] * s[1]);               /* float32 ** 2 stays float32 */
+    double costs = fma(u * u, 0.001, fma(an, an, td2 * 0.1));                /* :56 */
+    double newthdot = fma(fma(u, 3.0, (double)sinf(s[0]) * gain), dt, thdot); /* :58 */
+    newthdot = wd_clip(newthdot, -8.0, 8.0);                                 /* :59 */
+    double newth = fma(newthdot, dt, th);                                    /* :60 */
+    s[0] = (float)newth; s[1] = (float)newthdot;
+    float *o = obs + (size_t)env * 3;
+    o[0] = (float)cos(newth); o[1] = (float)sin(newth); o[2] = (float)newthdot;
+    reward[env] = (float)(-costs);
+    if (env_timestep[env] == episode_length) done[env] = 1;
+  }
+}
+
+/* _dsdt, acrobot/acrobot_step_numba.py:70-109 (all link constants 1.0 / 0.5, g = 9.8) */
+static void wd_acrobot_dsdt(const float *st, double torque, float *d) {
+  const double kPi = 3.141592653589793;
+  float theta1 = st[0], theta2 = st[1], dtheta1 = st[2], dtheta2 = st[3];
+  double c2 = (double)cosf(theta2), s2 = (double)sinf(theta2);
+  double d1 = ((0.25 + (1.25 + c2)) + 1.0) + 1.0;                           /* :85-90 */
+  double d2 = (0.25 + 0.5 * c2) + 1.0;                                       /* :91 */
+  double phi2 = (1.0 * 0.5 * 9.8) * cos((double)(float)(theta1 + theta2) - kPi / 2);
+  double phi1 = ((-0.5 * (double)(float)(dtheta2 * dtheta2)) * s2
+                 - ((double)dtheta2 * (double)dtheta1) * s2
+                 + ((1.0 * 0.5 + 1.0 * 1.0) * 9.8) * cos((double)theta1 - kPi / 2))
+                + phi2;                                                      /* :93-98 */
+  double ddtheta2 = (torque + d2 / d1 * phi1
+                     - (0.5 * (double)(float)(dtheta1 * dtheta1)) * s2 - phi2) /
+                    ((0.25 + 1.0) - d2 * d2 / d1);                           /* :100-101 */
+  double ddtheta1 = -(d2 * ddtheta2 + phi1) / d1;                            /* :102 */
+  d[0] = dtheta1; d[1] = dtheta2; d[2] = (float)ddtheta1; d[3] = (float)ddtheta2;
+}
+
+static double wd_wrap(double x, double m, double M) {                        /* :137-143 */
+  double diff = M - m;
+  while (x > M) x = x - diff;
+  while (x < m) x = x + diff;
+  return x;
+}
+
+/* NumbaClassicControlAcrobotEnvStep, acrobot/acrobot_step_numba.py:24-67 + rk4 :112-134 */
+WD_EXPORT void wd_oracle_acrobot_step(
+    int n_envs, float *state /*[E,1,4]*/, const int *action /*[E,1,1]*/, int *done,
+    float *reward, float *obs /*[E,1,6]*/, int *env_timestep, int episode_length) {
+  const double kPi = 3.141592653589793;
+  const double kMaxVel1 = 12.566370614359172, kMaxVel2 = 28.274333882308138;
+  const double dt = 0.2, dt2 = 0.1;
+  for (int env = 0; env < n_envs; env++) {
+    env_timestep[env] += 1;
+    float *s = state + (size_t)env * 4;
+    double torque = (double)(action[env] - 1);          /* AVAIL_TORQUE[action], :6 */
+    float k1[4], k2[4], k3[4], k4[4], u[4], ns[4];
+    wd_acrobot_dsdt(s, torque, k1);
+    for (int i = 0; i < 4; i++) u[i] = (float)((double)s[i] + (double)k1[i] * dt2);
+    wd_acrobot_dsdt(u, torque, k2);
+    for (int i = 0; i < 4; i++) u[i] = (float)((double)s[i] + (double)k2[i] * dt2);
+    wd_acrobot_dsdt(u, torque, k3);
+    for (int i = 0; i < 4; i++) u[i] = (float)((double)s[i] + (double)k3[i] * dt);
+    wd_acrobot_dsdt(u, torque, k4);
+    for (int i = 0; i < 4; i++) {
+      double sum = (((double)k1[i] + 2.0 * (double)k2[i]) + 2.0 * (double)k3[i]) + (double)k4[i];
+      ns[i] = (float)((double)s[i] + (dt / 6.0) * sum);
+    }
+    ns[0] = (float)wd_wrap((double)ns[0], -kPi, kPi);                        /* :51-54 */
+    ns[1] = (float)wd_wrap((double)ns[1], -kPi, kPi);
+    ns[2] = (float)fmin(fmax((double)ns[2], -kMaxVel1), kMaxVel1);
+    ns[3] = (float)fmin(fmax((double)ns[3], -kMaxVel2), kMaxVel2);
+    for (int i = 0; i < 4; i++) s[i] = ns[i];
+    float c0 = cosf(ns[0]);
+    int terminated = (float)(-c0 - cosf((float)(ns[1] + ns[0]))) > 1.0f;     /* :151-153 */
+    reward[env] = terminated ? 0.0f : -1.0f;                                 /* :44,60-61 */
+    float *o = obs + (size_t)env * 6;                                        /* :156-168 */
+    o[0] = c0; o[1] = sinf(ns[0]); o[2] = cosf(ns[1]); o[3] = sinf(ns[1]);
+    o[4] = ns[2]; o[5] = ns[3];
+    if (env_timestep[env] == episode_length || terminated) done[env] = 1;    /* :66-67 */
+  }
 }

@@ -165,3 +165,76 @@ def test_numpy_port_matches_reference(name):
         assert close(np.array([rew[a] for a in range(N)]), fx["rewards"][t], 1e-6).all(), t
         assert bool(done) == bool(fx["done"][t])
         assert (env.still_in_the_game == fx["still_in_the_game"][t]).all()
+
+
+# ------------------------------------------------------- classic control
+_CC_ENVS = ["cartpole", "mountain_car", "continuous_mountain_car", "pendulum", "acrobot"]
+
+
+@pytest.mark.parametrize("name", _CC_ENVS)
+def test_classic_control_oracle_vs_reference_kernels_in_the_cuda_simulator(name, oracle_lib):
+    """tests/golden/classic_control_cudasim.npz holds inputs/outputs of the reference's OWN
+    numba kernels executed by numba's CUDA simulator (tests/golden/
+    make_classic_control_golden.py).  The simulator applies NumPy scalar typing instead of
+    numba's compiled typing, so this pins the algorithm -- every branch, clip, wrap, reward
+    and done rule, and the argument order -- to 1e-5 abs-or-rel (Acrobot 2e-4), not the last
+    bit."""
+    g = load_golden("classic_control_cudasim.npz")
+    T = int(g["episode_length"])
+    consts = [float(c) for c in g[f"{name}__consts"]]
+    fn = getattr(oracle_lib, f"wd_oracle_{name}_step")
+    steps, E = g[f"{name}__state_in"].shape[:2]
+    flips = 0
+    seen = set()
+    for s in range(steps):
+        state = g[f"{name}__state_in"][s].copy()
+        ts = g[f"{name}__timestep_in"][s].copy()
+        action = np.ascontiguousarray(g[f"{name}__action"][s])
+        done = np.zeros(E, np.int32)
+        reward = np.full((E, 1), 7.0, np.float32)
+        obs = np.full_like(g[f"{name}__obs"][s], 7.0)
+        fn(E, state, action, done, reward, obs, *consts, ts, T)
+        mine = np.concatenate([state.reshape(E, -1), obs.reshape(E, -1), reward], 1)
+        ref = np.concatenate([g[f"{name}__state_out"][s].reshape(E, -1),
+                              g[f"{name}__obs"][s].reshape(E, -1), g[f"{name}__reward"][s]], 1)
+        # Acrobot: velocities reach 28 rad/s and the RK4 stages cancel, so the simulator's
+        # NumPy typing shows up at the 1e-5..1e-4 level there
+        tol = 2e-4 if name == "acrobot" else 1e-5
+        ok = (np.abs(mine - ref) <= tol + tol * np.abs(ref)).all(1)
+        flips += int((~ok).sum()) + int((done[ok] != g[f"{name}__done"][s][ok]).sum())
+        assert (ts == g[f"{name}__timestep_out"][s]).all()
+        seen |= set(np.unique(done).tolist())
+    assert flips == 0, (name, flips)
+    assert 1 in seen and (name != "mountain_car" or 2 in seen)
+
+
+@pytest.mark.parametrize("name,cls", [
+    ("mountain_car", "MountainCarPhysics"),
+    ("continuous_mountain_car", "ContinuousMountainCarPhysics"),
+    ("pendulum", "PendulumPhysics"), ("acrobot", "AcrobotPhysics")])
+def test_classic_control_oracle_vs_float64_physics(name, cls, oracle_lib):
+    """The C oracle (the reference's numba kernels restated) against the float64 restatement
+    of the gym integrators that the CPU envs use: same physics, different precision."""
+    from warp_drive_b200.envs.single_agent import classic_control as cc
+
+    phys = getattr(cc, cls)()
+    g = load_golden("classic_control_cudasim.npz")
+    consts = [float(c) for c in g[f"{name}__consts"]]
+    fn = getattr(oracle_lib, f"wd_oracle_{name}_step")
+    state_in = g[f"{name}__state_in"][0]
+    action = np.ascontiguousarray(g[f"{name}__action"][0])
+    E = state_in.shape[0]
+    state = state_in.copy()
+    done = np.zeros(E, np.int32)
+    reward = np.zeros((E, 1), np.float32)
+    obs = np.zeros_like(g[f"{name}__obs"][0])
+    ts = np.zeros(E, np.int32)
+    fn(E, state, action, done, reward, obs, *consts, ts, 1000)
+    bad = 0
+    for e in range(E):
+        phys.state = np.array(state_in[e, 0], dtype=np.float64)
+        o, r, terminated, _, _ = phys.step(action[e, 0, 0] if action.dtype.kind == "i"
+                                           else action[e, 0])
+        ok = np.allclose(obs[e, 0], o, rtol=1e-4, atol=1e-5) and abs(reward[e, 0] - r) <= 1e-4 * max(1, abs(r))
+        bad += (not ok) or (bool(done[e]) != bool(terminated))
+    assert bad <= 1, (name, bad)     # one row may sit on a wrap / clip / goal threshold

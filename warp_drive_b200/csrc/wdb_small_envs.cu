@@ -151,7 +151,7 @@ WDB_API int wdb_tag_gridworld_step(void *stream, int n_envs, int n_agents, int *
 // cartpole/cartpole_step_numba.py:6-83.  One thread per env; the reference launches one
 // 1-thread block per env.  Arithmetic follows numba's typing of that source: float32
 // everywhere except where the float64 literal 4.0/3.0 promotes (thetaacc, xacc and the
-// two velocity updates).
+// two velocity updates); checked against numba's type annotations of the reference kernel.
 __global__ void __launch_bounds__(256)
 cartpole_step_kernel(int n_envs, float4 *__restrict__ state, const int *__restrict__ action,
                      int *__restrict__ done, float *__restrict__ reward,
@@ -167,16 +167,25 @@ cartpole_step_kernel(int n_envs, float4 *__restrict__ state, const int *__restri
   const float x = s.x, x_dot = s.y, theta = s.z, theta_dot = s.w;
   const float force = (action[env] > 0.5f) ? force_mag : -force_mag;
   const float costheta = cosf(theta), sintheta = sinf(theta);
-  const float temp = (force + polemass_length * (theta_dot * theta_dot) * sintheta) / total_mass;
+  // Fused multiply-adds exactly where the reference binary has them (ptxas on numba's PTX,
+  // oracle/_ref/numba_cartpole.cubin): FFMA for the force sum, g*sin - cos*temp and the two
+  // position updates; DFMA for the two velocity updates; plain mul/div elsewhere.
+  const float temp = __fdiv_rn(
+      __fmaf_rn(__fmul_rn(polemass_length, __fmul_rn(theta_dot, theta_dot)), sintheta, force),
+      total_mass);
+  const float c2m = __fdiv_rn(__fmul_rn(masspole, __fmul_rn(costheta, costheta)), total_mass);
+  const float torque = __fmaf_rn(gravity, sintheta, -__fmul_rn(costheta, temp));
   const double thetaacc =
-      (double)(gravity * sintheta - costheta * temp) /
-      ((double)length * (4.0 / 3.0 - (double)(masspole * (costheta * costheta) / total_mass)));
-  const double xacc = (double)temp - (double)polemass_length * thetaacc * (double)costheta / (double)total_mass;
+      __ddiv_rn((double)torque, __dmul_rn((double)length, __dsub_rn(4.0 / 3.0, (double)c2m)));
+  const double xacc = __dsub_rn(
+      (double)temp,
+      __ddiv_rn(__dmul_rn(__dmul_rn((double)polemass_length, thetaacc), (double)costheta),
+                (double)total_mass));
   float4 n;
-  n.x = x + tau * x_dot;
-  n.y = (float)((double)x_dot + (double)tau * xacc);
-  n.z = theta + tau * theta_dot;
-  n.w = (float)((double)theta_dot + (double)tau * thetaacc);
+  n.x = __fmaf_rn(tau, x_dot, x);
+  n.y = (float)__fma_rn((double)tau, xacc, (double)x_dot);
+  n.z = __fmaf_rn(tau, theta_dot, theta);
+  n.w = (float)__fma_rn((double)tau, thetaacc, (double)theta_dot);
   state[env] = n;
   obs[env] = n;
   const bool terminated = (n.x < -x_thr) || (n.x > x_thr) || (n.z < -theta_thr) || (n.z > theta_thr);

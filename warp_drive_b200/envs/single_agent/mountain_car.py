@@ -1,0 +1,6 @@
+"""Import path of the reference's example_envs/single_agent/classic_control/mountain_car/mountain_car.py;
+the classes live in classic_control.py."""
+from warp_drive_b200.envs.single_agent.classic_control import (  # noqa: F401
+    ClassicControlMountainCarEnv,
+    CUDAClassicControlMountainCarEnv,
+)

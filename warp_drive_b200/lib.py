@@ -107,6 +107,12 @@ _SIGNATURES = {
     "wdb_mlp_pack_obs": (_i, [_vp, _vp, _ll, _i, _vp]),
     "wdb_mlp_policy_forward_tiles": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _ll, _vp, _vp, _vp]),
     "wdb_discounted_returns": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f]),
+    "wdb_mountain_car_step": (
+        _i, [_vp, _i, _vp, _vp, _vp, _vp, _vp] + [_f] * 7 + [_vp, _i]),
+    "wdb_continuous_mountain_car_step": (
+        _i, [_vp, _i, _vp, _vp, _vp, _vp, _vp] + [_f] * 8 + [_vp, _i]),
+    "wdb_pendulum_step": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
+    "wdb_acrobot_step": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
     "wdb_cartpole_step": (
         _i,
         [_vp, _i, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _f, _f, _f, _f, _vp, _i],

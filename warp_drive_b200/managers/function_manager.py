@@ -78,6 +78,51 @@ def _k_cartpole_step(fm, a, block, grid):
     ), "CartPoleEnvStep")
 
 
+def _k_mountain_car_step(fm, a, block, grid):
+    # NumbaClassicControlMountainCarEnvStep(...) -- mountain_car_step_numba.py:14-28
+    assert len(a) == 14, f"MountainCar step takes 14 arguments, got {len(a)}"
+    _libmod.check(_libmod.load().wdb_mountain_car_step(
+        _stream(), fm._num_envs, _P(a[0]), _P(a[1]), _P(a[2]), _P(a[3]), _P(a[4]),
+        *[float(_scalar(v)) for v in a[5:12]], _P(a[12]), int(_scalar(a[13])),
+    ), "MountainCarEnvStep")
+
+
+def _k_continuous_mountain_car_step(fm, a, block, grid):
+    # NumbaClassicControlContinuousMountainCarEnvStep(...)
+    # -- continuous_mountain_car_step_numba.py:14-29
+    assert len(a) == 15, f"ContinuousMountainCar step takes 15 arguments, got {len(a)}"
+    _require_float_actions(a[1], "ContinuousMountainCar")
+    _libmod.check(_libmod.load().wdb_continuous_mountain_car_step(
+        _stream(), fm._num_envs, _P(a[0]), _P(a[1]), _P(a[2]), _P(a[3]), _P(a[4]),
+        *[float(_scalar(v)) for v in a[5:13]], _P(a[13]), int(_scalar(a[14])),
+    ), "ContinuousMountainCarEnvStep")
+
+
+def _k_pendulum_step(fm, a, block, grid):
+    # NumbaClassicControlPendulumEnvStep(...) -- pendulum_step_numba.py:30-37
+    assert len(a) == 7, f"Pendulum step takes 7 arguments, got {len(a)}"
+    _require_float_actions(a[1], "Pendulum")
+    _libmod.check(_libmod.load().wdb_pendulum_step(
+        _stream(), fm._num_envs, _P(a[0]), _P(a[1]), _P(a[2]), _P(a[3]), _P(a[4]),
+        _P(a[5]), int(_scalar(a[6])),
+    ), "PendulumEnvStep")
+
+
+def _k_acrobot_step(fm, a, block, grid):
+    # NumbaClassicControlAcrobotEnvStep(...) -- acrobot_step_numba.py:24-31
+    assert len(a) == 7, f"Acrobot step takes 7 arguments, got {len(a)}"
+    _libmod.check(_libmod.load().wdb_acrobot_step(
+        _stream(), fm._num_envs, _P(a[0]), _P(a[1]), _P(a[2]), _P(a[3]), _P(a[4]),
+        _P(a[5]), int(_scalar(a[6])),
+    ), "AcrobotEnvStep")
+
+
+def _require_float_actions(handle, env):
+    t = handle.tensor if hasattr(handle, "tensor") else handle
+    if torch.is_tensor(t) and t.dtype != torch.float32:
+        raise TypeError(f"{env} takes continuous float32 actions, got {t.dtype}")
+
+
 def _k_testkernel(fm, a, block, grid):
     # testkernel(x, y, done, actions, multiplier, target, step, episode_length)
     assert len(a) == 8
@@ -152,6 +197,14 @@ _KERNELS = {
     "NumbaTagGridWorldStep": _k_tag_gridworld_step,
     "NumbaClassicControlCartPoleEnvStep": _k_cartpole_step,
     "CudaClassicControlCartPoleEnvStep": _k_cartpole_step,
+    "NumbaClassicControlMountainCarEnvStep": _k_mountain_car_step,
+    "CudaClassicControlMountainCarEnvStep": _k_mountain_car_step,
+    "NumbaClassicControlContinuousMountainCarEnvStep": _k_continuous_mountain_car_step,
+    "CudaClassicControlContinuousMountainCarEnvStep": _k_continuous_mountain_car_step,
+    "NumbaClassicControlPendulumEnvStep": _k_pendulum_step,
+    "CudaClassicControlPendulumEnvStep": _k_pendulum_step,
+    "NumbaClassicControlAcrobotEnvStep": _k_acrobot_step,
+    "CudaClassicControlAcrobotEnvStep": _k_acrobot_step,
     "testkernel": _k_testkernel,
     "reset_in_float_when_done_2d": _k_reset_2d,
     "reset_in_int_when_done_2d": _k_reset_2d,
