@@ -226,6 +226,48 @@ def test_cpu_cartpole_env_runs():
     assert 5 < steps <= 50
 
 
+@pytest.mark.parametrize("module,cls,obs_dim,continuous", [
+    ("mountain_car", "ClassicControlMountainCarEnv", 2, False),
+    ("continuous_mountain_car", "ClassicControlContinuousMountainCarEnv", 2, True),
+    ("acrobot", "ClassicControlAcrobotEnv", 6, False),
+    ("pendulum", "ClassicControlPendulumEnv", 3, True)])
+def test_cpu_classic_control_envs_run(module, cls, obs_dim, continuous):
+    """Same module paths, class names, `name` attributes and step()/reset() contract as
+    example_envs/single_agent/classic_control/* of the reference; the device twin declares
+    the reference's data dictionary (state [+ constants] [+ reset pool])."""
+    import importlib
+
+    from warp_drive_b200.env_wrapper import EnvWrapper
+
+    mod = importlib.import_module(f"warp_drive_b200.envs.single_agent.{module}")
+    env_cls = getattr(mod, cls)
+    assert env_cls.name == cls
+    env = EnvWrapper(env_cls(episode_length=30, seed=5), env_backend="cpu")
+    o = env.reset()
+    assert o[0].shape == (obs_dim,) and o[0].dtype == np.float32
+    again = env.reset()
+    assert np.array_equal(o[0], again[0])          # fixed seed -> fixed initial state
+    rs = np.random.RandomState(0)
+    for steps in range(1, 31):
+        a = rs.uniform(-2, 2, (1,)).astype(np.float32) if continuous else int(rs.randint(0, 3))
+        o, r, d, _ = env.step({0: a})
+        assert o[0].shape == (obs_dim,) and np.isfinite(o[0]).all() and np.isfinite(r[0])
+        if d["__all__"]:
+            break
+    assert d["__all__"] and steps <= 30
+
+    dev = getattr(mod, "CUDA" + cls)(episode_length=30, env_backend="b200", reset_pool_size=4,
+                                     seed=5)
+    data = dev.get_data_dictionary()
+    assert "state" in data and not data["state"]["attributes"]["save_copy_and_apply_at_reset"]
+    pool = dev.get_reset_pool_dictionary()
+    assert pool["state_reset_pool"]["data"].shape[0] == 4
+    assert pool["state_reset_pool"]["attributes"]["reset_target"] == "state"
+    fixed = getattr(mod, "CUDA" + cls)(episode_length=30, env_backend="b200", seed=5)
+    assert fixed.get_data_dictionary()["state"]["attributes"]["save_copy_and_apply_at_reset"]
+    assert len(fixed.get_reset_pool_dictionary()) == 0
+
+
 def test_spaces_and_registrar():
     from warp_drive_b200.utils import spaces
     from warp_drive_b200.utils.env_registrar import EnvironmentRegistrar

@@ -79,8 +79,12 @@ class EnvWrapper:
             num_envs=int(self.cuda_data_manager.meta_info("n_envs")),
             blocks_per_env=int(self.cuda_data_manager.meta_info("blocks_per_env")),
             process_id=process_id)
-        # no nvcc / numba JIT: the kernels are prebuilt in libwdb200.so
-        self.cuda_function_manager.initialize_default_functions()
+        # no nvcc / numba JIT for the built-in envs: their kernels are prebuilt in libwdb200.so.
+        # A custom env whose .cu path sits in the registrar is compiled for sm_100a here
+        # (reference env_wrapper.py:177-219 -> compile_and_load_cuda).
+        self.cuda_function_manager.compile_and_load_cuda(
+            env_name=self.name, customized_env_registrar=env_registrar,
+            event_messenger=event_messenger)
         self.cuda_function_feed = CUDAFunctionFeed(self.cuda_data_manager)
 
         prefix = "Numba" if self.env_backend == "numba" else "Cuda"

@@ -11,6 +11,7 @@ arguments so nothing is recompiled per shape.
 """
 import ctypes
 import logging
+import os
 import time
 from typing import Optional
 
@@ -263,6 +264,7 @@ class CUDAFunctionManager:
         self._cuda_functions = {}
         self._cuda_function_names = []
         self._custom = {}
+        self._custom_modules = []      # user cubins (utils/custom_kernels.py)
         self._shared_tensors = {}
         self._keepalive = []
         self._scratch_int = None
@@ -275,18 +277,46 @@ class CUDAFunctionManager:
     # --- module loading: the library is prebuilt, these only keep the reference's call
     # --- sites working (env_wrapper.py:177-219, tests load a .fatbin / numba module)
     def load_cuda_from_binary_file(self, cubin, default_functions_included=True):
+        """Reference tests pass the path of their own prebuilt fatbin here
+        (tests/.../test_action_sampler.py:33-40): ignored, the default kernels are in
+        libwdb200.so.  A cubin built by utils.custom_kernels.compile_module IS loaded."""
+        if isinstance(cubin, str) and cubin.endswith(".cubin") and os.path.exists(cubin):
+            self._load_custom_module(cubin)
         if default_functions_included:
             self.initialize_default_functions()
 
     def load_cuda_from_source_code(self, code, default_functions_included=True):
-        raise NotImplementedError(
-            "libwdb200 is prebuilt; register custom device code as a callable with "
-            "register_function(name, fn) (see INTEGRATION.md)")
+        """Compile CUDA-C source (a path to a .cu file or the source text) for sm_100a with the
+        reference's three compile-time constants and load it next to the prebuilt kernels
+        (reference: pycuda_function_manager.py:197-232 does this with pycuda's
+        SourceModule).  Its extern "C" kernels become get_function() names."""
+        from warp_drive_b200.utils import custom_kernels
+
+        cubin = custom_kernels.compile_module(code, self._num_envs, self._num_agents,
+                                              self._blocks_per_env)
+        self._load_custom_module(cubin)
+        if default_functions_included:
+            self.initialize_default_functions()
+
+    def _load_custom_module(self, cubin):
+        from warp_drive_b200.utils import custom_kernels
+
+        module = custom_kernels.CustomCudaModule(cubin)
+        self._custom_modules.append(module)
+        return module
 
     def compile_and_load_cuda(self, env_name=None, template_header_file=None,
                               template_runner_file=None, template_path=None,
                               default_functions_included=True,
                               customized_env_registrar=None, event_messenger=None):
+        """The built-in envs need no compilation.  If `customized_env_registrar` holds a `.cu`
+        path for `env_name` (env_registrar.add_cuda_env_src_path, reference
+        pycuda_function_manager.py:268-282), that file is compiled for sm_100a and its kernels
+        take precedence over built-ins of the same name."""
+        if customized_env_registrar is not None and env_name is not None:
+            src = customized_env_registrar.get_cuda_env_src_path(env_name)
+            if src is not None:
+                self.load_cuda_from_source_code(src, default_functions_included=False)
         if default_functions_included:
             self.initialize_default_functions()
 
@@ -316,8 +346,11 @@ class CUDAFunctionManager:
         for fname in func_names or []:
             if fname in self._cuda_functions:
                 continue
+            module = next((m for m in self._custom_modules if m.has(fname)), None)
             if fname in self._custom:
                 adapter = self._custom[fname]
+            elif module is not None:
+                adapter = module.launcher(fname)
             elif fname == "sample_actions":
                 adapter = _k_noop  # launched through CUDASampler.sample
             elif fname in _KERNELS:
@@ -335,6 +368,8 @@ class CUDAFunctionManager:
         for cname in constant_names:
             value = np.ascontiguousarray(data_manager.shared_constant(cname))
             self._shared_tensors[cname] = torch.from_numpy(value.reshape(-1)).to(self.device)
+            for module in self._custom_modules:   # user code keeps its __constant__ symbols
+                module.set_constant(cname, value)
 
     def shared_constant_tensor(self, name):
         if name not in self._shared_tensors:
@@ -533,7 +568,8 @@ class CUDAEnvironmentReset:
         fm = self._function_manager
         if reset_function_name is None or (
                 reset_function_name not in fm._cuda_functions
-                and reset_function_name not in fm._custom):
+                and reset_function_name not in fm._custom
+                and not any(m.has(reset_function_name) for m in fm._custom_modules)):
             return
         fm.initialize_functions([reset_function_name])
         self._cuda_custom_reset = fm.get_function(reset_function_name)

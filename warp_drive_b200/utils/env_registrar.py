@@ -1,7 +1,8 @@
 """EnvironmentRegistrar: name -> env class lookup for EnvWrapper(env_name=...).
-API of warp_drive/utils/env_registrar.py:4-132.  The reference also records a path to a
-user .cu file that it JIT-compiles; with a prebuilt libwdb200.so custom device code is
-registered through CUDAFunctionManager.register_function instead."""
+API of warp_drive/utils/env_registrar.py:4-132, including the path of a user `.cu` file:
+the reference JIT-compiles it with nvcc + pycuda; here CUDAFunctionManager.
+compile_and_load_cuda compiles it for sm_100a (utils/custom_kernels.py) and serves its
+kernels next to the prebuilt libwdb200 ones."""
 
 
 class EnvironmentRegistrar:
@@ -41,6 +42,12 @@ class EnvironmentRegistrar:
     def has_env(self, name, env_backend="cpu"):
         table = self._cpu_envs if env_backend == "cpu" else self._device_envs
         return name.lower() in table
+
+    def add_cuda_env_src_path(self, name, cuda_env_src_path, env_backend="pycuda"):
+        """Register the ABSOLUTE path of a custom env's CUDA source (reference :88-119)."""
+        assert str(cuda_env_src_path).endswith(".cu"), (
+            "the customized environment is expected to be a CUDA source code (*.cu)")
+        self._customized_env_path[name.lower()] = str(cuda_env_src_path)
 
     def get_cuda_env_src_path(self, name, env_backend="pycuda"):
         return self._customized_env_path.get(name.lower())
