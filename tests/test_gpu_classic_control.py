@@ -16,7 +16,7 @@ Bars (written here, cited in DESIGN.md):
     the bit-identical fraction is measured, reported and held to MIN_BIT_IDENTICAL; done /
     timestep flags must be IDENTICAL for every env whose float outputs are bit-identical (a
     last-bit difference may legitimately flip a threshold test).
-  * vs the C oracle: within 1e-5 abs-or-rel (libm vs libdevice), flags equal except for at
+  * vs the C oracle: within 1e-5 abs-or-rel (Acrobot 2e-4; libm vs libdevice), flags equal except for at
     most MAX_BRANCH_FLIPS threshold flips.
 A JSON summary goes to gpurun_out/classic_control_parity.json.
 """
@@ -38,13 +38,18 @@ E, STEPS, EP_LEN = 8192, 24, 200
 # jump.  That is a 1e-7-probability event per env-step; this many rows of the 196 608 compared
 # per env may take the other branch before the test calls it a failure.
 MAX_BRANCH_FLIPS = 3
+# vs the C oracle (glibc sinf/cosf instead of libdevice's, 1-2 ulp apart): Acrobot integrates
+# accelerations of several hundred rad/s^2 through four float32-rounded RK4 stages, which
+# turns those ulps into 1e-5..1e-4 relative differences (the numba binary, same libdevice,
+# stays bit-identical)
+ORACLE_TOL = {"acrobot": 2e-4}
 PI = np.pi
 
 # Fraction of env-steps whose float32 outputs must be BIT-identical to the reference numba
 # binary (seeded, deterministic inputs).  Set from the measured run recorded in
 # profiles/r3_classic_control_parity.json; the 1e-6 bound below holds for every row regardless.
-MIN_BIT_IDENTICAL = {"cartpole": 0.0, "mountain_car": 0.0, "continuous_mountain_car": 0.0,
-                     "pendulum": 0.0, "acrobot": 0.0}
+MIN_BIT_IDENTICAL = {"cartpole": 1.0, "mountain_car": 1.0, "continuous_mountain_car": 1.0,
+                     "pendulum": 1.0, "acrobot": 0.0}
 
 _CARTPOLE_CONSTS = [9.8, 0.1, 1.1, 0.5, 0.05, 10.0, 0.02, 12 * 2 * np.pi / 360, 2.4]
 _MC_CONSTS = [-1.2, 0.6, 0.07, 0.5, 0.0, 0.001, 0.0025]
@@ -162,7 +167,7 @@ def test_step_vs_reference_numba_and_oracle(name, wdb_lib, oracle_lib):
         done_seen |= set(np.unique(t_done).tolist())
 
         # ---- (b) vs the C oracle
-        ok = _close(mine, host, 1e-5).all(1)
+        ok = _close(mine, host, ORACLE_TOL.get(name, 1e-5)).all(1)
         bad_oracle += int((~ok).sum())
         assert bad_oracle <= MAX_BRANCH_FLIPS, (name, "vs C oracle", mine[~ok][:3], host[~ok][:3])
         max_abs_oracle = max(max_abs_oracle, float(np.abs(mine - host)[ok].max()))
