@@ -47,3 +47,56 @@ def test_ring_buffer_matches_the_reference_class():
         assert ring.isfull() == bool(g[f"ring__full_{i}"])
     with pytest.raises(AssertionError):
         RingBuffer(name="big", size=7, tensor=torch.zeros(6, 2))
+
+
+class _StubEnvWrapper:
+    """What the model classes read from an EnvWrapper (no device needed)."""
+
+    class _DM:
+        def get_shape(self, name=None):
+            return (8, 4, 1, 3)
+
+    def __init__(self, obs_dim=3, act_dim=1):
+        from warp_drive_b200.utils import spaces
+
+        class _Env:
+            observation_space = {0: spaces.Box(-1.0, 1.0, shape=(obs_dim,), dtype=np.float32)}
+            action_space = {0: spaces.Box(-2.0, 2.0, shape=(act_dim,), dtype=np.float32)}
+
+        self.env = _Env()
+        self.n_agents = 1
+        self.cuda_data_manager = self._DM()
+
+
+def test_actor_and_critic_follow_the_reference_contract():
+    from warp_drive_b200.training.models.fully_connected import ModelFactory
+    from warp_drive_b200.training.models.fully_connected_actor_critic import ActorAsPolicy
+
+    env = _StubEnvWrapper()
+    kw = dict(env=env, policy="shared", policy_tag_to_agent_id_map={"shared": [0]})
+    actor = ModelFactory.create("fully_connected_actor")(
+        model_config={"type": "fully_connected_actor", "fc_dims": [16, 8], "output_w": 2.0}, **kw)
+    critic = ModelFactory.create("fully_connected_action_value_critic")(
+        model_config={"type": "fully_connected_action_value_critic", "fc_dims": [16, 8]}, **kw)
+    # parameter names of the reference checkpoints (fully_connected_actor_critic.py:31-41,99-109)
+    assert sorted(actor.state_dict()) == [
+        "fc.0.0.bias", "fc.0.0.weight", "fc.1.0.bias", "fc.1.0.weight",
+        "policy_head.bias", "policy_head.weight"]
+    assert sorted(critic.state_dict()) == [
+        "fc.0.0.bias", "fc.0.0.weight", "fc.1.0.bias", "fc.1.0.weight",
+        "vf_head.bias", "vf_head.weight"]
+    assert critic.fc["0"][0].in_features == 3 + 1
+    obs = torch.randn(5, 4, 1, 3)
+    act = actor(obs)
+    assert isinstance(act, list) and len(act) == 1 and act[0].shape == (5, 4, 1, 1)
+    assert act[0].abs().max() <= 2.0                       # output_w * tanh
+    with torch.no_grad():
+        actor.policy_head.bias.fill_(50.0)
+    assert torch.allclose(actor(obs)[0], torch.full((5, 4, 1, 1), 2.0))
+    q = critic(obs, act)
+    assert q.shape == (5, 4, 1)
+    assert torch.equal(q, critic(obs, act[0]))             # list or tensor action
+    q.sum().backward()                                       # dJ/d(actor) flows through Q
+    assert actor.policy_head.weight.grad is not None
+    probs, values = ActorAsPolicy(actor)(obs)
+    assert values is None and torch.equal(probs[0], actor(obs)[0])

@@ -155,6 +155,15 @@ class ModelFactory:
 
     @classmethod
     def create(cls, model_name):
+        if model_name not in cls._registry and model_name in (
+                "fully_connected_actor", "fully_connected_action_value_critic"):
+            # the DDPG pair (reference factory.py:10-16), imported on first use
+            from warp_drive_b200.training.models.fully_connected_actor_critic import (
+                FullyConnectedActionValueCritic, FullyConnectedActor)
+
+            cls._registry["fully_connected_actor"] = FullyConnectedActor
+            cls._registry["fully_connected_action_value_critic"] = (
+                FullyConnectedActionValueCritic)
         if model_name not in cls._registry:
             raise ValueError(f"unknown model type '{model_name}'")
         return cls._registry[model_name]
