@@ -100,3 +100,33 @@ def test_actor_and_critic_follow_the_reference_contract():
     assert actor.policy_head.weight.grad is not None
     probs, values = ActorAsPolicy(actor)(obs)
     assert values is None and torch.equal(probs[0], actor(obs)[0])
+
+
+def test_a2c_negative_positive_env_sampling():
+    """single_mountain_car.yaml's `neg_pos_env_ratio` (a2c.py:58-69,196-220 of the reference):
+    envs that reached the goal (done == 2) are all kept, the others down-sampled."""
+    from warp_drive_b200.training.algorithms.policygradient import A2C
+
+    torch.manual_seed(0)
+    T, E, Np = 6, 40, 1
+    done = torch.zeros(T, E, dtype=torch.int32)
+    done[3, [2, 17, 30]] = 2          # three envs reached the goal
+    done[5, 8] = 1                    # an episode end is not a positive
+    keep, n_pos, n_neg = A2C._sample_positive_negative_env_ids(done, 5)
+    assert n_pos == 3 and n_neg == 15 and keep.numel() == 18
+    assert set(keep[:3].tolist()) == {2, 17, 30} and len(set(keep.tolist())) == 18
+    assert A2C._sample_positive_negative_env_ids(done, 50)[0] is None     # nothing to drop
+    assert A2C._sample_positive_negative_env_ids(torch.zeros_like(done), 5)[0] is None
+    algo = A2C(discount_factor_gamma=0.99, vf_loss_coeff=1.0, entropy_coeff=0.05)
+    probs = [torch.softmax(torch.randn(T, E, Np, 3), -1).requires_grad_()]
+    values = torch.randn(T, E, Np, requires_grad=True)
+    loss, metrics = algo.compute_loss_and_metrics(
+        timestep=10, actions_batch=torch.randint(0, 3, (T, E, Np, 1)),
+        rewards_batch=-torch.ones(T, E, Np), done_flags_batch=done,
+        action_probabilities_batch=probs, value_functions_batch=values,
+        perform_logging=True, negative_positive_ratio=5)
+    assert metrics["Num of Positive Sampled Envs"] == 3
+    assert metrics["Num of Negative Sampled Envs"] == 15
+    loss.backward()
+    touched = (values.grad.abs().sum(dim=(0, 2)) > 0).sum().item()
+    assert touched == 18               # only the sampled envs contribute

@@ -137,3 +137,90 @@ def test_discounted_returns_kernel_matches_recursion():
     want = discounted_returns(rewards, done, values, 0.98)          # host recursion
     got = discounted_returns(rewards.cuda(), done.cuda(), values.cuda(), 0.98).cpu()
     assert torch.allclose(got, want, atol=1e-5, rtol=1e-5)
+
+
+# --------------------------------------------------------------- classic control (8 f2)
+@pytest.mark.parametrize("config,cls", [
+    ("single_acrobot", "CUDAClassicControlAcrobotEnv"),
+    ("single_mountain_car", "CUDAClassicControlMountainCarEnv")])
+def test_train_discrete_classic_control_with_the_reference_configs(config, cls, tmp_path):
+    """single_acrobot.yaml / single_mountain_car.yaml (values of the reference's files) through
+    the A2C trainer; MountainCar additionally exercises `neg_pos_env_ratio` (done == 2)."""
+    from warp_drive_b200.env_wrapper import EnvWrapper
+    from warp_drive_b200.envs.single_agent import classic_control as cc
+    from warp_drive_b200.training.trainer import Trainer
+
+    cfg = _run_config(config, num_envs=128, train_batch_size=128 * 20, num_episodes=256)
+    cfg["env"].update(episode_length=40, reset_pool_size=32)
+    cfg["saving"]["basedir"] = str(tmp_path)
+    env = getattr(cc, cls)(**cfg["env"])
+    wrapper = EnvWrapper(env, num_envs=128, env_backend="numba")
+    trainer = Trainer(env_wrapper=wrapper, config=cfg,
+                      policy_tag_to_agent_id_map={"shared": [0]}, results_dir="x", verbose=False)
+    lines = _train_and_check(trainer)
+    assert lines[-1]["shared"]["Mean episodic steps"] <= 40
+    if config == "single_mountain_car":
+        assert "Num of Positive Sampled Envs" in lines[-1]["shared"]
+
+
+@pytest.mark.parametrize("config,cls", [
+    ("single_pendulum", "CUDAClassicControlPendulumEnv"),
+    ("single_continuous_mountain_car", "CUDAClassicControlContinuousMountainCarEnv")])
+def test_train_ddpg_on_continuous_classic_control(config, cls, tmp_path):
+    """single_pendulum.yaml / single_continuous_mountain_car.yaml through TrainerDDPG: actor
+    forward -> OU sampler kernel -> env step kernel -> replay ring -> n-step DDPG update."""
+    import json
+
+    from warp_drive_b200.env_wrapper import EnvWrapper
+    from warp_drive_b200.envs.single_agent import classic_control as cc
+    from warp_drive_b200.training.trainer_ddpg import TrainerDDPG
+
+    E, T = 256, 8
+    cfg = _run_config(config, num_envs=E, train_batch_size=E * T, num_episodes=E * 2)
+    cfg["env"].update(episode_length=32, reset_pool_size=64)
+    cfg["saving"]["basedir"] = str(tmp_path)
+    env = getattr(cc, cls)(**cfg["env"])
+    wrapper = EnvWrapper(env, num_envs=E, env_backend="numba")
+    trainer = TrainerDDPG(env_wrapper=wrapper, config=cfg,
+                          policy_tag_to_agent_id_map={"shared": [0]}, results_dir="d",
+                          verbose=False)
+    assert trainer.n_step == 5 and trainer.engine.ring_capacity == T + 4
+    assert trainer.num_iters == 8
+    actor0 = [p.detach().clone() for p in trainer.actor_models["shared"].parameters()]
+    critic0 = [p.detach().clone() for p in trainer.critic_models["shared"].parameters()]
+    target0 = [p.detach().clone() for p in trainer.target_actor_models["shared"].parameters()]
+    trainer.train()
+    for before, model in ((actor0, trainer.actor_models), (critic0, trainer.critic_models),
+                          (target0, trainer.target_actor_models)):
+        after = list(model["shared"].parameters())
+        assert any(not torch.equal(a, b) for a, b in zip(before, after))
+        assert all(torch.isfinite(b).all() for b in after)
+    # the target net trails the online net (tau = 0.05), it is not a copy of it
+    assert any(not torch.equal(a, b) for a, b in zip(
+        trainer.actor_models["shared"].parameters(),
+        trainer.target_actor_models["shared"].parameters()))
+    lines = [json.loads(l) for l in open(os.path.join(trainer.save_dir, "results.json"))]
+    assert len(lines) == trainer.num_iters
+    trained = [rec["shared"] for rec in lines if "Critic loss" in rec["shared"]]
+    assert len(trained) == trainer.num_iters - 1       # iteration 0 only fills the ring
+    for rec in trained:
+        assert np.isfinite(rec["Actor loss"]) and np.isfinite(rec["Critic loss"])
+    # actions carry OU noise around the actor output and stay finite
+    dm = wrapper.cuda_data_manager
+    acts = dm.data_on_device_via_torch("sampled_actions_batch_shared")
+    assert acts.dtype == torch.float32 and torch.isfinite(acts).all() and acts.std() > 0
+    # the ring holds a time-ordered window: timesteps of one env advance by one (mod resets)
+    ckpts = sorted(os.path.basename(p) for p in glob.glob(os.path.join(trainer.save_dir, "*.state_dict")))
+    assert any(c.startswith("shared_actor_") for c in ckpts)
+    assert any(c.startswith("shared_critic_") for c in ckpts)
+    if config == "single_continuous_mountain_car":      # evaluator: True in that config
+        assert "Mean episodic reward (test)" in lines[-1]["shared"]
+    # checkpoints round-trip through load_model_checkpoint
+    ts = trainer.current_timestep["shared"]
+    paths = {"shared": {k: os.path.join(trainer.save_dir, f"shared_{k}_{ts}.state_dict")
+                        for k in ("actor", "critic")}}
+    with torch.no_grad():
+        for p in trainer.actor_models["shared"].parameters():
+            p.zero_()
+    trainer.load_model_checkpoint(paths)
+    assert any(p.abs().sum() > 0 for p in trainer.actor_models["shared"].parameters())

@@ -64,6 +64,19 @@ class _PolicyGradient:
                                  value_functions_batch=None, perform_logging=False,
                                  negative_positive_ratio=-1):
         assert timestep is not None
+        n_pos = n_neg = None
+        if negative_positive_ratio > 0:
+            # sparse-goal envs (MountainCar: done == 2 marks "goal reached",
+            # mountain_car_step_numba.py:66-70): keep every env that reached the goal in this
+            # batch and at most ratio x as many of the others (a2c.py:58-69, 196-220)
+            keep, n_pos, n_neg = self._sample_positive_negative_env_ids(
+                done_flags_batch, negative_positive_ratio)
+            if keep is not None:
+                actions_batch = actions_batch[:, keep]
+                rewards_batch = rewards_batch[:, keep]
+                done_flags_batch = done_flags_batch[:, keep]
+                action_probabilities_batch = [p[:, keep] for p in action_probabilities_batch]
+                value_functions_batch = value_functions_batch[:, keep]
         values_detached = value_functions_batch.detach()
         returns = discounted_returns(rewards_batch, done_flags_batch, values_detached,
                                      self.discount_factor_gamma)
@@ -104,7 +117,23 @@ class _PolicyGradient:
                 metrics[f"Std. of action_{k} over agents"] = a[..., k].std(dim=2).mean().item()
                 metrics[f"Std. of action_{k} over envs"] = a[..., k].std(dim=1).mean().item()
                 metrics[f"Std. of action_{k} over time"] = a[..., k].std(dim=0).mean().item()
+            if n_pos is not None:
+                metrics["Num of Positive Sampled Envs"] = n_pos
+                metrics["Num of Negative Sampled Envs"] = n_neg
         return loss, metrics
+
+    @staticmethod
+    def _sample_positive_negative_env_ids(done_flags_batch, negative_positive_ratio):
+        """(env index tensor or None when nothing is dropped, #positive, #negative kept)."""
+        positives = (done_flags_batch == 2).any(dim=0)
+        pos_ids = positives.nonzero(as_tuple=True)[0]
+        neg_ids = (~positives).nonzero(as_tuple=True)[0]
+        n_pos, total = int(pos_ids.numel()), int(done_flags_batch.shape[1])
+        n_neg = int(n_pos * negative_positive_ratio)
+        if n_pos == 0 or n_pos + n_neg >= total:
+            return None, n_pos, int(neg_ids.numel())
+        pick = torch.randperm(int(neg_ids.numel()), device=neg_ids.device)[:n_neg]
+        return torch.cat((pos_ids, neg_ids[pick])), n_pos, n_neg
 
 
 class A2C(_PolicyGradient):

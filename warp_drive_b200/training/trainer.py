@@ -283,7 +283,8 @@ class Trainer:
             self.current_timestep[policy] += self.training_batch_size
             loss, metrics = self.trainers[policy].compute_loss_and_metrics(
                 self.current_timestep[policy], actions.long(), rewards, done_flags_batch,
-                probs, values, perform_logging=logging_flag)
+                probs, values, perform_logging=logging_flag,
+                negative_positive_ratio=self.config["trainer"].get("neg_pos_env_ratio", -1))
             lr = self.lr_schedules[policy].get_param_value(self.current_timestep[policy])
             for group in self.optimizers[policy].param_groups:
                 group["lr"] = lr
