@@ -224,3 +224,32 @@ def test_train_ddpg_on_continuous_classic_control(config, cls, tmp_path):
             p.zero_()
     trainer.load_model_checkpoint(paths)
     assert any(p.abs().sum() > 0 for p in trainer.actor_models["shared"].parameters())
+
+
+def test_evaluate_episodes_counts_one_episode_per_env(tmp_path):
+    """Trainer.evaluate_episodes (trainer_base.py:794-846 of the reference): one episode per
+    env replica, reward / step sums accumulated on the device.  CartPole pays 1 per step, so
+    the two sums must agree env by env."""
+    from warp_drive_b200.env_wrapper import EnvWrapper
+    from warp_drive_b200.envs.single_agent.cartpole import CUDAClassicControlCartPoleEnv
+    from warp_drive_b200.training.trainer import Trainer
+
+    cfg = _run_config("single_cartpole", num_envs=128, train_batch_size=128 * 10,
+                      num_episodes=64)
+    cfg["env"].update(episode_length=60, reset_pool_size=16)
+    cfg["saving"]["basedir"] = str(tmp_path)
+    env = CUDAClassicControlCartPoleEnv(**cfg["env"])
+    wrapper = EnvWrapper(env, num_envs=128, env_backend="numba")
+    trainer = Trainer(env_wrapper=wrapper, config=cfg,
+                      policy_tag_to_agent_id_map={"shared": [0]}, results_dir="e",
+                      verbose=False)
+    reward_sum, step_sum = trainer.evaluate_episodes()
+    steps = step_sum["shared"].cpu().numpy()
+    rewards = reward_sum["shared"].cpu().numpy()[:, 0]
+    assert ((steps >= 1) & (steps <= 60)).all()
+    assert np.array_equal(rewards, steps.astype(np.float32))
+    assert 5 < steps.mean() < 60          # an untrained policy drops the pole early
+    # the training state is usable afterwards
+    dm = wrapper.cuda_data_manager
+    assert not dm.data_on_device_via_torch("_done_").any()
+    trainer.train()

@@ -375,6 +375,40 @@ class Trainer:
         if self.verbose:
             verbose_print("Trainer exits gracefully", self.device_id)
 
+    # ------------------------------------------------------------------ evaluation
+    def evaluate_episodes(self, **sample_params):
+        """Play one episode in every env replica with the current actor (scale=0: no
+        exploration noise; for categorical policies pass nothing) and return per-env reward /
+        step sums (trainer_base.py:794-846); accumulated on the device, no per-step host
+        transfer.  The env states are restarted afterwards."""
+        eng = self.engine
+        dm = self.cuda_envs.cuda_data_manager
+        fused, eng.fused = eng.fused, None     # generic multi-launch step while evaluating
+        dev = dm.device
+        reward_sum = {p: torch.zeros((self.num_envs, len(ids)), device=dev)
+                      for p, ids in self.policy_tag_to_agent_id_map.items()}
+        step_sum = {p: torch.zeros(self.num_envs, dtype=torch.int32, device=dev)
+                    for p in self.policies}
+        self.cuda_envs.reset_all_envs()
+        done = dm.data_on_device_via_torch("_done_")
+        with torch.no_grad():
+            for _ in range(self.cuda_envs.episode_length):
+                probs = RolloutEngine.evaluate_policies(eng, -1)
+                RolloutEngine.sample_actions(eng, probs, -1, **sample_params)
+                self.cuda_envs.step_all_envs()
+                undone = done == 0
+                rewards = dm.data_on_device_via_torch(_REWARDS)
+                for p in self.policies:
+                    r_p = rewards if eng.covers_all[p] else rewards.index_select(1, eng.ids[p])
+                    reward_sum[p] += r_p * undone[:, None]
+                    step_sum[p] += undone.to(torch.int32)
+                # done envs restart but keep their flag: one episode per env is counted
+                self.cuda_envs.reset_only_done_envs(undo_done_after_reset=False)
+        eng.fused = fused
+        self.cuda_envs.reset_all_envs()
+        eng.resync_observations()
+        return reward_sum, step_sum
+
     # ------------------------------------------------------------------ episode states
     def fetch_episode_states(self, list_of_states=None, env_id=0, include_rewards_actions=False,
                              include_probabilities=False):

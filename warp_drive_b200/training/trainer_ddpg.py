@@ -352,36 +352,6 @@ class TrainerDDPG(Trainer):
                         "Mean episodic steps (test)": float(step_sum[policy].float().mean())})
         return metrics_dict
 
-    def evaluate_episodes(self, **sample_params):
-        """Play one episode in every env replica with the current actor (scale=0: no
-        exploration noise) and return per-env reward / step sums (trainer_base.py:794-846);
-        accumulated on the device, no per-step host transfer.  Training state (ring, env
-        states) is restarted afterwards."""
-        eng = self.engine
-        dm = self.cuda_envs.cuda_data_manager
-        dev = dm.device
-        reward_sum = {p: torch.zeros((self.num_envs, len(ids)), device=dev)
-                      for p, ids in self.policy_tag_to_agent_id_map.items()}
-        step_sum = {p: torch.zeros(self.num_envs, dtype=torch.int32, device=dev)
-                    for p in self.policies}
-        self.cuda_envs.reset_all_envs()
-        done = dm.data_on_device_via_torch("_done_")
-        with torch.no_grad():
-            for _ in range(self.cuda_envs.episode_length):
-                probs = RolloutEngine.evaluate_policies(eng, -1)
-                RolloutEngine.sample_actions(eng, probs, -1, **sample_params)
-                self.cuda_envs.step_all_envs()
-                undone = done == 0
-                rewards = dm.data_on_device_via_torch(_REWARDS)
-                for p in self.policies:
-                    r_p = rewards if eng.covers_all[p] else rewards.index_select(1, eng.ids[p])
-                    reward_sum[p] += r_p * undone[:, None]
-                    step_sum[p] += undone.to(torch.int32)
-                # done envs restart but keep their flag: one episode per env is counted
-                self.cuda_envs.reset_only_done_envs(undo_done_after_reset=False)
-        self.cuda_envs.reset_all_envs()
-        return reward_sum, step_sum
-
     # ------------------------------------------------------------------ checkpoints
     def save_model_checkpoint(self, iteration=0):
         if self.device_id != 0:
