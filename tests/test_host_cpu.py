@@ -350,6 +350,38 @@ def test_param_scheduler_and_config_merge():
         assert load_run_config(name)["name"] == name
 
 
+def test_all_nine_reference_run_configs_are_present():
+    """Every run config of warp_drive/training/run_configs/ has a twin here with the same
+    schema; where /root/reference is present (build container) the values are compared too
+    (saving.basedir, a path on the reference authors' machine, excepted)."""
+    import yaml
+
+    from warp_drive_b200.training.trainer import load_run_config
+
+    names = ["default_configs", "single_acrobot", "single_cartpole",
+             "single_continuous_mountain_car", "single_mountain_car", "single_pendulum",
+             "tag_continuous", "tag_gridworld", "tag_gridworld_with_reset_pool"]
+    ref_dir = "/root/reference/warp_drive/training/run_configs"
+    for name in names:
+        ours = load_run_config(name)
+        if name != "default_configs":
+            assert {"name", "env", "trainer", "policy", "saving"} <= set(ours)
+            for pol in ours["policy"].values():
+                assert pol["algorithm"] in ("A2C", "PPO", "DDPG")
+        path = os.path.join(ref_dir, f"{name}.yaml")
+        if name == "default_configs" or not os.path.exists(path):
+            continue
+        with open(path, encoding="utf8") as fp:
+            theirs = yaml.safe_load(fp)
+        for cfg in (ours, theirs):
+            cfg["saving"].pop("basedir", None)
+        assert ours == theirs, name
+    ddpg = load_run_config("single_pendulum")
+    assert ddpg["trainer"]["n_step"] == 5 and ddpg["policy"]["shared"]["tau"] == 0.05
+    assert ddpg["policy"]["shared"]["model"]["actor"]["output_w"] == 2.0
+    assert load_run_config("single_mountain_car")["trainer"]["neg_pos_env_ratio"] == 10
+
+
 def test_forward_sm_split_cost_model():
     """RolloutEngine._forward_side_by_side splits the SMs between two policies so that the
     slower launch is as short as possible (cost in tile-times: tiles per CTA, 1.3x for the
