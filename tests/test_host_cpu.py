@@ -44,6 +44,41 @@ def test_library_is_sm100a_only(wdb_lib):
     assert archs == {"sm_100a"}, archs
 
 
+def test_kernel_resource_usage_matches_the_residency_the_design_assumes(wdb_lib):
+    """DESIGN.md 3.1 / 3.2 size the grids on: fused env kernel 96 registers x 320 threads ->
+    two CTAs per SM (register file 65536); its 1024-thread instance (BASELINE config 4) must
+    fit one CTA; the persistent MLP kernel 416 threads x 128 registers -> one CTA per SM.
+    A compiler or source change that silently breaks this shows up here, without a GPU."""
+    from warp_drive_b200 import lib as wlib
+
+    out = subprocess.run(["cuobjdump", "--dump-resource-usage", wlib.LIB_PATH],
+                         capture_output=True, text=True).stdout
+    usage = {}
+    name = None
+    for line in out.splitlines():
+        line = line.strip()
+        if line.startswith("Function "):
+            name = line[len("Function "):].rstrip(":")
+        elif line.startswith("REG:") and name:
+            usage[name] = {k: int(v) for k, v in re.findall(r"([A-Z]+):(\d+)", line)}
+    def find(*parts):
+        hits = [u for n, u in usage.items() if all(p in n for p in parts)]
+        assert hits, (parts, list(usage)[:5])
+        return hits
+
+    for u in find("tag_continuous_kernel", "Li320E"):
+        assert u["REG"] * 320 * 2 <= 65536 and u["STACK"] <= 128, u
+    for u in find("tag_continuous_kernel", "Li1024E"):
+        assert u["REG"] * 1024 <= 65536, u
+    for u in find("mlp_forward_kernel"):
+        assert u["REG"] * 416 <= 65536 and u["STACK"] <= 32, u
+    for kernel in ("cartpole_step_kernel", "mountain_car_step_kernel", "pendulum_step_kernel",
+                   "acrobot_step_kernel", "tag_gridworld_step_kernel", "sample_actions_kernel",
+                   "reset_when_done_kernel"):
+        for u in find(kernel):
+            assert u["REG"] <= 80 and u["LOCAL"] == 0, (kernel, u)
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "warp_drive_b200")
     for dirpath, _, files in os.walk(pkg):
