@@ -230,8 +230,12 @@ reset_when_done_kernel(const wdb_reset_desc *__restrict__ table, int n_arrays,
       for (long long i = begin; i < words; i += step) dst[i] = src[i];
     }
   }
-  if (blockIdx.y == 0 && threadIdx.x == 0) {
-    if (pool_rng && n_pool > 0) rng_offsets(pool_rng)[env] = pool_off + n_pool;
+  if (pool_rng && n_pool > 0) {
+    // every thread of the CTA must have read pool_off before it is advanced (a late warp
+    // reading the new offset would draw a different pool row: torn reset); the early
+    // return above is CTA-uniform, so the barrier is safe
+    __syncthreads();
+    if (blockIdx.y == 0 && threadIdx.x == 0) rng_offsets(pool_rng)[env] = pool_off + n_pool;
   }
   // undo is done by a second tiny kernel when gridDim.y > 1 (other CTAs of this env
   // still need done[env]); with gridDim.y == 1 it is safe here.

@@ -292,10 +292,14 @@ class RolloutEngine:
     def bookkeep(self, t):
         """done / rewards -> batches, running episodic sums without host syncs
         (trainer_base.py:514-601 uses nonzero()/len())."""
-        done = self._tensor("_done_")
+        raw_done = self._tensor("_done_")
         rewards = self._tensor(_REWARDS)
         if t >= 0:
-            self._tensor(f"{_DONE_FLAGS}_batch")[t].copy_(done)
+            # the batch keeps the raw flag (MountainCar writes done == 2 at the goal; the
+            # reference's neg/pos sampling tests for == 2)
+            self._tensor(f"{_DONE_FLAGS}_batch")[t].copy_(raw_done)
+        # any non-zero flag means "done" (trainer_base.py:534-601 uses done_flags.nonzero())
+        done = (raw_done > 0).to(torch.int32)
         donef = done.to(torch.float32)
         for p in self.policies:
             r_p = rewards if self.covers_all[p] else rewards.index_select(1, self.ids[p])
@@ -337,7 +341,10 @@ class RolloutEngine:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                self.step(0)
+                # an evaluation-style step: advances the envs AND the engine's current
+                # observations consistently, records nothing (a step(0) here would leave
+                # cur_obs one state behind the env for the first captured transition)
+                self.step(-1)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()

@@ -99,6 +99,11 @@ class Trainer:
         assert env_wrapper is not None and env_wrapper.env_backend != "cpu"
         assert config is not None
         assert obs_dim_corresponding_to_num_agents in ("first", "last")
+        # the rollout engine views observations as [E, N, F]; 'last' ([E, ..., N]) would be
+        # silently scrambled across agents and features
+        assert obs_dim_corresponding_to_num_agents == "first", (
+            "obs_dim_corresponding_to_num_agents='last' is not supported by the B200 rollout "
+            "engine (observations must be [num_envs, num_agents, ...])")
         assert not create_separate_placeholders_for_each_policy, (
             "separate per-policy step placeholders are not implemented in the B200 trainer")
         self.cuda_envs = env_wrapper
@@ -369,6 +374,9 @@ class Trainer:
                 # the timestep is encoded in the file name ({policy}_{timestep}.state_dict)
                 self.current_timestep[policy] = int(
                     os.path.basename(path).split(".state_dict")[0].split("_")[-1])
+        # the tensor-core rollout forward keeps its own packed bf16 copy of the weights
+        if getattr(self, "engine", None) is not None:
+            self.engine.refresh_forward_weights()
 
     def graceful_close(self):
         self.cuda_sample_controller = None
