@@ -54,6 +54,14 @@ BYTES_FUSED = 516      # sample (2 x 21 probs) + step: reads 192, writes 324
 BYTES_STEP_ONLY = 348  # step with actions in
 
 
+def workload_config(n_envs, n_agents=105):
+    """The `config` object of the JSON line -- identical for the b200 arm and the
+    --impl reference arm (both measure BASELINE.json configs[1])."""
+    return {"workload": f"tag_continuous {n_envs} envs/GPU x (5 taggers + 100 runners), "
+                        "discrete 21x21 actions, K=10 partial obs (BASELINE.json configs[1])",
+            "envs_per_gpu": n_envs, "agents": n_agents}
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -278,7 +286,7 @@ def time_e2e_host_buffers(wrapper, n_steps, warmup=3, n_copy_streams=4):
     return ms, h2d, d2h
 
 
-def cpu_baseline(sample_steps, n_procs=None):
+def cpu_baseline(sample_steps, n_procs=None, warmup=2):
     """oracle/numpy_ref.py on the host cores (bounded sample of config 2)."""
     from oracle.numpy_ref import timed_agent_steps_per_sec
     from warp_drive_b200.envs.tag_continuous import TagContinuous
@@ -294,7 +302,7 @@ def cpu_baseline(sample_steps, n_procs=None):
     cfg["episode_length"] = env.episode_length
     init = {k: np.array(dd[k]["data"]) for k in
             ("loc_x", "loc_y", "speed", "direction", "acceleration")}
-    return timed_agent_steps_per_sec(cfg, init, sample_steps, warmup=2, n_procs=n_procs)
+    return timed_agent_steps_per_sec(cfg, init, sample_steps, warmup=warmup, n_procs=n_procs)
 
 
 def c_oracle_rate(n_envs=64, n_steps=10):
@@ -344,19 +352,22 @@ def run_reference_arm(args):
         return 0
     cores = os.cpu_count() or 1
     steps = max(1, min(args.steps, 400))
-    res = cpu_baseline(steps, n_procs=cores)
+    warmup = max(3, min(args.warmup, 50))
+    res = cpu_baseline(steps, n_procs=cores, warmup=warmup)
     value = res["agent_steps_per_sec"]
     line = {
         "impl": "reference", "metric": "agent_steps_per_sec", "value": value,
-        "unit": "agent-steps/s", "n_gpus": args.gpus, "steps": steps, "warmup": 2,
+        "unit": "agent-steps/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": 1000.0 * cores * res["n_agents"] / value, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "tag_continuous 5 taggers + 100 runners, K=10 partial obs, "
-                               "one env replica per host core (bounded sample of config 2)"},
+        "config": workload_config(args.envs),
         "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": cores,
                          "kind": "port",
-                         "sample": f"{steps} env-steps x {cores} processes x 105 agents, "
-                                   "oracle/numpy_ref.py"},
+                         "sample": f"bounded sample of the workload: {steps} env-steps x {cores} "
+                                   "env replicas (one per host core, all cores busy) x 105 "
+                                   "agents after {warmup} warm-up steps, oracle/numpy_ref.py = "
+                                   "the reference's NumPy step() restated".replace(
+                                       "{warmup}", str(warmup))},
         "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
     }
@@ -538,18 +549,17 @@ def main():
                   "synchronize, CUDA events, max over ranks); >= 3 warm graph replays first",
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": f"tag_continuous {E} envs/GPU x (5 taggers + 100 runners), "
-                               "discrete 21x21 actions, K=10 partial obs, 2 policies "
-                               "fully_connected [256,256], rollout step = forward + sample "
-                               "+ step + reset + push-to-batch",
-                   "policy_forward": ("wdb_mlp_policy_forward: fused tcgen05/TMEM MLP kernel, "
-                                      "bf16 operands, fp32 accumulate" if engine.fused_forward
-                                      else f"torch/cuBLAS {args.forward_precision} GEMMs (library)"),
-                   "envs_per_gpu": E, "agents": N, "graph_steps": T,
-                   "cuda_graph": not args.no_graph,
-                   "l2": "working set per step (~110 MB obs+probs+batch slots, batch slot "
-                         "changes every step) exceeds what stays L2-resident; dominant "
-                         "kernel additionally timed with an explicit L2 flush"},
+        "config": workload_config(E, N),
+        "config_detail": {
+            "rollout_step": "2 policies fully_connected [256,256]: forward + sample + step + "
+                            "reset + push-to-batch",
+            "policy_forward": ("wdb_mlp_policy_forward: fused tcgen05/TMEM MLP kernel, "
+                               "bf16 operands, fp32 accumulate" if engine.fused_forward
+                               else f"torch/cuBLAS {args.forward_precision} GEMMs (library)"),
+            "graph_steps": T, "cuda_graph": not args.no_graph,
+            "l2": "working set per step (~110 MB obs+probs+batch slots, batch slot "
+                  "changes every step) exceeds what stays L2-resident; dominant "
+                  "kernel additionally timed with an explicit L2 flush"},
         "clocks": dict(clocks.summary(), window="timed region + 0.4 s of the same rollout "
                                                   "replayed right after (untimed)"),
         "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
