@@ -163,7 +163,13 @@ def test_engine_cuda_graph_matches_eager(fused):
     wb, eb, _ = _engine(E, T, False, fused)
     ea.rollout()
     ea.rollout()
-    eb.step(0)              # the graph path ran one eager warm-up step before capturing
+    eb.step(-1)             # the graph path ran one eager warm-up step before capturing
+    if fused:
+        # ... which must leave the engine's current observations in step with the env state
+        # (a recording step(0) as warm-up left cur_obs one state behind: ADVICE r1)
+        obs = wb.cuda_data_manager.data_on_device_via_torch("observations")
+        for p_, ids in pm.items():
+            assert torch.equal(eb.cur_obs[p_], obs[:, sorted(ids)]), p_
     eb.rollout()
     eb.rollout()
     torch.cuda.synchronize()
