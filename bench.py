@@ -48,18 +48,43 @@ ENV_CONFIG = dict(
     step_reward_for_runner=0.0, edge_hit_penalty=0.0, end_of_game_reward_for_runner=1.0,
     tagging_distance=0.02)
 MODEL_CONFIG = {"type": "fully_connected", "fc_dims": [256, 256], "model_ckpt_filepath": ""}
+# BASELINE.json configs[3]: 2000 envs x 1024 agents, multi-block-per-env.  BASELINE.json does
+# not fix the tagger / runner split or the arena: 24 taggers + 1000 runners on a 64 x 64 grid
+# (config 2's agent density, SURVEY.md section 8d "Config 4"); everything else as config 2.
+ENV_CONFIG_4 = dict(ENV_CONFIG, num_taggers=24, num_runners=1000, grid_length=64.0)
+BENCH_CONFIGS = {
+    2: {"env": ENV_CONFIG, "blocks_per_env": 1, "graph_cap": 50,
+        "label": "BASELINE.json configs[1]"},
+    4: {"env": ENV_CONFIG_4, "blocks_per_env": 4, "graph_cap": 4,
+        "label": "BASELINE.json configs[3]"},
+}
+_ACTIVE = {"config": 2, "blocks_per_env": None}
+
+
+def active_env_config():
+    return BENCH_CONFIGS[_ACTIVE["config"]]["env"]
+
+
+def active_blocks_per_env():
+    return _ACTIVE["blocks_per_env"] or BENCH_CONFIGS[_ACTIVE["config"]]["blocks_per_env"]
 
 # algorithmic bytes per agent-step (SURVEY.md section 8d / BASELINE.md section 3)
 BYTES_FUSED = 516      # sample (2 x 21 probs) + step: reads 192, writes 324
 BYTES_STEP_ONLY = 348  # step with actions in
 
 
-def workload_config(n_envs, n_agents=105):
+def workload_config(n_envs, n_agents=None):
     """The `config` object of the JSON line -- identical for the b200 arm and the
-    --impl reference arm (both measure BASELINE.json configs[1])."""
-    return {"workload": f"tag_continuous {n_envs} envs/GPU x (5 taggers + 100 runners), "
-                        "discrete 21x21 actions, K=10 partial obs (BASELINE.json configs[1])",
-            "envs_per_gpu": n_envs, "agents": n_agents}
+    --impl reference arm (both measure the same BASELINE.json config)."""
+    ec = active_env_config()
+    n_agents = n_agents or ec["num_taggers"] + ec["num_runners"]
+    out = {"workload": f"tag_continuous {n_envs} envs/GPU x ({ec['num_taggers']} taggers + "
+                       f"{ec['num_runners']} runners), discrete 21x21 actions, K=10 partial obs, "
+                       f"grid {ec['grid_length']:g} ({BENCH_CONFIGS[_ACTIVE['config']]['label']})",
+           "envs_per_gpu": n_envs, "agents": n_agents}
+    if _ACTIVE["config"] == 4:
+        out["blocks_per_env"] = active_blocks_per_env()
+    return out
 
 
 def measured_peaks():
@@ -128,8 +153,9 @@ def build_engine(n_envs, seed, graph_steps, use_graph=True, forward_dtype=None,
     from warp_drive_b200.training.rollout import RolloutEngine
     from warp_drive_b200.training.utils.data_loader import create_and_push_data_placeholders
 
-    env = TagContinuous(**ENV_CONFIG)
-    wrapper = EnvWrapper(env, num_envs=n_envs, env_backend="b200")
+    env = TagContinuous(**active_env_config())
+    wrapper = EnvWrapper(env, num_envs=n_envs, env_backend="b200",
+                         blocks_per_env=active_blocks_per_env())
     wrapper.reset_all_envs()
     policy_map = {"runner": sorted(env.runners), "tagger": sorted(env.taggers)}
     sampler = CUDASampler(wrapper.cuda_function_manager)
@@ -219,7 +245,11 @@ def time_dominant_kernel(wrapper, engine, iters=30):
                                 obs_next_tiles=engine.obs_tiles or None)
             if i >= 3:
                 ev[i - 3][1].record()
-        name, nbytes = "tag_continuous_kernel<true> (fused sample+step+push+reset)", BYTES_FUSED
+        name = ("tag_continuous_kernel<true> (fused sample+step+push+reset)"
+                if active_blocks_per_env() == 1 else
+                f"tc_wide_kernel<true> (fused sample+step+push+reset, cluster of "
+                f"{active_blocks_per_env()} CTAs per env)")
+        nbytes = BYTES_FUSED
     torch.cuda.synchronize()
     ms = sorted(a.elapsed_time(b) for a, b in ev)
     return {"kernel": name, "ms_median": ms[len(ms) // 2], "ms_min": ms[0],
@@ -291,7 +321,7 @@ def cpu_baseline(sample_steps, n_procs=None, warmup=2):
     from oracle.numpy_ref import timed_agent_steps_per_sec
     from warp_drive_b200.envs.tag_continuous import TagContinuous
 
-    env = TagContinuous(**ENV_CONFIG)
+    env = TagContinuous(**active_env_config())
     env.reset()
     dd = env.get_data_dictionary()
     cfg = {k: dd[k]["data"] for k in (
@@ -310,7 +340,7 @@ def c_oracle_rate(n_envs=64, n_steps=10):
     import oracle
     from warp_drive_b200.envs.tag_continuous import TagContinuous
 
-    env = TagContinuous(**ENV_CONFIG)
+    env = TagContinuous(**active_env_config())
     env.reset()
     dd = env.get_data_dictionary()
     N, K = env.num_agents, env.num_other_agents_observed
@@ -351,8 +381,9 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    steps = max(1, min(args.steps, 400))
-    warmup = max(3, min(args.warmup, 50))
+    # config 4: one NumPy step of a 1024-agent env takes ~1 s, so the sample is shorter
+    steps = max(1, min(args.steps, 400 if args.config == 2 else 8))
+    warmup = max(3, min(args.warmup, 50)) if args.config == 2 else 3
     res = cpu_baseline(steps, n_procs=cores, warmup=warmup)
     value = res["agent_steps_per_sec"]
     line = {
@@ -364,10 +395,9 @@ def run_reference_arm(args):
         "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": cores,
                          "kind": "port",
                          "sample": f"bounded sample of the workload: {steps} env-steps x {cores} "
-                                   "env replicas (one per host core, all cores busy) x 105 "
-                                   "agents after {warmup} warm-up steps, oracle/numpy_ref.py = "
-                                   "the reference's NumPy step() restated".replace(
-                                       "{warmup}", str(warmup))},
+                                   f"env replicas (one per host core, all cores busy) x "
+                                   f"{res['n_agents']} agents after {warmup} warm-up steps, "
+                                   "oracle/numpy_ref.py = the reference's NumPy step() restated"},
         "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
     }
@@ -382,6 +412,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=2000, help="env replicas per GPU")
+    ap.add_argument("--config", type=int, default=2, choices=sorted(BENCH_CONFIGS),
+                    help="BASELINE.json config: 2 = 2000 x 105 (the headline), 4 = 2000 x 1024 "
+                         "agents, one env per thread-block cluster")
+    ap.add_argument("--blocks-per-env", type=int, default=0,
+                    help="config 4: CTAs per env (cluster size), default 4")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--forward-precision", default="tf32", choices=["fp32", "tf32", "bf16"],
                     help="precision of the torch policy forward when --torch-forward is given")
@@ -401,6 +436,8 @@ def main():
     ap.add_argument("--cta-threads", type=int, default=0,
                     help="A/B switch: thread budget of one tag_continuous CTA (wdb_set_option)")
     args = ap.parse_args()
+    _ACTIVE["config"] = args.config
+    _ACTIVE["blocks_per_env"] = args.blocks_per_env or None
     if args.impl == "reference":
         return run_reference_arm(args)
 
@@ -423,7 +460,8 @@ def main():
     K = args.steps
     W = max(3, args.warmup)
     # the rollout is captured as CUDA graphs of T timesteps; T divides K
-    T = max(d for d in range(1, min(K, 50) + 1) if K % d == 0)
+    cap = BENCH_CONFIGS[args.config]["graph_cap"]       # batch slots held in HBM
+    T = max(d for d in range(1, min(K, cap) + 1) if K % d == 0)
     if args.forward_precision == "tf32":
         torch.backends.cuda.matmul.allow_tf32 = True
         torch.backends.cudnn.allow_tf32 = True
@@ -535,6 +573,11 @@ def main():
                 "kernel_ms_in_rollout": in_loop,
                 "algorithmic_bytes_per_agent_step": dk["bytes_per_agent_step"],
                 "peak_source": peak_src,
+                "pair_evals": {"nominal_pairs_per_launch": E * N * (N - 1),
+                               "nominal_pairs_per_s": E * N * (N - 1) / (kernel_ms * 1e-3),
+                               "note": "the reference's O(N^2) neighbour sweep evaluates every "
+                                       "ordered pair; config 4 is issue-bound on this sweep "
+                                       "(SURVEY 8d), the cluster kernel scans only an x-window"},
                 "issue": issue_roofline(dk["kernel"], kernel_ms, E, N),
                 "l2": "kernel_ms = kernel_ms_l2_flushed_standalone: CUDA events around the "
                       "launch, L2 flushed before every launch; kernel_ms_in_rollout: events "
@@ -580,7 +623,26 @@ def main():
         try:
             from oracle.ref_gpu_bench import time_reference_tag_continuous
 
-            ref_gpu = time_reference_tag_continuous(wrapper.env, E)
+            if args.config == 2:
+                ref_gpu = time_reference_tag_continuous(wrapper.env, E)
+            else:
+                # the reference's multi-block mode spins on global memory and dead-locks unless
+                # every block of every env is co-resident (architecture_validate.py:53-99), and
+                # needs 2 x [E, N, N-1] scratch (16.8 GB at E = 2000): time 64 envs x 2 blocks
+                ref_gpu = time_reference_tag_continuous(wrapper.env, 64, bpe=2)
+                if "step_kernel_us" in ref_gpu:
+                    scale = E / 64.0
+                    ref_gpu["scaled_to_envs"] = E
+                    for k in ("step_kernel_us", "step_kernel_us_min", "sample_actions_kernel_us",
+                              "reset_13_launches_us_none_done", "reset_13_launches_us_all_done",
+                              "sequence_us_reset_only_when_done", "sequence_us_reset_every_step"):
+                        ref_gpu[k + "_at_64_envs"] = ref_gpu[k]
+                        ref_gpu[k] = ref_gpu[k] * scale
+                    ref_gpu["scaling_note"] = (
+                        "measured at 64 envs x 2 blocks (128 co-resident blocks), multiplied by "
+                        f"{scale:g} to {E} envs: the reference kernel's time is linear in the "
+                        "env count once the GPU is full (64 envs x 1024 threads fill 148 SMs "
+                        "less than once, so this favours the reference)")
         except Exception as err:  # noqa: BLE001
             ref_gpu = {"unavailable": f"{type(err).__name__}: {err}"}
         if "step_kernel_us" in ref_gpu:
@@ -611,11 +673,12 @@ def main():
                                 "sample": "measured at N=1 only (rank 0)"}
     elif not args.skip_cpu_baseline:
         cores = os.cpu_count() or 1
-        res = cpu_baseline(sample_steps=150, n_procs=cores)
+        n_sample = 150 if args.config == 2 else 6
+        res = cpu_baseline(sample_steps=n_sample, n_procs=cores)
         line["cpu_baseline"] = {
             "value": res["agent_steps_per_sec"], "unit": "agent-steps/s", "cores": cores,
             "kind": "port",
-            "sample": f"150 env-steps x {cores} processes x 105 agents of the same env "
+            "sample": f"{n_sample} env-steps x {cores} processes x {N} agents of the same env "
                       "config (oracle/numpy_ref.py = reference NumPy step restated)"}
         try:
             rate, threads = c_oracle_rate()

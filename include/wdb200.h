@@ -182,6 +182,8 @@ typedef struct wdb_tc_env {          /* the arguments of wdb_tag_continuous_step
   int *done, *env_timestep;
   int episode_length;
   int *stats;
+  int blocks_per_env;                /* <= 1: env replicas packed into CTAs; > 1: one env per
+                                      * cluster of that many CTAs (as wdb_tag_continuous_step) */
 } wdb_tc_env;
 
 typedef struct wdb_tc_policy_io {    /* per policy; agents of a policy are [E, Np, ...] */

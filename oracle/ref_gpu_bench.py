@@ -28,19 +28,19 @@ def _median(xs):
     return xs[len(xs) // 2]
 
 
-def time_reference_tag_continuous(env, n_envs, iters=20, flush=None, seed=7):
+def time_reference_tag_continuous(env, n_envs, iters=20, flush=None, seed=7, bpe=1):
     """env: a reset() TagContinuous host object (product env class: only used to read the
     initial state and constants).  Returns a dict of microsecond timings or
     {"unavailable": why}."""
     N = env.num_agents
-    if not ref_cuda.available(n_envs, N, 1):
-        return {"unavailable": f"oracle/_ref/ref_E{n_envs}_N{N}_B1.fatbin not built"}
+    if not ref_cuda.available(n_envs, N, bpe):
+        return {"unavailable": f"oracle/_ref/ref_E{n_envs}_N{N}_B{bpe}.fatbin not built"}
     dev = "cuda"
     dd = env.get_data_dictionary()
     K = int(env.num_other_agents_observed)
     F = 7 * K + 1
     E = n_envs
-    ref = ref_cuda.RefModule(E, N, 1)
+    ref = ref_cuda.RefModule(E, N, bpe)
 
     def rep(a, dt):
         a = np.asarray(a, dt)
@@ -153,9 +153,9 @@ def time_reference_tag_continuous(env, n_envs, iters=20, flush=None, seed=7):
                 ts.append(a.elapsed_time(b) * 1e3)
         out[key] = _median(ts)
     out.update({
-        "kernels": f"oracle/_ref/ref_E{E}_N{N}_B1.fatbin = the reference's CUDA-C sources "
+        "kernels": f"oracle/_ref/ref_E{E}_N{N}_B{bpe}.fatbin = the reference's CUDA-C sources "
                    "compiled in place with nvcc --fatbin -arch=sm_100a, launched with the "
-                   f"reference geometry (grid {E}, block {N})",
+                   f"reference geometry (grid {E * bpe}, block {(N - 1) // bpe + 1})",
         "step_kernel_us": _median(t_step), "step_kernel_us_min": min(t_step),
         "sample_actions_kernel_us": _median(t_sample),
         "reset_13_launches_us_none_done": t_reset[0],

@@ -37,13 +37,18 @@ def _dev(d):
             for k, v in d.items()}
 
 
+# blocks_per_env passed to wdb_tag_continuous_step: 1 = env replicas packed into CTAs; tests/
+# test_gpu_wide.py re-runs the tests of this module with 2 / 4 (one env per cluster of CTAs)
+_BPE = 1
+
+
 def wdb_tc_step(L, st, cfg, actions, obs, rewards, nd=None, nid=None, stats=None):
     from warp_drive_b200 import lib as wlib
 
     E, N = st["loc_x"].shape
     p = wlib.ptr
     wlib.check(L.wdb_tag_continuous_step(
-        wlib.stream_ptr(), E, N, 1, p(st["loc_x"]), p(st["loc_y"]), p(st["speed"]),
+        wlib.stream_ptr(), E, N, _BPE, p(st["loc_x"]), p(st["loc_y"]), p(st["speed"]),
         p(st["direction"]), p(st["acceleration"]), p(cfg["agent_types"]),
         p(st["edge_hit_reward_penalty"]), float(cfg["edge_hit_penalty"]),
         float(cfg["grid_length"]), p(cfg["acceleration_actions"]), p(cfg["turn_actions"]),

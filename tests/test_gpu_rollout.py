@@ -16,6 +16,9 @@ ENV_KW = dict(num_taggers=3, num_runners=20, grid_length=10.0, episode_length=40
               edge_hit_penalty=-0.5, tagging_distance=0.08, step_reward_for_runner=0.01)
 
 
+_BPE = 1     # blocks_per_env of the wrappers built here (tests/test_gpu_wide.py re-runs with 2)
+
+
 def _setup(E, T, full_obs=False, seed=11):
     from warp_drive_b200.env_wrapper import EnvWrapper
     from warp_drive_b200.envs.tag_continuous import TagContinuous
@@ -24,7 +27,7 @@ def _setup(E, T, full_obs=False, seed=11):
 
     kw = dict(ENV_KW, use_full_observation=full_obs)
     env = TagContinuous(**kw)
-    wrapper = EnvWrapper(env, num_envs=E, env_backend="b200")
+    wrapper = EnvWrapper(env, num_envs=E, env_backend="b200", blocks_per_env=_BPE)
     wrapper.reset_all_envs()
     policy_map = {"runner": sorted(env.runners), "tagger": sorted(env.taggers)}
     sampler = CUDASampler(wrapper.cuda_function_manager)

@@ -970,9 +970,7 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
   WDB_MARK(17)  // reset done
 }
 
-int g_tc_history = 1;   // wdb_set_option("tc_history", 0/1)
 int g_tc_threads = 320; // wdb_set_option("tc_cta_threads", n): thread budget of one CTA (<= 320)
-int g_tc_force_exact = 0;  // wdb_set_option("tc_force_exact", 0/1)
 
 struct LaunchPlan {
   int epb, block, grid;
@@ -1081,7 +1079,7 @@ int fill_params(TcParams &P, int n_envs, int n_agents, float *loc_x, float *loc_
       !still_in_the_game || !nearest_neighbor_ids || !rewards || !step_rewards ||
       !num_runners || !done || !env_timestep)
     return (int)cudaErrorInvalidValue;
-  if (n_envs <= 0 || n_agents < 2 || n_agents > 1024 || num_other_agents_observed < 0)
+  if (n_envs <= 0 || n_agents < 2 || n_agents > 4096 || num_other_agents_observed < 0)
     return (int)cudaErrorInvalidValue;
   P.n_envs = n_envs; P.N = n_agents; P.K = num_other_agents_observed;
   P.episode_length = episode_length;
@@ -1103,6 +1101,11 @@ int fill_params(TcParams &P, int n_envs, int n_agents, float *loc_x, float *loc_
 
 }  // namespace
 
+namespace wdb {
+int g_tc_history = 1;      // wdb_set_option("tc_history", 0/1)
+int g_tc_force_exact = 0;  // wdb_set_option("tc_force_exact", 0/1)
+}  // namespace wdb
+
 extern int g_mlp_max_ctas;   // wdb_mlp.cu
 
 WDB_API int wdb_set_option(const char *name, int value) {
@@ -1118,6 +1121,11 @@ WDB_API int wdb_set_option(const char *name, int value) {
     if (value < 0) return (int)cudaErrorInvalidValue;
     g_mlp_max_ctas = value;
     return 0;
+  }
+  {
+    bool handled = false;
+    const int rc = tc_wide_set_option(name, value, &handled);
+    if (handled) return rc;
   }
   if (is("tc_cta_threads")) {
     if (value < 32 || value > 320) return (int)cudaErrorInvalidValue;
@@ -1140,7 +1148,10 @@ WDB_API int wdb_tag_continuous_step(
     int *num_runners, float distance_margin_for_reward, float tag_reward_for_tagger,
     float tag_penalty_for_runner, float end_of_game_reward_for_runner, int *done,
     int *env_timestep, int episode_length, int *stats) {
-  (void)blocks_per_env;  // launch geometry is chosen here; kept for call compatibility
+  // blocks_per_env == 1: whole env replicas packed into one CTA (geometry chosen here);
+  // blocks_per_env > 1: the env is spread over that many CTAs, launched as one thread-block
+  // cluster (wdb_tc_wide.cu) -- the reference's multi-block mode, env_dim_mapper.h:22-31
+  if (blocks_per_env < 1) return (int)cudaErrorInvalidValue;
   TcParams P;
   int err = fill_params(P, n_envs, n_agents, loc_x, loc_y, speed, direction, acceleration,
                         agent_types, edge_hit_reward_penalty, edge_hit_penalty, grid_length,
@@ -1156,6 +1167,8 @@ WDB_API int wdb_tag_continuous_step(
   if (err) return err;
   if (!obs || !action_indices) return (int)cudaErrorInvalidValue;
   if ((uintptr_t)action_indices & 7) return (int)cudaErrorMisalignedAddress;
+  if (blocks_per_env > 1) return tc_wide_launch(P, nullptr, blocks_per_env, as_stream(stream));
+  if (n_agents > 1024) return (int)cudaErrorInvalidValue;   // one CTA per env: <= 1024 threads
   LaunchPlan plan;
   err = plan_launch(P, nullptr, neighbor_distances && neighbor_ids_sorted_by_distance, plan);
   if (err) return err;
@@ -1215,6 +1228,12 @@ WDB_API int wdb_tag_continuous_rollout_step(void *stream, const wdb_tc_env *env,
   Q.reset_table = ro->reset_table; Q.n_reset = ro->n_reset_arrays;
   Q.obs_at_reset = ro->obs_at_reset; Q.do_reset = ro->reset_done_envs;
   if (Q.do_reset && Q.n_reset > 0 && !Q.reset_table) return (int)cudaErrorInvalidValue;
+  if (env->blocks_per_env > 1) {
+    for (int p = 0; p < Q.n_policies; p++)
+      if (Q.obs_tiles[p]) return (int)cudaErrorInvalidValue;   // tiles come from the CTA tile
+    return tc_wide_launch(P, &Q, env->blocks_per_env, as_stream(stream));
+  }
+  if (env->n_agents > 1024) return (int)cudaErrorInvalidValue;
   LaunchPlan plan;
   err = plan_launch(P, &Q, env->neighbor_distances && env->neighbor_ids_sorted_by_distance,
                     plan);

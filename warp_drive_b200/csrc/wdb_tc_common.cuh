@@ -14,12 +14,8 @@
 
 using namespace wdb;
 
-namespace {
 
-
-// tag_continuous_step_pycuda.cu:7-9
-__constant__ float kTwoPi = 6.283185308;
-__constant__ float kEpsilon = 1.0e-10;
+namespace wdb {
 
 constexpr int kMaxPolicies = 4;
 constexpr int kListLen = 16;   // sorted candidate list kept per agent (self + K+1 <= 16)
@@ -90,6 +86,19 @@ struct FusedParams {
   const float *obs_at_reset;        // [E, N, F] (for obs_next of envs that reset)
   int do_reset;
 };
+
+// launch of the cluster kernel (wdb_tc_wide.cu); `fused` may be NULL (step-only)
+int tc_wide_launch(TcParams &P, const FusedParams *fused, int blocks_per_env, cudaStream_t st);
+int tc_wide_set_option(const char *name, int value, bool *handled);
+extern int g_tc_history, g_tc_force_exact;
+
+}  // namespace wdb
+
+namespace {
+
+// tag_continuous_step_pycuda.cu:7-9
+__constant__ float kTwoPi = 6.283185308;
+__constant__ float kEpsilon = 1.0e-10;
 
 // Byte offsets of the small shared-memory arrays (must agree between the kernel and
 // plan_launch): everything before the per-warp scratch, rounded up to 16 bytes so that the

@@ -67,9 +67,12 @@ class EnvWrapper:
             "CUDAEnvironmentContext")
         assert num_envs >= 1
         self.n_envs = num_envs
-        # the library picks its own launch geometry; blocks_per_env is recorded only
-        # because env classes read it back from the managers
+        # blocks_per_env == 1: the library packs whole env replicas into CTAs (its own
+        # geometry).  blocks_per_env > 1 (the reference's multi-block mode, env_wrapper.py:
+        # 150-160): TagContinuous runs one env per thread-block CLUSTER of that many CTAs
+        # (wdb_tc_wide.cu); custom envs get the same cluster launch (custom_kernels.py).
         self.blocks_per_env = 1 if blocks_per_env is None else int(blocks_per_env)
+        assert 1 <= self.blocks_per_env <= 8, "blocks_per_env: 1..8 (portable cluster size)"
 
         self.cuda_data_manager = CUDADataManager(
             num_agents=self.n_agents, episode_length=self.episode_length,

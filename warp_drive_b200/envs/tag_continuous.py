@@ -318,7 +318,10 @@ class TagContinuous(CUDAEnvironmentContext):
         d.add_data(name="end_of_game_reward_for_runner",
                    data=self.end_of_game_reward_for_runner)
         n_warps = (N + 31) // 32
-        if 36 * N + 8 * N * n_warps > 60000 or K + 2 > 16:
+        bpe = int(getattr(getattr(self, "cuda_function_manager", None), "blocks_per_env", 1) or 1)
+        # the single-CTA kernel spills its exact-path lists to the reference's [N, N-1] scratch
+        # for large envs; the cluster kernel (blocks_per_env > 1) keeps everything on chip
+        if bpe <= 1 and (36 * N + 8 * N * n_warps > 60000 or K + 2 > 16):
             self.allocate_reference_scratch = True
         if self.allocate_reference_scratch:
             d.add_data(name="neighbor_distances",

@@ -44,6 +44,7 @@ class TcEnv(ctypes.Structure):
         ("distance_margin_for_reward", _f), ("tag_reward_for_tagger", _f),
         ("tag_penalty_for_runner", _f), ("end_of_game_reward_for_runner", _f),
         ("done", _fp), ("env_timestep", _fp), ("episode_length", _i), ("stats", _fp),
+        ("blocks_per_env", _i),
     ]
 
 

@@ -47,6 +47,7 @@ def fill_tc_env(dm, stats=None, with_scratch=False, write_observations=True):
     env.env_timestep = _p(dm.device_data("_timestep_"))
     env.episode_length = int(dm.meta_info("episode_length"))
     env.stats = _p(stats)
+    env.blocks_per_env = int(dm.meta_info("blocks_per_env"))
     if with_scratch and len(dm.get_shape("neighbor_distances")) == 3:
         env.neighbor_distances = _p(dm.device_data("neighbor_distances"))
         env.neighbor_ids_sorted_by_distance = _p(

@@ -87,7 +87,8 @@ class RolloutEngine:
                 # the fused env step itself (and by pack_obs whenever cur_obs changes outside it)
                 # (off by default: measured at config 2, the env step's extra pass costs what
                 #  the forward saves -- see DESIGN.md 3.2)
-                if use_obs_tiles and not getattr(env_wrapper.env, "use_full_observation", False):
+                if (use_obs_tiles and int(getattr(env_wrapper, "blocks_per_env", 1) or 1) == 1
+                        and not getattr(env_wrapper.env, "use_full_observation", False)):
                     self.obs_tiles = {
                         p: torch.zeros(self.fused_forward[p].tiles_bytes(
                             self.E * len(self.policy_map[p])), dtype=torch.uint8, device=dev)
@@ -113,7 +114,12 @@ class RolloutEngine:
             return False
         if self.T < 1 or self.dm.reset_target_to_pool:
             return False
-        if not getattr(env, "use_full_observation", False):
+        bpe = int(getattr(self.env_wrapper, "blocks_per_env", 1) or 1)
+        if bpe > 1:
+            # one env per thread-block cluster (wdb_tc_wide.cu): <= 512 agents per CTA
+            if -(-self.N // bpe) > 512:
+                return False
+        elif not getattr(env, "use_full_observation", False):
             # the fused step pushes the per-policy observations from its shared-memory tile
             # (same sizing rule as plan_launch in wdb_tag_continuous.cu); envs too large for
             # that (e.g. 1024 agents) take the generic multi-launch path
