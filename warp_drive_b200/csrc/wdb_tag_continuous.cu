@@ -1124,7 +1124,9 @@ WDB_API int wdb_set_option(const char *name, int value) {
   }
   {
     bool handled = false;
-    const int rc = tc_wide_set_option(name, value, &handled);
+    int rc = tc_wide_set_option(name, value, &handled);
+    if (handled) return rc;
+    rc = tc_v2_set_option(name, value, &handled);
     if (handled) return rc;
   }
   if (is("tc_cta_threads")) {
@@ -1169,6 +1171,7 @@ WDB_API int wdb_tag_continuous_step(
   if ((uintptr_t)action_indices & 7) return (int)cudaErrorMisalignedAddress;
   if (blocks_per_env > 1) return tc_wide_launch(P, nullptr, blocks_per_env, as_stream(stream));
   if (n_agents > 1024) return (int)cudaErrorInvalidValue;   // one CTA per env: <= 1024 threads
+  if (tc_v2_eligible(P, nullptr)) return tc_v2_launch(P, nullptr, as_stream(stream));
   LaunchPlan plan;
   err = plan_launch(P, nullptr, neighbor_distances && neighbor_ids_sorted_by_distance, plan);
   if (err) return err;
@@ -1234,6 +1237,7 @@ WDB_API int wdb_tag_continuous_rollout_step(void *stream, const wdb_tc_env *env,
     return tc_wide_launch(P, &Q, env->blocks_per_env, as_stream(stream));
   }
   if (env->n_agents > 1024) return (int)cudaErrorInvalidValue;
+  if (tc_v2_eligible(P, &Q)) return tc_v2_launch(P, &Q, as_stream(stream));
   LaunchPlan plan;
   err = plan_launch(P, &Q, env->neighbor_distances && env->neighbor_ids_sorted_by_distance,
                     plan);

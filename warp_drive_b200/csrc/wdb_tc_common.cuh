@@ -90,6 +90,10 @@ struct FusedParams {
 // launch of the cluster kernel (wdb_tc_wide.cu); `fused` may be NULL (step-only)
 int tc_wide_launch(TcParams &P, const FusedParams *fused, int blocks_per_env, cudaStream_t st);
 int tc_wide_set_option(const char *name, int value, bool *handled);
+// second-generation small-env kernel (wdb_tc_small_v2.cu), wdb_set_option("tc_variant", 2)
+bool tc_v2_eligible(const TcParams &P, const FusedParams *fused);
+int tc_v2_launch(TcParams &P, const FusedParams *fused, cudaStream_t st);
+int tc_v2_set_option(const char *name, int value, bool *handled);
 extern int g_tc_history, g_tc_force_exact;
 
 }  // namespace wdb

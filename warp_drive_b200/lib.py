@@ -145,6 +145,12 @@ def load():
         fn.argtypes = argtypes
     assert lib.wdb_abi_version() == 1
     _lib = lib
+    # A/B switches for whole test / bench runs: WDB_OPTIONS="tc_variant=2,tc_v2_threads=224"
+    for item in filter(None, os.environ.get("WDB_OPTIONS", "").split(",")):
+        key, _, val = item.partition("=")
+        rc = lib.wdb_set_option(key.strip().encode(), int(val))
+        if rc != 0:
+            raise RuntimeError(f"WDB_OPTIONS: wdb_set_option({key!r}, {val}) failed ({rc})")
     return lib
 
 
