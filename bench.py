@@ -55,7 +55,7 @@ ENV_CONFIG_4 = dict(ENV_CONFIG, num_taggers=24, num_runners=1000, grid_length=64
 BENCH_CONFIGS = {
     2: {"env": ENV_CONFIG, "blocks_per_env": 1, "graph_cap": 50,
         "label": "BASELINE.json configs[1]"},
-    4: {"env": ENV_CONFIG_4, "blocks_per_env": 4, "graph_cap": 4,
+    4: {"env": ENV_CONFIG_4, "blocks_per_env": 2, "graph_cap": 4,
         "label": "BASELINE.json configs[3]"},
 }
 _ACTIVE = {"config": 2, "blocks_per_env": None}
@@ -416,7 +416,7 @@ def main():
                     help="BASELINE.json config: 2 = 2000 x 105 (the headline), 4 = 2000 x 1024 "
                          "agents, one env per thread-block cluster")
     ap.add_argument("--blocks-per-env", type=int, default=0,
-                    help="config 4: CTAs per env (cluster size), default 4")
+                    help="config 4: CTAs per env (cluster size), default 2")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--forward-precision", default="tf32", choices=["fp32", "tf32", "bf16"],
                     help="precision of the torch policy forward when --torch-forward is given")

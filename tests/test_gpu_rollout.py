@@ -262,10 +262,10 @@ def test_engine_obs_tiles_matches_fp32_forward():
 
 
 def test_config4_agent_count_through_wrapper_and_engine():
-    """BASELINE config 4 territory (1024 agents per env): EnvWrapper allocates the reference's
-    global neighbour scratch by itself, the env steps through the managers, and the
-    RolloutEngine falls back to the generic multi-launch timestep (the fused step's
-    observation tile does not fit shared memory at this size)."""
+    """BASELINE config 4 territory (1024 agents per env) with blocks_per_env = 1 and the
+    first-generation single-CTA kernel forced (wdb_set_option tc_wide_single = 0): EnvWrapper
+    allocates the reference's global neighbour scratch when asked to, the env steps through
+    the managers, and the RolloutEngine runs the generic multi-launch timestep."""
     from warp_drive_b200.env_wrapper import EnvWrapper
     from warp_drive_b200.envs.tag_continuous import TagContinuous
     from warp_drive_b200.managers.function_manager import CUDASampler
@@ -273,13 +273,16 @@ def test_config4_agent_count_through_wrapper_and_engine():
     from warp_drive_b200.training.rollout import RolloutEngine
     from warp_drive_b200.training.utils.data_loader import create_and_push_data_placeholders
 
+    from warp_drive_b200 import lib as wlib
+
     kw = dict(ENV_KW, num_taggers=24, num_runners=1000, grid_length=64.0,
               num_other_agents_observed=10, tagging_distance=0.3)
     env = TagContinuous(**kw)
+    env.allocate_reference_scratch = True          # the [E, N, N-1] arrays of the reference
     E, T = 2, 4
+    wlib.check(wlib.load().wdb_set_option(b"tc_wide_single", 0))
     w = EnvWrapper(env, num_envs=E, env_backend="b200")
     w.reset_all_envs()
-    assert env.allocate_reference_scratch          # decided when the data is registered
     pm = {"runner": sorted(env.runners), "tagger": sorted(env.taggers)}
     s = CUDASampler(w.cuda_function_manager)
     create_and_push_data_placeholders(env_wrapper=w, action_sampler=s,
@@ -289,11 +292,14 @@ def test_config4_agent_count_through_wrapper_and_engine():
     torch.manual_seed(0)
     cfg = {"type": "fully_connected", "fc_dims": [32, 32], "model_ckpt_filepath": ""}
     models = {p: FullyConnected(w, cfg, p, pm).cuda().eval() for p in pm}
-    eng = RolloutEngine(w, models, pm, s, T, use_cuda_graph=False)
+    eng = RolloutEngine(w, models, pm, s, T, use_cuda_graph=False, use_fused_step=False)
     assert eng.fused is None
-    for _ in range(3):
-        eng.rollout()
-    torch.cuda.synchronize()
+    try:
+        for _ in range(3):
+            eng.rollout()
+        torch.cuda.synchronize()
+    finally:
+        wlib.load().wdb_set_option(b"tc_wide_single", 1)
     dm = w.cuda_data_manager
     x, y = dm.pull_data_from_device("loc_x"), dm.pull_data_from_device("loc_y")
     assert ((x >= 0) & (x <= 64.0) & (y >= 0) & (y <= 64.0)).all()

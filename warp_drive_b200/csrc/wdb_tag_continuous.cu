@@ -1102,6 +1102,7 @@ int fill_params(TcParams &P, int n_envs, int n_agents, float *loc_x, float *loc_
 }  // namespace
 
 namespace wdb {
+int g_tc_wide_single = 1;  // wdb_set_option("tc_wide_single", 0/1)
 int g_tc_history = 1;      // wdb_set_option("tc_history", 0/1)
 int g_tc_force_exact = 0;  // wdb_set_option("tc_force_exact", 0/1)
 }  // namespace wdb
@@ -1117,6 +1118,7 @@ WDB_API int wdb_set_option(const char *name, int value) {
   };
   if (is("tc_history")) { g_tc_history = value ? 1 : 0; return 0; }
   if (is("tc_force_exact")) { g_tc_force_exact = value ? 1 : 0; return 0; }
+  if (is("tc_wide_single")) { g_tc_wide_single = value ? 1 : 0; return 0; }
   if (is("mlp_max_ctas")) {
     if (value < 0) return (int)cudaErrorInvalidValue;
     g_mlp_max_ctas = value;
@@ -1171,6 +1173,12 @@ WDB_API int wdb_tag_continuous_step(
   if ((uintptr_t)action_indices & 7) return (int)cudaErrorMisalignedAddress;
   if (blocks_per_env > 1) return tc_wide_launch(P, nullptr, blocks_per_env, as_stream(stream));
   if (n_agents > 1024) return (int)cudaErrorInvalidValue;   // one CTA per env: <= 1024 threads
+  // envs too large for the packed kernel's shared-memory tile: the x-binned kernel with the
+  // whole env in ONE CTA (a cluster of 1); wdb_set_option("tc_wide_single", 0) keeps the
+  // first-generation single-CTA path for A/B runs
+  if (g_tc_wide_single && n_agents > 320 && !use_full_observation &&
+      num_other_agents_observed + 2 <= kListLen)
+    return tc_wide_launch(P, nullptr, 1, as_stream(stream));
   if (tc_v2_eligible(P, nullptr)) return tc_v2_launch(P, nullptr, as_stream(stream));
   LaunchPlan plan;
   err = plan_launch(P, nullptr, neighbor_distances && neighbor_ids_sorted_by_distance, plan);
@@ -1237,6 +1245,12 @@ WDB_API int wdb_tag_continuous_rollout_step(void *stream, const wdb_tc_env *env,
     return tc_wide_launch(P, &Q, env->blocks_per_env, as_stream(stream));
   }
   if (env->n_agents > 1024) return (int)cudaErrorInvalidValue;
+  if (g_tc_wide_single && env->n_agents > 320 && !env->use_full_observation &&
+      env->num_other_agents_observed + 2 <= kListLen) {
+    for (int p = 0; p < Q.n_policies; p++)
+      if (Q.obs_tiles[p]) return (int)cudaErrorInvalidValue;
+    return tc_wide_launch(P, &Q, 1, as_stream(stream));
+  }
   if (tc_v2_eligible(P, &Q)) return tc_v2_launch(P, &Q, as_stream(stream));
   LaunchPlan plan;
   err = plan_launch(P, &Q, env->neighbor_distances && env->neighbor_ids_sorted_by_distance,

@@ -94,7 +94,7 @@ int tc_wide_set_option(const char *name, int value, bool *handled);
 bool tc_v2_eligible(const TcParams &P, const FusedParams *fused);
 int tc_v2_launch(TcParams &P, const FusedParams *fused, cudaStream_t st);
 int tc_v2_set_option(const char *name, int value, bool *handled);
-extern int g_tc_history, g_tc_force_exact;
+extern int g_tc_history, g_tc_force_exact, g_tc_wide_single;
 
 }  // namespace wdb
 

@@ -48,7 +48,7 @@
 
 namespace {
 
-constexpr int kWideMaxThreads = 512;
+constexpr int kWideMaxThreads = 1024;   // one CTA may carry a whole 1024-agent env (bpe = 1)
 constexpr int kWideMaxBins = 64;
 constexpr int kWideCap = 32;     // candidates one lane may collect (kHistCap)
 
@@ -58,6 +58,8 @@ struct WideParams {
   int nbins;        // x-bins (power of two <= 64); bin `nbins` holds the dead agents
   int npad;         // sorted planes length: round_up(N, 16), all +inf behind the alive agents
   int sw;           // staging row pitch in floats (odd)
+  int fpp;          // feature planes per staging pass (7: one pass ... 2: four passes)
+  int o_idcol;      // byte offset of the id columns inside a warp's scratch (stage follows)
   int use_window;   // 0: scan every alive agent (A/B switch)
   // byte offsets into dynamic shared memory (identical in every CTA: DSMEM addressing)
   int o_pos, o_sp, o_acc, o_dir, o_alive, o_cross, o_type, o_kx, o_ky, o_sid, o_tag,
@@ -125,7 +127,7 @@ __device__ __forceinline__ int sample_row_strided(float *row, const float *src, 
 }
 
 template <bool FUSED>
-__global__ void __launch_bounds__(kWideMaxThreads, 2)
+__global__ void __launch_bounds__(kWideMaxThreads, 1)
 tc_wide_kernel(const __grid_constant__ TcParams P, const __grid_constant__ FusedParams Q,
                const __grid_constant__ WideParams W) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -155,8 +157,10 @@ tc_wide_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Fused
   float *rightmin = reinterpret_cast<float *>(smem_raw + W.o_rightmin);  // [nbins + 1]
   int *misc = reinterpret_cast<int *>(smem_raw + W.o_misc);
   float *s_tab = reinterpret_cast<float *>(smem_raw + W.o_tab);
+  // per-warp scratch: [id columns | staging rows]; the candidate list of the threshold scan
+  // overlays both from the start (it is dead before either is written)
   unsigned char *s_scr = smem_raw + W.o_scr + (size_t)warp * W.scr_warp_bytes;
-  float *stage = reinterpret_cast<float *>(smem_raw + W.o_stage + (size_t)warp * W.stage_warp_bytes);
+  float *stage = reinterpret_cast<float *>(s_scr + W.stage_warp_bytes);
   float *ex_d = reinterpret_cast<float *>(smem_raw + W.o_exact);
   int *ex_ids = reinterpret_cast<int *>(ex_d + N);
 
@@ -180,10 +184,7 @@ tc_wide_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Fused
     misc[M_LOCK] = 0;
     misc[M_STEPS] = (FUSED && Q.step_running_sum) ? Q.step_running_sum[env] : 0;
   }
-  for (int i = tid; i < N; i += blockDim.x) {
-    stype[i] = P.agent_types[i];
-    tagcnt[i] = 0;
-  }
+  for (int i = tid; i < N; i += blockDim.x) stype[i] = P.agent_types[i];
   const int n_tab = FUSED ? Q.A0 + Q.A1 : 0;
   if (FUSED)
     for (int i = tid; i < n_tab; i += blockDim.x)
@@ -382,6 +383,9 @@ tc_wide_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Fused
   } else {
     __syncthreads();
   }
+  // tag credit counters (they overlay the counting-sort table, dead from here on)
+  for (int i = tid; i < N; i += blockDim.x) tagcnt[i] = 0;
+  __syncthreads();
   const int n_alive = P.use_full_obs ? 0 : misc[M_NALIVE];
 
   // ------------------------------------------------------------------ phases 2-4 (sorted order)
@@ -599,7 +603,7 @@ tc_wide_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Fused
     // ---- exact path: the reference's literal algorithm, one suspect agent at a time per
     // warp, on the CTA's one scratch list pair (rare: a spin lock serialises the warps)
     unsigned todo = __ballot_sync(full, suspect);
-    uint16_t *idcol = reinterpret_cast<uint16_t *>(s_scr) + lane;
+    uint16_t *idcol = reinterpret_cast<uint16_t *>(s_scr + W.o_idcol) + lane;
     if (todo) {
       if (lane == 0) {
         while (atomicCAS(&misc[M_LOCK], 0, 1) != 0) __nanosleep(64);
@@ -639,53 +643,54 @@ tc_wide_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Fused
     }
 
     // -------------------------------------------------------------- phase 3: features
-    // two column passes through the per-warp staging rows: [0, 4K) = dx, dy, dspeed, dacc and
-    // [4K, 7K + 1) = ddir, type, alive, time; each pass leaves by unit-stride row stores
+    // `fpp` feature planes per pass through the per-warp staging rows (7 planes dx, dy, dspeed,
+    // dacc, ddir, type, alive of K columns each, then the time column); each pass leaves by
+    // unit-stride row stores
     const int SW = W.sw;
     float *srow = stage + lane * SW;
     int *nn = P.nearest + (long long)gi2 * K;
     // destination row(s) of this lane's agent
     float *dst_obs = (have && P.obs) ? P.obs + (long long)gi2 * F : nullptr;
     float *dst_pol = nullptr;
-    int pol2 = 0, slot2 = 0, np2 = 0;
     if (FUSED && have) {
-      pol2 = Q.agent_policy[a2]; slot2 = Q.agent_slot[a2];
+      const int pol2 = Q.agent_policy[a2], slot2 = Q.agent_slot[a2];
 #pragma unroll
       for (int p = 0; p < kMaxPolicies; p++)
-        if (p == pol2) {
-          np2 = Q.policy_size[p];
-          if (Q.obs_next[p]) dst_pol = Q.obs_next[p] + ((long long)env * np2 + slot2) * F;
-        }
+        if (p == pol2 && Q.obs_next[p])
+          dst_pol = Q.obs_next[p] + ((long long)env * Q.policy_size[p] + slot2) * F;
     }
     const float spa = ssp[a2], acca = sacc[a2], dira = sdir[a2];
     const bool unit_v = (vnorm == 1.0f);
 #pragma unroll 1
-    for (int pass = 0; pass < 2; pass++) {
-      const int c0 = pass ? 4 * K : 0;
-      const int width = pass ? 3 * K + 1 : 4 * K;
+    for (int f_lo = 0; f_lo < 7; f_lo += W.fpp) {
+      const int f_hi = min(7, f_lo + W.fpp);
+      const bool last = (f_hi == 7);
+      const int c0 = f_lo * K;
+      const int width = (f_hi - f_lo) * K + (last ? 1 : 0);
       if (alive) {
         for (int p = 0; p < K; p++) {
-          float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
-          if (p < kk) {
-            const int b = net_ok ? (int)idcol[p * kWarp] : nn[p];
-            if (pass == 0) {
-              if (net_ok) nn[p] = b;                                   // :202-211
-              const float2 pb = pos[b];
-              f0 = div_by_const_f64(pb.x - pa.x, diag, inv_diag);      // :214-250
-              f1 = div_by_const_f64(pb.y - pa.y, diag, inv_diag);
-              const float dsp = ssp[b] - spa, dac = sacc[b] - acca;
-              f2 = unit_v ? dsp : dsp / vnorm;
-              f3 = unit_v ? dac : dac / vnorm;
-            } else {
-              f0 = div_by_two_pi(sdir[b] - dira, two_pi, inv_two_pi);
-              f1 = stype[b];
-              f2 = salive[b];
-            }
+          const bool valid = p < kk;
+          int b = 0;
+          if (valid) {
+            b = net_ok ? (int)idcol[p * kWarp] : nn[p];
+            if (f_lo == 0 && net_ok) nn[p] = b;                           // :202-211
           }
-          srow[0 * K + p] = f0; srow[1 * K + p] = f1; srow[2 * K + p] = f2;
-          if (pass == 0) srow[3 * K + p] = f3;
+          float *col = srow + p;
+          for (int f = f_lo; f < f_hi; f++) {                              // :214-250
+            float v = 0.0f;
+            if (valid) {
+              if (f == 0) v = div_by_const_f64(pos[b].x - pa.x, diag, inv_diag);
+              else if (f == 1) v = div_by_const_f64(pos[b].y - pa.y, diag, inv_diag);
+              else if (f == 2) { const float d = ssp[b] - spa; v = unit_v ? d : d / vnorm; }
+              else if (f == 3) { const float d = sacc[b] - acca; v = unit_v ? d : d / vnorm; }
+              else if (f == 4) v = div_by_two_pi(sdir[b] - dira, two_pi, inv_two_pi);
+              else if (f == 5) v = stype[b];
+              else v = salive[b];
+            }
+            col[(f - f_lo) * K] = v;
+          }
         }
-        if (pass == 1) srow[3 * K] = static_cast<float>(t_env) / P.episode_length;   // :251-253
+        if (last) srow[(7 - f_lo) * K] = static_cast<float>(t_env) / P.episode_length;  // :251-253
       }
       __syncwarp();
       for (int r = 0; r < kWarp; r++) {
@@ -884,6 +889,7 @@ tc_wide_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Fused
 
 int g_tc_wide_window = 1;   // wdb_set_option("tc_wide_window", 0/1)
 int g_tc_wide_bins = 0;     // wdb_set_option("tc_wide_bins", n): 0 = auto
+int g_tc_wide_fpp = 0;      // wdb_set_option("tc_wide_fpp", n): feature planes per pass, 0 = auto
 
 inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
@@ -902,6 +908,11 @@ int tc_wide_set_option(const char *name, int value, bool *handled) {
   if (is("tc_wide_bins")) {
     if (value < 0 || value > kWideMaxBins || (value & (value - 1))) return (int)cudaErrorInvalidValue;
     g_tc_wide_bins = value;
+    return 0;
+  }
+  if (is("tc_wide_fpp")) {
+    if (value < 0 || value > 7) return (int)cudaErrorInvalidValue;
+    g_tc_wide_fpp = value;
     return 0;
   }
   *handled = false;
@@ -926,32 +937,62 @@ int tc_wide_launch(TcParams &P, const FusedParams *Qp, int blocks_per_env, cudaS
   W.nbins = nbins;
   W.npad = round_up(N, 16);
   W.use_window = g_tc_wide_window;
-  const int width = 4 * K > 3 * K + 1 ? 4 * K : 3 * K + 1;
-  int sw = width | 1;
-  if (Qp) { if (sw < Qp->A0) sw = Qp->A0 | 1; if (sw < Qp->A1) sw = Qp->A1 | 1; }
-  W.sw = sw;
   P.use_history = (g_tc_history && !P.use_full_obs && K + 2 <= kListLen) ? 1 : 0;
   P.force_exact = g_tc_force_exact;
   const int n_chunks = (N + 31) / 32, NB1 = nbins + 1;
-  int off = 0;
-  auto take = [&](int bytes) { const int o = off; off = align_up(off + bytes, 16); return o; };
-  W.o_pos = take(8 * N); W.o_sp = take(4 * N); W.o_acc = take(4 * N); W.o_dir = take(4 * N);
-  W.o_alive = take(4 * N); W.o_cross = take(N); W.o_type = take(4 * N);
-  W.o_kx = take(4 * W.npad); W.o_ky = take(4 * W.npad); W.o_sid = take(2 * W.npad);
-  W.o_tag = take(2 * N); W.o_tagcnt = take(4 * N);
-  W.o_wcount = take(2 * n_chunks * (NB1 + 1));
-  W.o_binbase = take(4 * (NB1 + 2)); W.o_leftmax = take(4 * (NB1 + 1));
-  W.o_rightmin = take(4 * (NB1 + 1)); W.o_misc = take(4 * M_COUNT);
-  W.o_tab = take(4 * (Qp ? Qp->A0 + Qp->A1 : 1));
   const int list_bytes = (kWideCap + 1) * 32 * 2, id_bytes = (kListLen - 1) * 32 * 2;
-  W.scr_warp_bytes = align_up(list_bytes > id_bytes ? list_bytes : id_bytes, 16);
-  W.o_scr = take(W.scr_warp_bytes * nw);
-  W.stage_warp_bytes = align_up(4 * 32 * sw, 16);
-  if (P.use_full_obs && !Qp) W.stage_warp_bytes = 16;
-  W.o_stage = take(W.stage_warp_bytes * nw);
-  W.o_exact = take(8 * N);
-  const size_t smem = (size_t)off;
-  if (smem > 227 * 1024) return (int)cudaErrorInvalidValue;
+  // residency target: 1024 threads per SM; the staging pass width shrinks until that many
+  // CTAs fit (the per-CTA copy of the env is what clusters pay for spreading an env out)
+  size_t smem = 0;
+  int want_ctas = 1024 / block;
+  if (want_ctas < 1) want_ctas = 1;
+  if (want_ctas > 8) want_ctas = 8;
+  static const int kFpp[4] = {7, 4, 3, 2};
+  bool fits = false;
+  for (; want_ctas >= 1 && !fits; want_ctas--) {
+    const size_t budget = (size_t)(227 * 1024) / want_ctas - 1024;
+    for (int t = 0; t < 4 && !fits; t++) {
+      const int fpp = g_tc_wide_fpp ? g_tc_wide_fpp : kFpp[t];
+      int width = 1;                       // widest pass: planes x K (+ the time column)
+      for (int f_lo = 0; f_lo < 7; f_lo += fpp) {
+        const int f_hi = f_lo + fpp < 7 ? f_lo + fpp : 7;
+        const int w = (f_hi - f_lo) * K + (f_hi == 7 ? 1 : 0);
+        if (w > width) width = w;
+      }
+      int sw = width | 1;
+      if (Qp) {       // the staging rows also hold the lane-strided CDF while sampling
+        if (sw < Qp->A0) sw = Qp->A0 | 1;
+        if (sw < Qp->A1) sw = Qp->A1 | 1;
+      }
+      W.sw = sw; W.fpp = fpp;
+      int off = 0;
+      auto take = [&](int bytes) { const int o = off; off = align_up(off + bytes, 16); return o; };
+      W.o_pos = take(8 * N); W.o_sp = take(4 * N); W.o_acc = take(4 * N); W.o_dir = take(4 * N);
+      W.o_alive = take(4 * N); W.o_cross = take(N); W.o_type = take(4 * N);
+      W.o_kx = take(4 * W.npad); W.o_ky = take(4 * W.npad); W.o_sid = take(2 * W.npad);
+      W.o_tag = take(2 * N);
+      const int wc_bytes = 2 * n_chunks * (NB1 + 1);
+      W.o_wcount = take(wc_bytes > 4 * N ? wc_bytes : 4 * N);
+      W.o_tagcnt = W.o_wcount;            // overlay: the sort table is dead when tags are counted
+      W.o_binbase = take(4 * (NB1 + 2)); W.o_leftmax = take(4 * (NB1 + 1));
+      W.o_rightmin = take(4 * (NB1 + 1)); W.o_misc = take(4 * M_COUNT);
+      W.o_tab = take(4 * (Qp ? Qp->A0 + Qp->A1 : 1));
+      W.o_idcol = 0;
+      W.stage_warp_bytes = align_up(id_bytes, 16);          // offset of the staging rows
+      int stage_bytes = 4 * 32 * sw;
+      if (P.use_full_obs && !Qp) stage_bytes = 16;
+      int region = W.stage_warp_bytes + stage_bytes;
+      if (region < list_bytes) region = list_bytes;
+      W.scr_warp_bytes = align_up(region, 16);
+      W.o_scr = take(W.scr_warp_bytes * nw);
+      W.o_stage = W.o_scr;
+      W.o_exact = take(8 * N);
+      smem = (size_t)off;
+      fits = smem <= budget;
+      if (g_tc_wide_fpp) break;
+    }
+  }
+  if (!fits) return (int)cudaErrorInvalidValue;
   if (!P.use_full_obs && !P.obs && !Qp) return (int)cudaErrorInvalidValue;
 
   FusedParams Q = {};

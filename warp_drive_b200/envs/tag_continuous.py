@@ -321,7 +321,9 @@ class TagContinuous(CUDAEnvironmentContext):
         bpe = int(getattr(getattr(self, "cuda_function_manager", None), "blocks_per_env", 1) or 1)
         # the single-CTA kernel spills its exact-path lists to the reference's [N, N-1] scratch
         # for large envs; the cluster kernel (blocks_per_env > 1) keeps everything on chip
-        if bpe <= 1 and (36 * N + 8 * N * n_warps > 60000 or K + 2 > 16):
+        # and so does the one-CTA-per-env variant of that kernel that serves N > 320
+        packed = N <= 320 or K + 2 > 16 or bool(self.use_full_observation)
+        if bpe <= 1 and packed and (36 * N + 8 * N * n_warps > 60000 or K + 2 > 16):
             self.allocate_reference_scratch = True
         if self.allocate_reference_scratch:
             d.add_data(name="neighbor_distances",

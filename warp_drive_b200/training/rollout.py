@@ -115,11 +115,14 @@ class RolloutEngine:
         if self.T < 1 or self.dm.reset_target_to_pool:
             return False
         bpe = int(getattr(self.env_wrapper, "blocks_per_env", 1) or 1)
-        if bpe > 1:
-            # one env per thread-block cluster (wdb_tc_wide.cu): <= 512 agents per CTA
-            if -(-self.N // bpe) > 512:
+        k_obs = int(getattr(env, "num_other_agents_observed", 0))
+        full = bool(getattr(env, "use_full_observation", False))
+        if bpe > 1 or (self.N > 320 and not full and k_obs + 2 <= 16):
+            # one env per thread-block cluster, or one large env per CTA (wdb_tc_wide.cu):
+            # <= 1024 agents per CTA
+            if -(-self.N // bpe) > 1024:
                 return False
-        elif not getattr(env, "use_full_observation", False):
+        elif not full:
             # the fused step pushes the per-policy observations from its shared-memory tile
             # (same sizing rule as plan_launch in wdb_tag_continuous.cu); envs too large for
             # that (e.g. 1024 agents) take the generic multi-launch path
