@@ -405,6 +405,408 @@ def run_reference_arm(args):
     return 0
 
 
+# ----------------------------------------------------------------------------- config 3
+# BASELINE.json configs[2]: "Cartpole-v1 single_agent 10000 envs, PPO, 1xB200 (small-agent
+# sampler-bound path)".  Env and policy from run_configs/single_cartpole.yaml (episode 500,
+# fully_connected [32, 32]); SURVEY.md section 8d: reset_pool_size 1000.
+CARTPOLE_CONSTS = [9.8, 0.1, 1.1, 0.5, 0.05, 10.0, 0.02, 12 * 2 * math.pi / 360, 2.4]
+BYTES_CARTPOLE = 76     # state 16 R + 16 W, obs 16 W, reward 4, action 4, probs 8, done/timestep 12
+
+
+def cartpole_c_oracle_rate(n_envs, n_steps, warmup=3):
+    """CPU arm of config 3: the C restatement of the reference's CartPole step (oracle/
+    wd_oracle.c, following cartpole_step_numba.py:6-83; the reference's own CPU physics live in
+    the third-party gym package, which is not installed -> "port") on all host cores."""
+    import oracle
+
+    L = oracle.lib()
+    rs = np.random.RandomState(0)
+    st = rs.uniform(-0.05, 0.05, (n_envs, 1, 4)).astype(np.float32)
+    done = np.zeros(n_envs, np.int32)
+    rew = np.zeros((n_envs, 1), np.float32)
+    obs = np.zeros((n_envs, 1, 4), np.float32)
+    ts = np.zeros(n_envs, np.int32)
+    acts = rs.randint(0, 2, (n_steps + warmup, n_envs, 1, 1)).astype(np.int32)
+    t0 = 0.0
+    for t in range(n_steps + warmup):
+        if t == warmup:
+            t0 = time.perf_counter()
+        L.wd_oracle_cartpole_step(n_envs, st, acts[t], done, rew, obs, *CARTPOLE_CONSTS, ts, 500)
+        d = done > 0
+        if d.any():
+            st[d] = rs.uniform(-0.05, 0.05, (int(d.sum()), 1, 4)).astype(np.float32)
+            ts[d] = 0
+            done[d] = 0
+    dt = time.perf_counter() - t0
+    return n_envs * n_steps / dt, L.wd_oracle_num_threads()
+
+
+def config3_line_config(n_envs):
+    return {"workload": f"CartPole-v1 single agent, {n_envs} envs/GPU, discrete(2), "
+                        "fully_connected [32,32] policy, reset pool 1000 "
+                        "(BASELINE.json configs[2])",
+            "envs_per_gpu": n_envs, "agents": 1}
+
+
+def run_reference_arm_config3(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    steps = max(1, min(args.steps, 2000))
+    warmup = max(3, min(args.warmup, 50))
+    rate, threads = cartpole_c_oracle_rate(args.envs3, steps, warmup)
+    line = {
+        "impl": "reference", "metric": "agent_steps_per_sec", "value": rate,
+        "unit": "agent-steps/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": 1000.0 * args.envs3 / rate, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config3_line_config(args.envs3),
+        "cpu_baseline": {"value": rate, "unit": "agent-steps/s", "cores": threads, "kind": "port",
+                         "sample": f"{steps} env-steps x {args.envs3} envs, C restatement of the "
+                                   "reference CartPole step (gym's CPU physics are third-party "
+                                   "and absent), OpenMP over all cores, random actions"},
+        "e2e": {"value": rate, "unit": "agent-steps/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def run_config3(args):
+    """One 'step' = one rollout timestep of every CartPole replica: forward -> sample -> step
+    -> bookkeeping -> done-masked reset (from the pool) -> push to batch.  The whole T-step
+    rollout is ONE launch (wdb_single_agent_rollout)."""
+    import torch
+    import torch.distributed as dist
+
+    from warp_drive_b200 import lib as wlib
+    from warp_drive_b200.env_wrapper import EnvWrapper
+    from warp_drive_b200.envs.single_agent.cartpole import CUDAClassicControlCartPoleEnv
+    from warp_drive_b200.managers.function_manager import CUDASampler
+    from warp_drive_b200.training.models.fully_connected import FullyConnected
+    from warp_drive_b200.training.rollout import RolloutEngine
+    from warp_drive_b200.training.utils.data_loader import create_and_push_data_placeholders
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    assert world == args.gpus
+    E, K, W = args.envs3, args.steps, max(3, args.warmup)
+    T = max(d for d in range(1, min(K, 100) + 1) if K % d == 0)
+    env = CUDAClassicControlCartPoleEnv(episode_length=500, env_backend="b200",
+                                        reset_pool_size=1000, seed=1234 + rank)
+    w = EnvWrapper(env, num_envs=E, env_backend="b200")
+    w.reset_all_envs()
+    pm = {"shared": [0]}
+    sampler = CUDASampler(w.cuda_function_manager)
+    create_and_push_data_placeholders(env_wrapper=w, action_sampler=sampler,
+                                      policy_tag_to_agent_id_map=pm,
+                                      training_batch_size_per_env=T)
+    sampler.init_random(1234 + rank)
+    w.init_reset_pool(seed=99 + rank)
+    torch.manual_seed(1234 + rank)
+    mcfg = {"type": "fully_connected", "fc_dims": [32, 32], "model_ckpt_filepath": ""}
+    models = {"shared": FullyConnected(w, mcfg, "shared", pm).cuda().eval()}
+    eng = RolloutEngine(w, models, pm, sampler, T, use_cuda_graph=False)
+    assert eng.sa is not None, "the whole-rollout kernel is not in use"
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, math.ceil(W / T))):
+        eng.rollout()
+    reps = args.reps if args.reps > 0 else 9
+    rep_ms = []
+    with ClockSampler(local_rank) as clocks:
+        c0 = wlib.launch_count()
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            a.record()
+            for _ in range(K // T):
+                eng.rollout()
+            b.record()
+            barrier()
+            t = torch.tensor([a.elapsed_time(b)], device="cuda", dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            rep_ms.append(float(t.item()))
+        launches = (wlib.launch_count() - c0) // reps
+        t_hold = time.perf_counter()
+        while time.perf_counter() - t_hold < 0.4:
+            for _ in range(8):
+                eng.rollout()
+            torch.cuda.synchronize()
+    elapsed_ms = sorted(rep_ms)[len(rep_ms) // 2]
+    value = world * E * K / (elapsed_ms / 1000.0)
+
+    # ---- e2e: public EnvWrapper API with host buffers, every step
+    dm = w.cuda_data_manager
+    actions_d = dm.data_on_device_via_torch("sampled_actions")
+    rs = np.random.RandomState(0)
+    host_actions = [torch.from_numpy(rs.randint(0, 2, tuple(actions_d.shape)).astype(np.int32)
+                                     ).pin_memory() for _ in range(4)]
+    host_out = {k: torch.empty(dm.data_on_device_via_torch(k).shape,
+                               dtype=dm.data_on_device_via_torch(k).dtype).pin_memory()
+                for k in ("observations", "rewards", "_done_")}
+    n_e2e = min(K, 100)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for i in range(3 + n_e2e):
+        if i == 3:
+            torch.cuda.synchronize()
+            a.record()
+        w.step_with_host_buffers(host_actions[i % 4], host_out, 1)
+        w.reset_only_done_envs()
+    b.record()
+    torch.cuda.synchronize()
+    e2e_ms = a.elapsed_time(b) / n_e2e
+    t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * E / (float(t.item()) / 1000.0)
+    h2d = actions_d.numel() * 4
+    d2h = sum(v.numel() * v.element_size() for v in host_out.values())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- the dominant (only) kernel alone: one T-step launch, L2 flushed before each
+    peaks, peak_src = measured_peaks()
+    flush = torch.zeros(128 * 1024 * 1024, dtype=torch.float32, device="cuda")
+    ts = []
+    for i in range(12):
+        flush.add_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); eng.rollout(); b.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            ts.append(a.elapsed_time(b))
+    kernel_ms = sorted(ts)[len(ts) // 2]
+    per_step_us = kernel_ms * 1e3 / T
+    achieved = BYTES_CARTPOLE * E * T / (kernel_ms * 1e-3) / 1e9
+    flops = 2.0 * (4 * 32 + 32 * 32 + 32 * 2) * E * T
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+        "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+        "kernel": f"sa_rollout_kernel (ONE launch = {T} timesteps x {E} envs: fp32 forward + "
+                  "sample + step + bookkeeping + pool reset + push)",
+        "kernel_ms": kernel_ms, "kernel_us_per_timestep": per_step_us,
+        "algorithmic_bytes_per_agent_step": BYTES_CARTPOLE,
+        "peak_source": peak_src,
+        "note": "10 000 single-agent envs move 0.76 MB per timestep: this path is bound by the "
+                "dependent per-env chain (forward 1.2 K FMA -> softmax -> sample -> float64 "
+                "physics), not by HBM; the figure of merit is launches and microseconds per "
+                "timestep (the reference: ~50 launches and >= 5 host syncs per timestep)",
+        "fp32_forward_gflops": flops / (kernel_ms * 1e-3) / 1e9,
+    }
+    line = {
+        "metric": "agent_steps_per_sec", "value": value, "unit": "agent-steps/s",
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": elapsed_ms / K,
+        "ms_per_step_reps": [m / K for m in rep_ms],
+        "timing": f"median of {reps} repetitions of the K-step region (each: barrier + "
+                  "synchronize, CUDA events, max over ranks)",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": config3_line_config(E),
+        "config_detail": {"timesteps_per_launch": T, "cuda_graph": False,
+                          "l2": "working set (state + batch slots of one rollout, "
+                                f"{E * T * 28 / 1e6:.1f} MB) is L2-resident by nature; the "
+                                "kernel is additionally timed with an explicit L2 flush"},
+        "clocks": dict(clocks.summary(), window="timed region + 0.4 s of the same rollout"),
+        "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
+                "path": "EnvWrapper.step_with_host_buffers + reset_only_done_envs, every step"},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+    }
+    if world == 1:
+        # same-box GPU anchor: the reference's own numba step kernel (cubin built from the
+        # reference sources by oracle/build_ref_numba.py), one launch = one env step only
+        try:
+            from oracle import ref_numba
+
+            ref = ref_numba.RefNumbaKernel("cartpole")
+            st = dm.data_on_device_via_torch("state").clone()
+            act = torch.zeros((E, 1, 1), dtype=torch.int32, device="cuda")
+            dn = torch.zeros(E, dtype=torch.int32, device="cuda")
+            rw = torch.zeros((E, 1), device="cuda")
+            ob = torch.zeros((E, 1, 4), device="cuda")
+            tsr = torch.zeros(E, dtype=torch.int32, device="cuda")
+            rt = []
+            for i in range(22):
+                st.copy_(dm.data_on_device_via_torch("state"))
+                tsr.zero_()
+                flush.add_(1)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                ref(E, st, act, dn, rw, ob, *CARTPOLE_CONSTS, tsr, 500)
+                b.record()
+                torch.cuda.synchronize()
+                if i >= 2:
+                    rt.append(a.elapsed_time(b) * 1e3)
+            line["ref_gpu"] = {
+                "kernel": "oracle/_ref/numba_cartpole.cubin = NumbaClassicControlCartPoleEnvStep "
+                          "compiled by numba from the reference source, launched as the "
+                          f"reference does (grid {E}, block 1)",
+                "step_kernel_us": sorted(rt)[len(rt) // 2],
+                "ours_us_per_timestep_whole_path": per_step_us,
+                "note": "the reference kernel is the env step ALONE (no forward, sampler, "
+                        "bookkeeping, reset or push); ours is the whole timestep"}
+        except Exception as err:  # noqa: BLE001
+            line["ref_gpu"] = {"unavailable": f"{type(err).__name__}: {err}"}
+        if not args.skip_cpu_baseline:
+            rate, threads = cartpole_c_oracle_rate(E, 300)
+            line["cpu_baseline"] = {
+                "value": rate, "unit": "agent-steps/s", "cores": threads, "kind": "port",
+                "sample": f"300 env-steps x {E} envs, C restatement of the reference CartPole "
+                          "step (oracle/wd_oracle.c), OpenMP over all cores"}
+    else:
+        line["cpu_baseline"] = {"value": None, "unit": "agent-steps/s", "cores": 0,
+                                "kind": "port", "sample": "measured at N=1 only (rank 0)"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+# ----------------------------------------------------------------------------- --mode train
+def run_train_mode(args):
+    """One 'step' = one rollout timestep INSIDE full training iterations: T-step rollout ->
+    A2C/PPO update of both policies (forward + backward over the [T, E, Np, F] batch, returns
+    scan kernel, Adam) -> ONE flat NCCL all-reduce (mean) of all gradients
+    (training/utils/distributed.py; reference: DDP over gloo, trainer_a2c.py:137-146).
+    At --gpus 8 with 2000 envs per GPU this is BASELINE.json configs[4] (16000 envs sharded
+    over 8 x B200, PPO + NCCL gradient all-reduce)."""
+    import copy
+
+    import torch
+    import torch.distributed as dist
+    import yaml
+
+    from warp_drive_b200.env_wrapper import EnvWrapper
+    from warp_drive_b200.envs.tag_continuous import TagContinuous
+    from warp_drive_b200.training.trainer import Trainer
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    assert world == args.gpus
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    E, T = args.envs, args.train_steps
+    K = args.steps
+    n_iters = max(1, K // T)
+    K = n_iters * T
+    with open(os.path.join(ROOT, "warp_drive_b200", "training", "run_configs",
+                           "tag_continuous.yaml"), encoding="utf8") as fp:
+        cfg = yaml.safe_load(fp)
+    cfg["env"].update(ENV_CONFIG)
+    cfg["trainer"].update(num_envs=E, train_batch_size=E * T, num_episodes=10 ** 6, seed=1234)
+    for p in cfg["policy"].values():
+        p["algorithm"] = args.algo
+        if args.algo == "PPO":
+            p["clip_param"] = 0.1
+    cfg["saving"].update(metrics_log_freq=10 ** 9, model_params_save_freq=10 ** 9,
+                         basedir="/tmp", name="bench_train", tag=f"rank{rank}")
+    env = TagContinuous(**cfg["env"])
+    wrapper = EnvWrapper(env, num_envs=E, env_backend="b200")
+    pm = {"runner": sorted(env.runners), "tagger": sorted(env.taggers)}
+    trainer = Trainer(wrapper, copy.deepcopy(cfg), pm, num_devices=world, device_id=rank,
+                      verbose=False)
+    wrapper.reset_all_envs()
+    trainer.engine.resync_observations()
+    N = wrapper.n_agents
+    ar_events = []
+    orig_ar = trainer._allreduce_gradients
+
+    def timed_allreduce():
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); orig_ar(); b.record()
+        ar_events.append((a, b))
+
+    trainer._allreduce_gradients = timed_allreduce
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def iteration(i, ev=None):
+        if ev:
+            ev[0].record()
+        trainer._generate_rollout_batch()
+        if ev:
+            ev[1].record()
+        trainer._update_model_params(i)
+        if ev:
+            ev[2].record()
+
+    for i in range(max(3, math.ceil(args.warmup / T))):
+        iteration(i)
+    ar_events.clear()
+    reps = args.reps if args.reps > 0 else 5
+    rep_ms, phases = [], []
+    with ClockSampler(local_rank) as clocks:
+        for _ in range(reps):
+            evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n_iters)]
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            a.record()
+            for i in range(n_iters):
+                iteration(1000 + i, evs[i])
+            b.record()
+            barrier()
+            t = torch.tensor([a.elapsed_time(b)], device="cuda", dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            rep_ms.append(float(t.item()))
+            phases += [(e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])) for e in evs]
+    elapsed_ms = sorted(rep_ms)[len(rep_ms) // 2]
+    value = world * E * N * K / (elapsed_ms / 1000.0)
+    ar_us = sorted(a.elapsed_time(b) * 1e3 for a, b in ar_events) if ar_events else []
+    n_grad = sum(p.numel() for p in trainer._trained_params())
+    if rank == 0:
+        roll = sorted(p[0] for p in phases)[len(phases) // 2]
+        upd = sorted(p[1] for p in phases)[len(phases) // 2]
+        it_ms = elapsed_ms / n_iters
+        line = {
+            "metric": "agent_steps_per_sec", "mode": "train", "value": value,
+            "unit": "agent-steps/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
+            "ms_per_step": elapsed_ms / K, "ms_per_step_reps": [m / K for m in rep_ms],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": dict(workload_config(E, N), mode="train",
+                                                algorithm=args.algo, rollout_steps=T),
+            "train": {
+                "iteration_ms": it_ms, "rollout_ms": roll, "update_ms": upd,
+                "allreduce_us_median": ar_us[len(ar_us) // 2] if ar_us else None,
+                "allreduce_us_max": ar_us[-1] if ar_us else None,
+                "allreduce_share_of_iteration": (ar_us[len(ar_us) // 2] / 1e3 / it_ms)
+                if ar_us else 0.0,
+                "gradient_elements": n_grad, "gradient_bytes": 4 * n_grad,
+                "collective": "one flat NCCL all-reduce (sum) of every trained parameter's "
+                              "gradient + divide by world size, per iteration; no collective "
+                              "on the rollout path (env replicas are independent)",
+                "limiter": "update (torch autograd forward + backward over the "
+                           f"[{T}, {E}, Np, 71] batches)" if upd > roll else "rollout",
+            },
+            "clocks": dict(clocks.summary(), window="timed region"),
+            "gpu_launches": None,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -412,9 +814,18 @@ def main():
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs", type=int, default=2000, help="env replicas per GPU")
-    ap.add_argument("--config", type=int, default=2, choices=sorted(BENCH_CONFIGS),
-                    help="BASELINE.json config: 2 = 2000 x 105 (the headline), 4 = 2000 x 1024 "
-                         "agents, one env per thread-block cluster")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4],
+                    help="BASELINE.json config: 2 = 2000 x 105 (the headline), 3 = CartPole x "
+                         "10000 envs (whole rollout in one launch), 4 = 2000 x 1024 agents, one "
+                         "env per thread-block cluster")
+    ap.add_argument("--envs3", type=int, default=10000, help="config 3: env replicas per GPU")
+    ap.add_argument("--mode", default="rollout", choices=["rollout", "train"],
+                    help="train: full training iterations (rollout + A2C/PPO update + the flat "
+                         "NCCL gradient all-reduce); config 2 env, 2000 envs per GPU = BASELINE "
+                         "config 5 at --gpus 8")
+    ap.add_argument("--train-steps", type=int, default=10,
+                    help="--mode train: rollout timesteps per training iteration")
+    ap.add_argument("--algo", default="PPO", choices=["A2C", "PPO"])
     ap.add_argument("--blocks-per-env", type=int, default=0,
                     help="config 4: CTAs per env (cluster size), default 2")
     ap.add_argument("--no-graph", action="store_true")
@@ -436,10 +847,14 @@ def main():
     ap.add_argument("--cta-threads", type=int, default=0,
                     help="A/B switch: thread budget of one tag_continuous CTA (wdb_set_option)")
     args = ap.parse_args()
+    if args.config == 3:
+        return run_reference_arm_config3(args) if args.impl == "reference" else run_config3(args)
     _ACTIVE["config"] = args.config
     _ACTIVE["blocks_per_env"] = args.blocks_per_env or None
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.mode == "train":
+        return run_train_mode(args)
 
     import torch
     import torch.distributed as dist
@@ -448,6 +863,11 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
+    # host side of the e2e path: this rank's process (and the pinned buffers it first-touches)
+    # on the NUMA node of its GPU
+    from warp_drive_b200.utils.numa import bind_process_to_gpu
+
+    bound_cores = bind_process_to_gpu(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -607,6 +1027,8 @@ def main():
                                                   "replayed right after (untimed)"),
         "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
+                "host_cores_bound": (f"{len(bound_cores)} cores local to GPU {local_rank}"
+                                     if bound_cores else "not bound"),
                 "path": "EnvWrapper.step_with_host_buffers: pinned host actions in, "
                         "observations/rewards/done out to pinned host memory every step "
                         f"(obs copy split over {args.copy_streams} streams), host waits per step"},

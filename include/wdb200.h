@@ -265,6 +265,49 @@ int wdb_pendulum_step(void *stream, int n_envs, float *state, const float *actio
 int wdb_acrobot_step(void *stream, int n_envs, float *state, const int *action, int *done,
                      float *reward, float *obs, int *env_timestep, int episode_length);
 
+/* ------------------------------------------ whole rollout, single-agent envs ---- */
+/* ONE launch = n_steps rollout timesteps of a discrete-action single-agent env, one thread
+ * per env replica: FullyConnected forward (fp32, weights in shared memory) -> categorical
+ * sample -> step -> bookkeeping -> done-masked reset -> push to the batch slots.  Replaces
+ * the body of TrainerBase._generate_rollout_batch (trainer_base.py:383-428) for
+ * ClassicControl{CartPole,MountainCar,Acrobot}Env: per timestep the reference issues the
+ * model forward, sample_actions, Numba...EnvStep, ~20 bookkeeping torch ops and one reset
+ * kernel per registered array.  The step physics are the same compiled functions the
+ * stand-alone step kernels call. */
+enum { WDB_SA_CARTPOLE = 0, WDB_SA_MOUNTAIN_CAR = 1, WDB_SA_ACROBOT = 2 };
+
+typedef struct wdb_sa_rollout {
+  int env_kind, n_envs, n_steps, episode_length, state_dim, use_argmax;
+  float env_params[12];              /* the scalar arguments of the env's step function, in
+                                      * the order of wdb_cartpole_step / wdb_mountain_car_step */
+  float *state;                      /* [E, state_dim] */
+  float *observations;               /* [E, F] current observation (read and updated) */
+  int *done, *env_timestep;          /* [E] */
+  float *rewards;                    /* [E] */
+  int *sampled_actions;              /* [E] */
+  int n_hidden;                      /* hidden Linear + ReLU layers (0..3), then the softmax head */
+  int dims[5];                       /* F, H1, ..., A */
+  const float *w[4], *b[4];          /* nn.Linear weights [out, in] and biases, fp32 */
+  void *rng_state;
+  const float *uniforms;             /* test hook [n_steps, E]; NULL = device RNG */
+  float *obs_batch;                  /* [n_steps, E, F] or NULL */
+  int *actions_batch;                /* [n_steps, E] or NULL */
+  float *rewards_batch;              /* [n_steps, E] or NULL */
+  int *done_batch;                   /* [n_steps, E] or NULL */
+  float *probs_batch;                /* [n_steps, E, A] or NULL (tests) */
+  float *reward_running_sum;         /* [E] or NULL */
+  int *step_running_sum;             /* [E] or NULL */
+  float *episodic_reward_sum;        /* scalar or NULL */
+  unsigned long long *episodic_step_sum, *num_completed;   /* scalars or NULL */
+  const wdb_reset_desc *reset_table; /* device table of the arrays to restore when done */
+  int n_reset_arrays;
+  void *pool_rng;                    /* RNG state of the reset pools, or NULL */
+  int reset_done_envs;
+} wdb_sa_rollout;
+
+int wdb_single_agent_rollout_supported(int n_hidden, const int *dims);
+int wdb_single_agent_rollout(void *stream, const wdb_sa_rollout *rollout);
+
 /* ------------------------------------------------------------- policy forward ---- */
 /* Fused policy/value MLP forward on the tensor cores (tcgen05 + TMEM), replacing the
  * rollout-time FullyConnected.forward (warp_drive/training/models/fully_connected.py:51-89):

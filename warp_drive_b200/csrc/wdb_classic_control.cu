@@ -16,18 +16,13 @@
 #include <math.h>
 
 #include "wdb_common.cuh"
+#include "wdb_sa_physics.cuh"
 
 namespace wdb {
 namespace {
 
 constexpr int kCcThreads = 256;
 
-// numba's `_clip(v, lo, hi)` (mountain_car_step_numba.py:5-11): two ordered tests.
-__device__ __forceinline__ double clip_f64(double v, double lo, double hi) {
-  if (v < lo) return lo;
-  if (v > hi) return hi;
-  return v;
-}
 
 // ===================================================================== MountainCar
 // NumbaClassicControlMountainCarEnvStep, mountain_car_step_numba.py:14-70.
@@ -46,20 +41,12 @@ mountain_car_step_kernel(int n_envs, float2 *__restrict__ state, const int *__re
   if (env >= n_envs) return;
   const int t = env_timestep[env] + 1;
   env_timestep[env] = t;
-  const float2 s = state[env];
-  const double pos0 = (double)s.x;
-  const double c = cos(__dmul_rn(pos0, 3.0));
-  const double push = __fma_rn((double)force, (double)(long long)(action[env] - 1),
-                               -__dmul_rn((double)gravity, c));
-  double vel = __dadd_rn(push, (double)s.y);
-  vel = clip_f64(vel, (double)(-max_speed), (double)max_speed);
-  double pos = __dadd_rn(pos0, vel);
-  pos = clip_f64(pos, (double)min_position, (double)max_position);
-  if (pos == (double)min_position && vel < 0.0) vel = 0.0;
-  const float2 n = make_float2((float)pos, (float)vel);
+  int terminated = 0;
+  const float2 n = mountain_car_physics(state[env], action[env], min_position, max_position,
+                                        max_speed, goal_position, goal_velocity, force,
+                                        gravity, &terminated);
   state[env] = n;
   obs[env] = n;
-  const bool terminated = pos >= (double)goal_position && vel >= (double)goal_velocity;
   reward[env] = -1.0f;
   if (t == episode_length) done[env] = 1;
   else if (terminated) done[env] = 2;
@@ -91,9 +78,9 @@ continuous_mountain_car_step_kernel(int n_envs, float2 *__restrict__ state,
   const double pos0 = (double)s.x;
   const double c = cos(__dmul_rn(pos0, 3.0));
   double vel = __dadd_rn(__fma_rn(c, -0.0025, (double)fp), (double)s.y);
-  vel = clip_f64(vel, (double)(-max_speed), (double)max_speed);
+  vel = sa_clip_f64(vel, (double)(-max_speed), (double)max_speed);
   double pos = __dadd_rn(pos0, vel);
-  pos = clip_f64(pos, (double)min_position, (double)max_position);
+  pos = sa_clip_f64(pos, (double)min_position, (double)max_position);
   if (pos == (double)min_position && vel < 0.0) vel = 0.0;
   const float2 n = make_float2((float)pos, (float)vel);
   state[env] = n;
@@ -134,14 +121,14 @@ pendulum_step_kernel(int n_envs, float2 *__restrict__ state, const float *__rest
   constexpr double kPi = 3.141592653589793;
   constexpr double kDt = 0.05;
   constexpr double kGain = 3 * 9.81 / (2 * 1.0);  // 3 * g / (2 * l)
-  const double u = clip_f64((double)action[env], -2.0, 2.0);
+  const double u = sa_clip_f64((double)action[env], -2.0, 2.0);
   const float2 s = state[env];
   const double th = (double)s.x, thdot = (double)s.y;
   const double an = __dsub_rn(python_mod_2pi(__dadd_rn(th, kPi)), kPi);
   const double td2 = (double)__fmul_rn(s.y, s.y);
   const double costs = __fma_rn(__dmul_rn(u, u), 0.001, __fma_rn(an, an, __dmul_rn(td2, 0.1)));
   double newthdot = __fma_rn(__fma_rn(u, 3.0, __dmul_rn((double)sinf(s.x), kGain)), kDt, thdot);
-  newthdot = clip_f64(newthdot, -8.0, 8.0);
+  newthdot = sa_clip_f64(newthdot, -8.0, 8.0);
   const double newth = __fma_rn(newthdot, kDt, th);
   state[env] = make_float2((float)newth, (float)newthdot);
   float *o = obs + (size_t)env * 3;
@@ -159,42 +146,6 @@ pendulum_step_kernel(int n_envs, float2 *__restrict__ state, const float *__rest
 // right float64 evaluation gives.  Types per numba: the state and every k / k_update array
 // are float32 (each stage is ROUNDED to float32 on store, :116-131); cos/sin of float32
 // angles are the float32 routines; everything that touches a constant is float64.
-struct Vec4 { float v[4]; };
-
-__device__ __forceinline__ Vec4 acrobot_dsdt(const Vec4 &s, double torque) {
-  constexpr double kPi = 3.141592653589793;
-  const float theta1 = s.v[0], theta2 = s.v[1], dtheta1 = s.v[2], dtheta2 = s.v[3];
-  const double c2 = (double)cosf(theta2);
-  const double s2 = (double)sinf(theta2);
-  // d1 = m1*lc1^2 + m2*(l1^2 + lc2^2 + 2*l1*lc2*cos(theta2)) + I1 + I2
-  const double d1 = ((0.25 + (1.25 + c2)) + 1.0) + 1.0;
-  // d2 = m2*(lc2^2 + l1*lc2*cos(theta2)) + I2
-  const double d2 = (0.25 + 0.5 * c2) + 1.0;
-  // phi2 = m2*lc2*g*cos(theta1 + theta2 - pi/2); theta1 + theta2 is a float32 add
-  const double phi2 = (1.0 * 0.5 * 9.8) * cos((double)__fadd_rn(theta1, theta2) - kPi / 2);
-  const double phi1 = ((-0.5 * (double)__fmul_rn(dtheta2, dtheta2)) * s2
-                       - ((double)dtheta2 * (double)dtheta1) * s2
-                       + ((1.0 * 0.5 + 1.0 * 1.0) * 9.8) * cos((double)theta1 - kPi / 2))
-                      + phi2;
-  const double ddtheta2 =
-      (torque + d2 / d1 * phi1 - (0.5 * (double)__fmul_rn(dtheta1, dtheta1)) * s2 - phi2) /
-      ((0.25 + 1.0) - d2 * d2 / d1);
-  const double ddtheta1 = -(d2 * ddtheta2 + phi1) / d1;
-  Vec4 d;
-  d.v[0] = dtheta1;
-  d.v[1] = dtheta2;
-  d.v[2] = (float)ddtheta1;
-  d.v[3] = (float)ddtheta2;
-  return d;
-}
-
-__device__ __forceinline__ double acrobot_wrap(double x, double m, double M) {
-  const double diff = M - m;
-  while (x > M) x = x - diff;
-  while (x < m) x = x + diff;
-  return x;
-}
-
 __global__ void __launch_bounds__(kCcThreads)
 acrobot_step_kernel(int n_envs, float4 *__restrict__ state, const int *__restrict__ action,
                     int *__restrict__ done, float *__restrict__ reward,
@@ -204,48 +155,13 @@ acrobot_step_kernel(int n_envs, float4 *__restrict__ state, const int *__restric
   if (env >= n_envs) return;
   const int t = env_timestep[env] + 1;
   env_timestep[env] = t;
-  constexpr double kPi = 3.141592653589793;
-  constexpr double kMaxVel1 = 12.566370614359172, kMaxVel2 = 28.274333882308138;
-  constexpr double kDt = 0.2, kDt2 = 0.1;
-  const double torque = (double)(action[env] - 1);  // AVAIL_TORQUE = [-1, 0, 1] (:6)
-  const float4 s4 = state[env];
-  Vec4 s; s.v[0] = s4.x; s.v[1] = s4.y; s.v[2] = s4.z; s.v[3] = s4.w;
-  // rk4 (:112-134)
-  const Vec4 k1 = acrobot_dsdt(s, torque);
-  Vec4 u;
-#pragma unroll
-  for (int i = 0; i < 4; i++) u.v[i] = (float)((double)s.v[i] + (double)k1.v[i] * kDt2);
-  const Vec4 k2 = acrobot_dsdt(u, torque);
-#pragma unroll
-  for (int i = 0; i < 4; i++) u.v[i] = (float)((double)s.v[i] + (double)k2.v[i] * kDt2);
-  const Vec4 k3 = acrobot_dsdt(u, torque);
-#pragma unroll
-  for (int i = 0; i < 4; i++) u.v[i] = (float)((double)s.v[i] + (double)k3.v[i] * kDt);
-  const Vec4 k4 = acrobot_dsdt(u, torque);
-  float ns[4];
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const double sum = (((double)k1.v[i] + 2.0 * (double)k2.v[i]) + 2.0 * (double)k3.v[i]) +
-                       (double)k4.v[i];
-    ns[i] = (float)((double)s.v[i] + (kDt / 6.0) * sum);
-  }
-  ns[0] = (float)acrobot_wrap((double)ns[0], -kPi, kPi);
-  ns[1] = (float)acrobot_wrap((double)ns[1], -kPi, kPi);
-  ns[2] = (float)fmin(fmax((double)ns[2], -kMaxVel1), kMaxVel1);
-  ns[3] = (float)fmin(fmax((double)ns[3], -kMaxVel2), kMaxVel2);
-  state[env] = make_float4(ns[0], ns[1], ns[2], ns[3]);
-  // _terminal (:151-153): float32 throughout
-  const float c0 = cosf(ns[0]);
-  const bool terminated = __fsub_rn(-c0, cosf(__fadd_rn(ns[1], ns[0]))) > 1.0f;
-  reward[env] = terminated ? 0.0f : -1.0f;
-  // _get_ob (:156-168)
+  float o6[6], rew;
+  int terminated = 0;
+  state[env] = acrobot_physics(state[env], action[env], o6, &rew, &terminated);
+  reward[env] = rew;
   float *o = obs + (size_t)env * 6;
-  o[0] = c0;
-  o[1] = sinf(ns[0]);
-  o[2] = cosf(ns[1]);
-  o[3] = sinf(ns[1]);
-  o[4] = ns[2];
-  o[5] = ns[3];
+#pragma unroll
+  for (int i = 0; i < 6; i++) o[i] = o6[i];
   if (t == episode_length || terminated) done[env] = 1;
 }
 

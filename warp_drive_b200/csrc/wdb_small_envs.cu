@@ -6,6 +6,7 @@
 // floor(128 / n_agents) envs per CTA (one thread per agent), CartPole is one thread per
 // env with float4 state I/O.  Both are HBM-streaming kernels.
 #include "wdb_common.cuh"
+#include "wdb_sa_physics.cuh"
 
 using namespace wdb;
 
@@ -163,29 +164,8 @@ cartpole_step_kernel(int n_envs, float4 *__restrict__ state, const int *__restri
   if (env >= n_envs) return;
   const int t = env_timestep[env] + 1;
   env_timestep[env] = t;
-  const float4 s = state[env];
-  const float x = s.x, x_dot = s.y, theta = s.z, theta_dot = s.w;
-  const float force = (action[env] > 0.5f) ? force_mag : -force_mag;
-  const float costheta = cosf(theta), sintheta = sinf(theta);
-  // Fused multiply-adds exactly where the reference binary has them (ptxas on numba's PTX,
-  // oracle/_ref/numba_cartpole.cubin): FFMA for the force sum, g*sin - cos*temp and the two
-  // position updates; DFMA for the two velocity updates; plain mul/div elsewhere.
-  const float temp = __fdiv_rn(
-      __fmaf_rn(__fmul_rn(polemass_length, __fmul_rn(theta_dot, theta_dot)), sintheta, force),
-      total_mass);
-  const float c2m = __fdiv_rn(__fmul_rn(masspole, __fmul_rn(costheta, costheta)), total_mass);
-  const float torque = __fmaf_rn(gravity, sintheta, -__fmul_rn(costheta, temp));
-  const double thetaacc =
-      __ddiv_rn((double)torque, __dmul_rn((double)length, __dsub_rn(4.0 / 3.0, (double)c2m)));
-  const double xacc = __dsub_rn(
-      (double)temp,
-      __ddiv_rn(__dmul_rn(__dmul_rn((double)polemass_length, thetaacc), (double)costheta),
-                (double)total_mass));
-  float4 n;
-  n.x = __fmaf_rn(tau, x_dot, x);
-  n.y = (float)__fma_rn((double)tau, xacc, (double)x_dot);
-  n.z = __fmaf_rn(tau, theta_dot, theta);
-  n.w = (float)__fma_rn((double)tau, thetaacc, (double)theta_dot);
+  const float4 n = cartpole_physics(state[env], action[env], gravity, masspole, total_mass,
+                                    length, polemass_length, force_mag, tau);
   state[env] = n;
   obs[env] = n;
   const bool terminated = (n.x < -x_thr) || (n.x > x_thr) || (n.z < -theta_thr) || (n.z > theta_thr);

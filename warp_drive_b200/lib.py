@@ -74,6 +74,25 @@ class TcRollout(ctypes.Structure):
     ]
 
 
+class SaRollout(ctypes.Structure):
+    """struct wdb_sa_rollout (include/wdb200.h)."""
+
+    _fields_ = [
+        ("env_kind", _i), ("n_envs", _i), ("n_steps", _i), ("episode_length", _i),
+        ("state_dim", _i), ("use_argmax", _i), ("env_params", _f * 12),
+        ("state", _fp), ("observations", _fp), ("done", _fp), ("env_timestep", _fp),
+        ("rewards", _fp), ("sampled_actions", _fp),
+        ("n_hidden", _i), ("dims", _i * 5), ("w", _fp * 4), ("b", _fp * 4),
+        ("rng_state", _fp), ("uniforms", _fp),
+        ("obs_batch", _fp), ("actions_batch", _fp), ("rewards_batch", _fp),
+        ("done_batch", _fp), ("probs_batch", _fp),
+        ("reward_running_sum", _fp), ("step_running_sum", _fp), ("episodic_reward_sum", _fp),
+        ("episodic_step_sum", _fp), ("num_completed", _fp),
+        ("reset_table", _fp), ("n_reset_arrays", _i), ("pool_rng", _fp),
+        ("reset_done_envs", _i),
+    ]
+
+
 _SIGNATURES = {
     "wdb_abi_version": (_i, []),
     "wdb_error_string": (ctypes.c_char_p, [_i]),
@@ -108,6 +127,8 @@ _SIGNATURES = {
     "wdb_mlp_pack_obs": (_i, [_vp, _vp, _ll, _i, _vp]),
     "wdb_mlp_policy_forward_tiles": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _ll, _vp, _vp, _vp]),
     "wdb_discounted_returns": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f]),
+    "wdb_single_agent_rollout_supported": (_i, [_i, ctypes.POINTER(_i)]),
+    "wdb_single_agent_rollout": (_i, [_vp, ctypes.POINTER(SaRollout)]),
     "wdb_mountain_car_step": (
         _i, [_vp, _i, _vp, _vp, _vp, _vp, _vp] + [_f] * 7 + [_vp, _i]),
     "wdb_continuous_mountain_car_step": (

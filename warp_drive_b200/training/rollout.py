@@ -73,6 +73,19 @@ class RolloutEngine:
             self.cur_obs = {p: obs.index_select(1, self.ids[p]).contiguous()
                             for p in self.policies}
 
+        # ---- whole-rollout single launch (discrete single-agent envs, small FullyConnected)
+        self.sa = None
+        if use_fused_step and self.fused is None:
+            from warp_drive_b200.training.fused_single_agent import FusedSingleAgentRollout
+
+            if (self.T >= 1 and not self.continuous
+                    and FusedSingleAgentRollout.eligible(env_wrapper, models, self.policy_map)):
+                p0 = self.policies[0]
+                self.sa = FusedSingleAgentRollout(env_wrapper, models[p0], p0, sampler)
+                self.sa.set_bookkeeping(
+                    self.reward_running_sum, self.episodic_reward_sum, self.step_running_sum,
+                    self.episodic_step_sum, self.num_completed_episodes)
+
         # ---- tensor-core forward (tcgen05 MLP kernel) for the fused path
         self.fused_forward = {}
         self.obs_tiles = {}
@@ -326,6 +339,10 @@ class RolloutEngine:
     def step(self, t, **sample_params):
         if self.fused is not None and not sample_params:
             return self.step_fused(t)
+        if self.sa is not None and self._sa_params_ok(sample_params):
+            with torch.no_grad():
+                self.sa.launch(1, t0=max(t, 0), record=t >= 0, **sample_params)
+            return None
         with torch.no_grad():
             probs = self.evaluate_policies(t)
             self.sample_actions(probs, t, **sample_params)
@@ -340,8 +357,17 @@ class RolloutEngine:
         for t in range(self.T):
             self.step(t, **sample_params)
 
+    @staticmethod
+    def _sa_params_ok(sample_params):
+        return all(k == "use_argmax" for k in sample_params)
+
     def rollout(self, **sample_params):
         """Generate one training batch (T timesteps for every env replica)."""
+        if self.sa is not None and self._sa_params_ok(sample_params):
+            # ONE launch for all T timesteps (no CUDA graph needed)
+            with torch.no_grad():
+                self.sa.launch(self.T, t0=0, record=True, **sample_params)
+            return
         if not self.use_cuda_graph or sample_params:
             self._rollout_eager(**sample_params)
             return
