@@ -346,6 +346,38 @@ int wdb_discounted_returns(void *stream, const float *rewards, const int *done,
                            const float *values, float *returns, int T, int n_envs,
                            int n_agents, float gamma);
 
+/* Fused A2C / PPO loss (a2c.py:80-130, ppo.py:82-141): ONE backward-in-time scan per (env,
+ * agent) computes the bootstrapped returns, advantages, Categorical log-prob and entropy of
+ * every head, the loss sums and the gradients of
+ *     loss = mean(-logp * adv) + vf_coeff * mean((V - R)^2) - entropy_coeff * sum_k mean(H_k)
+ * with respect to the probabilities and the values (PPO's clipped surrogate has the same
+ * gradient at ratio == 1, the reference's single-epoch case, ppo.py:127-136).
+ * sums (double[4], zeroed by the caller): sum(-logp*adv), sum((V-R)^2), sum_k sum(H_k), sum(adv). */
+typedef struct wdb_pg_loss {
+  int T, n_envs, n_agents, n_heads;
+  int n_actions[4];
+  const float *probs[4];             /* [T, E, Np, A_k] */
+  const float *values;               /* [T, E, Np] */
+  const int *actions;                /* [T, E, Np, n_heads] */
+  const float *rewards;              /* [T, E, Np] */
+  const int *done;                   /* [T, E] (non-zero = done) */
+  float gamma, vf_coeff, entropy_coeff;
+  float *grad_probs[4];              /* out, same shapes as probs (or NULL) */
+  float *grad_values;                /* out (or NULL) */
+  float *returns;                    /* out [T, E, Np] (or NULL) */
+  double *sums;                      /* out [4], accumulated atomically */
+} wdb_pg_loss;
+int wdb_pg_loss_and_grads(void *stream, const wdb_pg_loss *loss);
+
+/* Gradient-norm clipping + Adam over one flat float32 arena (torch.optim.Adam semantics, no
+ * weight decay; torch.nn.utils.clip_grad_norm_ semantics for the clip factor, which the Adam
+ * kernel reads from device memory: no host synchronisation).  Replaces the per-tensor
+ * optimizer loop of trainer_a2c.py:300-339. */
+int wdb_grad_sumsq(void *stream, const float *grads, long long n, double *out /* += */);
+int wdb_adam_step(void *stream, float *params, float *grads, float *exp_avg, float *exp_avg_sq,
+                  long long n, float lr, float beta1, float beta2, float eps, int step,
+                  float max_grad_norm /* <= 0: no clipping */, const double *grad_sumsq);
+
 #ifdef __cplusplus
 }
 #endif

@@ -93,6 +93,17 @@ class SaRollout(ctypes.Structure):
     ]
 
 
+class PgLoss(ctypes.Structure):
+    """struct wdb_pg_loss (include/wdb200.h)."""
+
+    _fields_ = [
+        ("T", _i), ("n_envs", _i), ("n_agents", _i), ("n_heads", _i), ("n_actions", _i * 4),
+        ("probs", _fp * 4), ("values", _fp), ("actions", _fp), ("rewards", _fp), ("done", _fp),
+        ("gamma", _f), ("vf_coeff", _f), ("entropy_coeff", _f),
+        ("grad_probs", _fp * 4), ("grad_values", _fp), ("returns", _fp), ("sums", _fp),
+    ]
+
+
 _SIGNATURES = {
     "wdb_abi_version": (_i, []),
     "wdb_error_string": (ctypes.c_char_p, [_i]),
@@ -127,6 +138,9 @@ _SIGNATURES = {
     "wdb_mlp_pack_obs": (_i, [_vp, _vp, _ll, _i, _vp]),
     "wdb_mlp_policy_forward_tiles": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _ll, _vp, _vp, _vp]),
     "wdb_discounted_returns": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f]),
+    "wdb_pg_loss_and_grads": (_i, [_vp, ctypes.POINTER(PgLoss)]),
+    "wdb_grad_sumsq": (_i, [_vp, _vp, _ll, _vp]),
+    "wdb_adam_step": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _i, _f, _vp]),
     "wdb_single_agent_rollout_supported": (_i, [_i, ctypes.POINTER(_i)]),
     "wdb_single_agent_rollout": (_i, [_vp, ctypes.POINTER(SaRollout)]),
     "wdb_mountain_car_step": (

@@ -51,6 +51,11 @@ class _PolicyGradient:
         self.vf_loss_coeff_schedule = ParamScheduler(vf_loss_coeff)
         self.entropy_coeff_schedule = ParamScheduler(entropy_coeff)
         self.clip_param = clip_param
+        # CUDA: returns / advantages / log-prob / entropy / loss AND the gradient with respect
+        # to the model outputs in one kernel (fused_loss.py); the torch expression below stays
+        # as the float32 reference the GPU tests compare against (and for the normalised /
+        # env-subsampled variants)
+        self.use_fused_loss = True
 
     @staticmethod
     def _normalize(x):
@@ -77,6 +82,11 @@ class _PolicyGradient:
                 done_flags_batch = done_flags_batch[:, keep]
                 action_probabilities_batch = [p[:, keep] for p in action_probabilities_batch]
                 value_functions_batch = value_functions_batch[:, keep]
+        if (self.use_fused_loss and value_functions_batch.is_cuda and n_pos is None
+                and not self.normalize_return and not self.normalize_advantage):
+            return self._fused_loss_and_metrics(
+                timestep, actions_batch, rewards_batch, done_flags_batch,
+                action_probabilities_batch, value_functions_batch, perform_logging)
         values_detached = value_functions_batch.detach()
         returns = discounted_returns(rewards_batch, done_flags_batch, values_detached,
                                      self.discount_factor_gamma)
@@ -120,6 +130,45 @@ class _PolicyGradient:
             if n_pos is not None:
                 metrics["Num of Positive Sampled Envs"] = n_pos
                 metrics["Num of Negative Sampled Envs"] = n_neg
+        return loss, metrics
+
+    def _fused_loss_and_metrics(self, timestep, actions_batch, rewards_batch, done_flags_batch,
+                                action_probabilities_batch, value_functions_batch,
+                                perform_logging):
+        from warp_drive_b200.training.algorithms.fused_loss import fused_pg_loss
+
+        vf_c = self.vf_loss_coeff_schedule.get_param_value(timestep)
+        ent_c = self.entropy_coeff_schedule.get_param_value(timestep)
+        loss, parts, returns = fused_pg_loss(
+            value_functions_batch, list(action_probabilities_batch), actions_batch,
+            rewards_batch, done_flags_batch, self.discount_factor_gamma, vf_c, ent_c,
+            ppo=self.clip_param is not None, want_returns=perform_logging)
+        metrics = {}
+        if perform_logging:
+            values = value_functions_batch.detach()
+            advantages = returns - values
+            var_expl = 1 - advantages.var() / (returns.var() + _EPSILON)
+            policy_loss, vf_loss, mean_entropy = (float(x) for x in parts)
+            metrics = {
+                "VF loss coefficient": vf_c, "Entropy coefficient": ent_c,
+                "Total loss": loss.item(), "Policy loss": policy_loss,
+                "Value function loss": vf_loss,
+                "Mean rewards": rewards_batch.mean().item(),
+                "Max. rewards": rewards_batch.max().item(),
+                "Min. rewards": rewards_batch.min().item(),
+                "Mean value function": values.mean().item(),
+                "Mean advantages": advantages.mean().item(),
+                "Mean (norm.) advantages": advantages.mean().item(),
+                "Mean (discounted) returns": returns.mean().item(),
+                "Mean normalized returns": returns.mean().item(),
+                "Mean entropy": mean_entropy,
+                "Variance explained by the value function": max(-1.0, var_expl.item()),
+            }
+            a = actions_batch.float()
+            for k in range(a.shape[-1]):
+                metrics[f"Std. of action_{k} over agents"] = a[..., k].std(dim=2).mean().item()
+                metrics[f"Std. of action_{k} over envs"] = a[..., k].std(dim=1).mean().item()
+                metrics[f"Std. of action_{k} over time"] = a[..., k].std(dim=0).mean().item()
         return loss, metrics
 
     @staticmethod

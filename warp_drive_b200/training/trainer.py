@@ -174,6 +174,17 @@ class Trainer:
         self.load_model_checkpoint()
         for policy in self.policies:
             self.models[policy].cuda()
+        # ONE flat float32 arena for the parameters and one for the gradients of every trained
+        # policy: Adam / clipping run as flat kernels (utils/flat_adam.py) and the multi-GPU
+        # gradient all-reduce is a single in-place NCCL call on `_arena_grads`
+        from warp_drive_b200.training.utils.flat_adam import FlatAdam
+
+        total = sum(FlatAdam.numel(self.models[p].parameters()) for p in self.policies)
+        dev = next(self.models[self.policies[0]].parameters()).device
+        self._arena_params = torch.empty(total, dtype=torch.float32, device=dev)
+        self._arena_grads = torch.zeros(total, dtype=torch.float32, device=dev)
+        self._arena_off = 0
+        for policy in self.policies:
             self._initialize_optimizer(policy)
         for policy in self.policies_to_train:
             self._initialize_policy_algorithm(policy)
@@ -209,7 +220,14 @@ class Trainer:
     def _initialize_optimizer(self, policy):
         self.lr_schedules[policy] = ParamScheduler(self._get_config(["policy", policy, "lr"]))
         lr = self.lr_schedules[policy].get_param_value(self.current_timestep[policy])
-        self.optimizers[policy] = torch.optim.Adam(self.models[policy].parameters(), lr=lr)
+        from warp_drive_b200.training.utils.flat_adam import FlatAdam
+
+        n = FlatAdam.numel(self.models[policy].parameters())
+        lo = self._arena_off
+        self._arena_off += n
+        self.optimizers[policy] = FlatAdam(
+            self.models[policy].parameters(), lr=lr,
+            arena=(self._arena_params[lo:lo + n], self._arena_grads[lo:lo + n]))
 
     def _initialize_policy_algorithm(self, policy):
         c = self._get_config(["policy", policy])
@@ -235,11 +253,12 @@ class Trainer:
                 dist.broadcast(p.data, src=0)
 
     def _allreduce_gradients(self):
-        """ONE flat NCCL all-reduce (mean) over the gradients of every trained policy."""
-        from warp_drive_b200.training.utils.distributed import flat_allreduce_mean_
+        """ONE NCCL all-reduce (mean) over the gradients of every policy, in place on the flat
+        gradient arena (every .grad is a view into it: no packing, no copies back)."""
+        import torch.distributed as dist
 
-        grads = [p.grad for p in self._trained_params() if p.grad is not None]
-        self._flat_grad = flat_allreduce_mean_(grads, self.num_devices, self._flat_grad)
+        dist.all_reduce(self._arena_grads, op=dist.ReduceOp.SUM)
+        self._arena_grads.div_(self.num_devices)
 
     # ------------------------------------------------------------------ training loop
     def train(self):
@@ -303,10 +322,9 @@ class Trainer:
             if logging_flag:
                 grad_norm = float(sum(p.grad.norm(2) for p in self.models[policy].parameters()
                                       if p.grad is not None))
-            if self.clip_grad_norm[policy]:
-                nn.utils.clip_grad_norm_(self.models[policy].parameters(),
-                                         self.max_grad_norm[policy])
-            self.optimizers[policy].step()
+            # clip_grad_norm_ + Adam as two flat kernels, clip factor stays on the device
+            self.optimizers[policy].step(
+                max_grad_norm=self.max_grad_norm[policy] if self.clip_grad_norm[policy] else None)
             if logging_flag:
                 n_done = int(self.engine.num_completed_episodes)
                 metrics.update({
