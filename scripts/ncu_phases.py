@@ -9,6 +9,11 @@ import io
 import subprocess
 import sys
 
+PHASES_V2 = [(0, 60, "sample_row_regs (register CDF + mask search)"), (60, 232, "prologue + sampling"),
+             (232, 280, "kinematics"), (280, 530, "selection (history scan, sort, verify, exact)"),
+             (530, 560, "kk / ids store + bookkeeping loads"), (560, 600, "rewards"),
+             (600, 650, "finalize rewards / done / pushes"), (650, 700, "feature chunks"),
+             (700, 770, "chunk copy-out"), (770, 100000, "reset")]
 PHASES = [(0, 560, "inlined helpers (scan, sort network, division, CDF)"),
           (560, 650, "prologue loads"), (650, 722, "sampling + kinematics"),
           (722, 790, "obs setup / bookkeeping loads"),
@@ -46,8 +51,12 @@ def main():
         s, n = val(r, "# Samples"), val(r, "Instructions Executed")
         tot_s += s
         tot_i += n
-        key = cur if cur != "wdb_tag_continuous.cu" else next(
-            name for a, b, name in PHASES if a <= ln < b)
+        if cur == "wdb_tag_continuous.cu":
+            key = next(name for a, b, name in PHASES if a <= ln < b)
+        elif cur == "wdb_tc_small_v2.cu":
+            key = "v2: " + next(name for a, b, name in PHASES_V2 if a <= ln < b)
+        else:
+            key = cur
         agg[key]["smp"] += s
         agg[key]["inst"] += n
         for st in stalls:

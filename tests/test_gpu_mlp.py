@@ -88,3 +88,77 @@ def test_fused_mlp_from_tiles_equals_fp32_path(F, H, A0, A1, rows):
     torch.cuda.synchronize()
     for a, b in zip(outs[0], outs[1]):
         assert torch.equal(a, b)
+
+
+def test_bf16_forward_gap_on_config2_shapes():
+    """How far the bf16-operand rollout forward is from the float32 forward the update
+    recomputes: on config-2 shapes (71 -> 256 -> 256 -> 21 / 21) with default
+    and with 'trained-scale' (3x) weights and observations drawn like the env's (|x| <= 1,
+    mostly small): max |p_bf16 - p_fp32| <= 5e-3, mean KL(p_fp32 || p_bf16) <= 1e-5, and the
+    PPO ratio exp(logp_fp32 - logp_bf16) of sampled actions stays within 1 +- 2e-2 (the PPO
+    clip is 0.1)."""
+    import json
+    import os
+
+    from warp_drive_b200.training.models.fused_forward import FusedPolicyForward
+
+    rows, F, H, A = 2000 * 100, 71, 256, 21
+    out = {}
+    for scale in (1.0, 3.0):
+        torch.manual_seed(11)
+        model = _Model(F, H, A, A).cuda()
+        for p in model.policy_head.parameters():
+            p.data.mul_(scale)
+        fwd = FusedPolicyForward(model)
+        g = torch.Generator(device="cuda").manual_seed(5)
+        obs = (torch.rand(rows, F, device="cuda", generator=g) * 2 - 1) * \
+            torch.rand(rows, 1, device="cuda", generator=g)
+        p0 = torch.empty((rows, A), device="cuda")
+        p1 = torch.empty((rows, A), device="cuda")
+        fwd(obs, p0, p1, None)
+        with torch.no_grad():
+            (q0, q1), _ = model(obs)
+        err = max((p0 - q0).abs().max().item(), (p1 - q1).abs().max().item())
+        kl = 0.5 * ((q0 * (q0.clamp_min(1e-30) / p0.clamp_min(1e-30)).log()).sum(-1).mean().item()
+                    + (q1 * (q1.clamp_min(1e-30) / p1.clamp_min(1e-30)).log()).sum(-1).mean().item())
+        a0 = torch.multinomial(p0, 1, generator=g)
+        ratio = (q0.gather(1, a0) / p0.gather(1, a0))
+        out[f"head_scale_{scale:g}"] = {"max_abs_prob_err": err, "mean_kl": kl,
+                                        "ppo_ratio_min": ratio.min().item(),
+                                        "ppo_ratio_max": ratio.max().item()}
+        assert err <= 5e-3, (scale, err)
+        assert kl <= 1e-5, (scale, kl)
+        assert 0.98 <= ratio.min().item() and ratio.max().item() <= 1.02, (scale, out)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(root, "gpurun_out", "mlp_bf16_gap.json"), "w") as fp:
+        json.dump(out, fp, indent=1)
+
+
+def test_single_head_policy_on_the_tensor_cores():
+    """A1 = 0: gridworld / classic-control policies with one action head."""
+    from warp_drive_b200.training.models.fused_forward import FusedPolicyForward
+
+    class _One(_Model):
+        def __init__(self, F, H, A0):
+            super().__init__(F, H, A0, 1)
+            self.output_dims = [A0]
+            self.policy_head = torch.nn.ModuleList([torch.nn.Linear(H, A0)])
+
+    for F, H, A0, rows in [(21, 32, 5, 250), (4, 32, 2, 10000), (6, 64, 3, 777)]:
+        torch.manual_seed(F + H)
+        model = _One(F, H, A0).cuda()
+        from warp_drive_b200.utils.spaces import Box
+
+        model.observation_space = Box(-1.0, 1.0, shape=(F,))
+        assert FusedPolicyForward.supported(model)
+        fwd = FusedPolicyForward(model)
+        obs = torch.randn(rows, F, device="cuda")
+        p0 = torch.full((rows, A0), -1.0, device="cuda")
+        v = torch.full((rows,), -1.0, device="cuda")
+        fwd(obs, p0, None, v)
+        with torch.no_grad():
+            (q0,), qv = model(obs)
+        assert (p0.sum(-1) - 1).abs().max() < 1e-4
+        assert (p0 - q0).abs().max().item() < 2e-2
+        assert ((v - qv).abs() / (1 + qv.abs())).max().item() < 5e-2

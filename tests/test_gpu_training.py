@@ -87,6 +87,23 @@ def test_train_tag_continuous_fused_rollouts(tmp_path):
                                      include_rewards_actions=True)
     assert states["loc_x"].shape[1] == 12 and states["loc_x"].shape[0] >= 2
     assert np.isfinite(states["loc_x"]).all()
+    # the device-side episode log (one pull at the end) returns exactly what the reference-
+    # shaped per-step host pulls return
+    names = ["loc_x", "loc_y", "speed", "still_in_the_game", "observations"]
+    t2.cuda_sample_controller.init_random(77)
+    dev = t2.fetch_episode_states(names, env_id=3, include_rewards_actions=True,
+                                  include_probabilities=True)
+    t2.cuda_sample_controller.init_random(77)
+    host = t2._fetch_episode_states_host_pull(names, env_id=3, include_rewards_actions=True,
+                                              include_probabilities=True)
+    assert set(dev) == set(host)
+    for k in names + ["sampled_actions", "rewards"]:
+        assert dev[k].shape == host[k].shape, (k, dev[k].shape, host[k].shape)
+        assert np.array_equal(dev[k], host[k], equal_nan=True), k
+    assert len(dev["probabilities"]) == len(host["probabilities"])
+    for pa, pb in zip(dev["probabilities"], host["probabilities"]):
+        for x, y in zip(pa, pb):
+            assert np.array_equal(x, y)
     trainer.graceful_close()
 
 

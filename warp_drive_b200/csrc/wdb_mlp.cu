@@ -504,7 +504,7 @@ mlp_forward_kernel(const unsigned char *__restrict__ blob, const void *__restric
       if (tma_ok) {
         if (tid == 0) {                                    // its completion is awaited before the
           tma_store(g0, smem_addr(s_p0), n0);              // staging buffer is written again
-          tma_store(g1, smem_addr(s_p1), n1);
+          if (n1) tma_store(g1, smem_addr(s_p1), n1);      // (single-head policies: A1 == 0)
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       } else {
@@ -642,7 +642,9 @@ size_t mlp_smem_bytes(const MlpHeader &hd) {
 }
 
 bool mlp_shape_ok(int F, int H, int A0, int A1) {
-  return F >= 1 && F <= 256 && H >= 16 && H <= 256 && (H % 32) == 0 && A0 >= 1 && A1 >= 1 &&
+  // A1 == 0: a single-head policy (gridworld, classic control); the second output part then
+  // carries only the value column
+  return F >= 1 && F <= 256 && H >= 16 && H <= 256 && (H % 32) == 0 && A0 >= 1 && A1 >= 0 &&
          A0 <= 32 && A1 + 1 <= 32;
 }
 
@@ -670,8 +672,9 @@ WDB_API int wdb_mlp_pack_weights(void *stream, void *blob, const float *w1, cons
                                  const float *bh0, const float *wh1, const float *bh1,
                                  const float *wv, const float *bv, int F, int H, int A0,
                                  int A1) {
-  if (!blob || !w1 || !b1 || !w2 || !b2 || !wh0 || !bh0 || !wh1 || !bh1 || !wv || !bv)
+  if (!blob || !w1 || !b1 || !w2 || !b2 || !wh0 || !bh0 || !wv || !bv)
     return (int)cudaErrorInvalidValue;
+  if (A1 > 0 && (!wh1 || !bh1)) return (int)cudaErrorInvalidValue;
   if (!mlp_shape_ok(F, H, A0, A1)) return (int)cudaErrorInvalidValue;
   const MlpHeader hd = make_header(F, H, A0, A1);
   cudaStream_t st = as_stream(stream);
@@ -684,7 +687,8 @@ WDB_API int wdb_mlp_pack_weights(void *stream, void *blob, const float *w1, cons
   pack_matrix_kernel<<<(H * H + T - 1) / T, T, 0, st>>>(w2, H, H, H, H, bf(hd.off_w2));
   // W3 = [head0; head1; value] stacked along N (zero padded to N3 rows by the memset)
   pack_rows_kernel<<<(A0 * H + T - 1) / T, T, 0, st>>>(wh0, A0, H, 0, H, bf(hd.off_w3));
-  pack_rows_kernel<<<(A1 * H + T - 1) / T, T, 0, st>>>(wh1, A1, H, A0, H, bf(hd.off_w3));
+  if (A1 > 0)
+    pack_rows_kernel<<<(A1 * H + T - 1) / T, T, 0, st>>>(wh1, A1, H, A0, H, bf(hd.off_w3));
   pack_rows_kernel<<<(H + T - 1) / T, T, 0, st>>>(wv, 1, H, A0 + A1, H, bf(hd.off_w3));
   g_launch_count += 5;
   pack_misc_kernel<<<(max(H, hd.N3) + T - 1) / T, T, 0, st>>>(hd, b, b1, b2, bh0, bh1, bv);
@@ -697,7 +701,8 @@ template <bool TILES>
 int launch_forward(void *stream, const void *blob, int F, int H, int A0, int A1,
                    const void *input, long long rows, float *probs0, float *probs1,
                    float *values) {
-  if (!blob || !input || !probs0 || !probs1 || rows <= 0) return (int)cudaErrorInvalidValue;
+  if (!blob || !input || !probs0 || (A1 > 0 && !probs1) || rows <= 0)
+    return (int)cudaErrorInvalidValue;
   if (!mlp_shape_ok(F, H, A0, A1)) return (int)cudaErrorInvalidValue;
   if (TILES && (reinterpret_cast<uintptr_t>(input) & 15)) return (int)cudaErrorInvalidValue;
   const MlpHeader hd = make_header(F, H, A0, A1);

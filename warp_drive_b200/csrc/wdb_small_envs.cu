@@ -23,8 +23,9 @@ tag_gridworld_step_kernel(int n_envs, int N, int epb, int *__restrict__ loc_x,
                           float tag_reward_for_tagger, float tag_penalty_for_runner,
                           float step_cost_for_tagger, int use_full_observation, int B,
                           int *__restrict__ env_timestep, int episode_length,
-                          const int *__restrict__ index_to_action) {
-  extern __shared__ int s_mem[];
+                          const int *__restrict__ index_to_action, int tile_floats,
+                          int tile_pad) {
+  extern __shared__ __align__(16) int s_mem[];
   int *s_x = s_mem;                 // [epb*N]
   int *s_y = s_x + epb * N;         // [epb*N]
   int *s_tagged = s_y + epb * N;    // [epb]
@@ -78,26 +79,59 @@ tag_gridworld_step_kernel(int n_envs, int N, int epb, int *__restrict__ loc_x,
   }
 
   const float fB = static_cast<float>(B);
+  const int envs_here = min(epb, n_envs - blockIdx.x * epb);
   if (use_full_observation) {
     // :25-51.  Every row r of an env is [x_0..x_{N-1}]/B, [y_*]/B, [is_runner_*],
-    // onehot(r), t/T.  The CTA's envs are contiguous in obs, so the whole tile is
-    // written with unit-stride 4-byte stores.
+    // onehot(r), t/T.
     const int F = 4 * N + 1;
-    const int envs_here = min(epb, n_envs - blockIdx.x * epb);
     float *o = obs + (long long)blockIdx.x * epb * N * F;
     const int total = envs_here * N * F;
-    for (int i = tid; i < total; i += blockDim.x) {
-      const int e = i / (N * F);
-      const int rem = i - e * (N * F);
-      const int row = rem / F;
-      const int col = rem - row * F;
-      float v;
-      if (col < N) v = s_x[e * N + col] / fB;
-      else if (col < 2 * N) v = s_y[e * N + col - N] / fB;
-      else if (col < 3 * N) v = (col - 2 * N == N - 1) ? 1.0f : 0.0f;
-      else if (col < 4 * N) v = (col - 3 * N == row) ? 1.0f : 0.0f;
-      else v = s_t[e] / static_cast<float>(episode_length);
-      o[i] = v;
+    if (tile_floats > 0) {
+      // staged: each agent thread assembles ITS row in shared memory from per-env float
+      // planes (one int->float division per agent, no index arithmetic per element), then the
+      // CTA's tile -- contiguous in `obs` -- leaves as 16-byte vectors
+      float *s_fx = reinterpret_cast<float *>(s_move + 10);     // [epb*N] x / B
+      float *s_fy = s_fx + epb * N;                              // [epb*N] y / B
+      float *tile = s_fy + epb * N + tile_pad;                   // 16-byte aligned
+      if (active) {
+        s_fx[le * N + a] = x / fB;
+        s_fy[le * N + a] = y / fB;
+      }
+      __syncthreads();
+      if (active) {
+        float *row = tile + (le * N + a) * F;
+        const float *fx = s_fx + le * N, *fy = s_fy + le * N;
+        for (int j = 0; j < N; j++) {
+          row[j] = fx[j];
+          row[N + j] = fy[j];
+          row[2 * N + j] = (j == N - 1) ? 1.0f : 0.0f;
+          row[3 * N + j] = (j == a) ? 1.0f : 0.0f;
+        }
+        row[4 * N] = s_t[le] / static_cast<float>(episode_length);
+      }
+      __syncthreads();
+      if ((((uintptr_t)o) & 15) == 0 && (total & 3) == 0) {
+        const float4 *src = reinterpret_cast<const float4 *>(tile);
+        float4 *dst = reinterpret_cast<float4 *>(o);
+        for (int i = tid; i < total / 4; i += blockDim.x) dst[i] = src[i];
+      } else {
+        for (int i = tid; i < total; i += blockDim.x) o[i] = tile[i];
+      }
+    } else {
+      // large envs (the tile does not fit shared memory): unit-stride element stores
+      for (int i = tid; i < total; i += blockDim.x) {
+        const int e = i / (N * F);
+        const int rem = i - e * (N * F);
+        const int row = rem / F;
+        const int col = rem - row * F;
+        float v;
+        if (col < N) v = s_x[e * N + col] / fB;
+        else if (col < 2 * N) v = s_y[e * N + col - N] / fB;
+        else if (col < 3 * N) v = (col - 2 * N == N - 1) ? 1.0f : 0.0f;
+        else if (col < 4 * N) v = (col - 3 * N == row) ? 1.0f : 0.0f;
+        else v = s_t[e] / static_cast<float>(episode_length);
+        o[i] = v;
+      }
     }
   } else {
     // :52-109 partial observation: 6 floats per agent
@@ -135,15 +169,41 @@ WDB_API int wdb_tag_gridworld_step(void *stream, int n_envs, int n_agents, int *
   if (!loc_x || !loc_y || !actions || !done || !rewards || !obs || !env_timestep ||
       !index_to_action || n_envs <= 0 || n_agents < 2 || n_agents > 1024)
     return (int)cudaErrorInvalidValue;
-  const int epb = n_agents >= kGwThreads ? 1 : kGwThreads / n_agents;
+  int epb = n_agents >= kGwThreads ? 1 : kGwThreads / n_agents;
+  // full observations are staged in a shared-memory tile that leaves as 16-byte vectors:
+  // keep the CTA's tile (epb * N * (4N + 1) floats) a multiple of 16 bytes where possible
+  const int F = 4 * n_agents + 1;
+  if (use_full_observation && epb >= 4 && ((epb * n_agents * F) & 3) != 0) epb &= ~3;
   const int block = max(32, round_up(epb * n_agents, 32));
   const int grid = (n_envs + epb - 1) / epb;
-  const size_t smem = sizeof(int) * (size_t)(2 * epb * n_agents + 3 * epb + 10);
+  const int n_int = 2 * epb * n_agents + 3 * epb + 10;
+  size_t smem = sizeof(int) * (size_t)n_int;
+  int tile_floats = 0, tile_pad = 0;
+  if (use_full_observation) {
+    const size_t planes = 2ull * epb * n_agents;
+    const size_t head = (size_t)n_int + planes;
+    tile_pad = (int)((4 - (head & 3)) & 3);
+    const size_t tile = (size_t)epb * n_agents * F;
+    if ((head + tile_pad + tile) * 4 <= 96 * 1024) {
+      tile_floats = (int)tile;
+      smem = (head + tile_pad + tile) * 4;
+      static size_t configured = 0;
+      if (smem > 48 * 1024 && smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(tag_gridworld_step_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = smem;
+      }
+    } else {
+      tile_pad = 0;
+    }
+  }
   tag_gridworld_step_kernel<<<grid, block, smem, as_stream(stream)>>>(
       n_envs, n_agents, epb, loc_x, loc_y, actions, done, rewards, obs, wall_hit_penalty,
       tag_reward_for_tagger, tag_penalty_for_runner, step_cost_for_tagger,
       use_full_observation, world_boundary, env_timestep, episode_length,
-      index_to_action);
+      index_to_action, tile_floats, tile_pad);
   return finish_launch();
 }
 

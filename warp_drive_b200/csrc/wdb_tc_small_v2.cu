@@ -13,30 +13,41 @@
 //     probability tile, no CDF rows in shared memory;
 //   * the reward / tag phase runs BEFORE the observations are assembled, so the barrier pair
 //     around the observation store collapses into the chunk loop;
-//   * observations are assembled COOPERATIVELY, `chunk_rows` rows at a time: a warp handles
-//     32 / K rows x K neighbours per pass (94 % of the lanes busy whatever the number of dead
-//     agents), the chunk leaves by TMA bulk stores while the next chunk is assembled.
+//   * observations leave through a tile of `chunk_rows` rows that is filled and stored (TMA
+//     bulk stores) in passes: each thread assembles its agent's row in the pass the row
+//     belongs to.
+//   * ALIVE-FIRST working order: runners that were tagged out (about a third of the agents,
+//     averaged over a config-2 episode) only need an all-zero observation row.  After the
+//     kinematics every env's alive agents take the first slots of the env's thread range
+//     (shared-memory counters), the key planes are written compacted, and from the k-nearest
+//     selection on thread j of an env works on the agent in slot j: warps that hold only
+//     dead agents skip the whole selection, and the candidate scan covers the alive agents
+//     only.  Keys carry slot numbers; they are mapped back to agent ids after the
+//     verification (the exact path keeps the reference's id order).
 // 46-70 KB per CTA -> 3 (EPB = 3) or 4 (EPB = 2) CTAs per SM = 28-30 warps.
 // Selected by wdb_set_option("tc_variant", 2); every parity test runs against both variants.
 #include "wdb_tc_common.cuh"
 
 namespace {
 
+constexpr int kHistIds = kListLen - 2;   // neighbour ids kept per agent for the threshold
+
 struct V2Params {
   int chunk_rows;        // rows of the observation tile (multiple of 4)
   int tile_bytes;
 };
 
-// Register CDF + the reference's binary search on bit masks (A <= 32).
-__device__ __forceinline__ int sample_row_regs(const float *__restrict__ src, int A, float u) {
-  float v[32];
+// Register CDF + the reference's binary search on bit masks (A <= W, W = 24 or 32).
+template <int W>
+__device__ __forceinline__ int sample_row_regs_w(const float *__restrict__ src, int A, float u) {
+  float v[W];
 #pragma unroll
-  for (int i = 0; i < 32; i++) v[i] = i < A ? src[i] : 0.0f;
+  for (int i = 0; i < W; i++) v[i] = i < A ? src[i] : 0.0f;
 #pragma unroll
-  for (int i = 1; i < 32; i++) v[i] = v[i] + v[i - 1];     // same left-to-right additions
+  for (int i = 1; i < W; i++) v[i] = v[i] + v[i - 1];     // same left-to-right additions
   uint32_t lt = 0, eq = 0;
 #pragma unroll
-  for (int i = 0; i < 32; i++) {
+  for (int i = 0; i < W; i++) {
     if (i < A) {
       if (v[i] < u) lt |= 1u << i;
       if (fabsf(v[i] - u) < 1.0e-8f) eq |= 1u << i;
@@ -49,6 +60,9 @@ __device__ __forceinline__ int sample_row_regs(const float *__restrict__ src, in
     if ((lt >> mid) & 1u) left = mid + 1; else right = mid - 1;
   }
   return left > A - 1 ? A - 1 : left;
+}
+__device__ __forceinline__ int sample_row_regs(const float *__restrict__ src, int A, float u) {
+  return A <= 24 ? sample_row_regs_w<24>(src, A, u) : sample_row_regs_w<32>(src, A, u);
 }
 
 template <bool FUSED, int MAXT, int MINB>
@@ -81,12 +95,13 @@ tc_small_v2_kernel(const __grid_constant__ TcParams P, const __grid_constant__ F
   int *s_rowbase = s_ntag + 4;    // [N] (unused here, keeps tc_small_bytes' layout)
   int *s_rowstride = s_rowbase + N;
   unsigned char *s_scr = smem_raw + tc_small_bytes(epb, N);
-  // v2 extras behind the per-warp scratch: tile row -> (env slot << 7 | agent), per-agent
-  // neighbour count (255 = agent is out of the game), then the observation chunk tile
+  // v2 extras behind the per-warp scratch: tile row -> (env slot << 7 | agent), working slot
+  // -> agent id, last step's neighbour ids per agent, then the observation chunk tile
   uint16_t *s_rho = reinterpret_cast<uint16_t *>(s_scr + (size_t)nwarps * P.scr_warp_bytes);
-  unsigned char *s_kk = reinterpret_cast<unsigned char *>(s_rho + ((EN + 7) & ~7));
-  float *s_tile = reinterpret_cast<float *>(
-      reinterpret_cast<unsigned char *>(s_kk) + ((EN + 15) & ~15));
+  unsigned char *s_perm = reinterpret_cast<unsigned char *>(s_rho + ((EN + 7) & ~7));
+  unsigned char *s_hist = s_perm + ((EN + 15) & ~15);          // [EN][kHistIds]
+  int *s_ndead = reinterpret_cast<int *>(s_hist + (((size_t)EN * kHistIds + 15) & ~(size_t)15));
+  float *s_tile = reinterpret_cast<float *>(s_ndead + ((epb + 3) & ~3));
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -167,12 +182,13 @@ tc_small_v2_kernel(const __grid_constant__ TcParams P, const __grid_constant__ F
 
   if (tid < N) stype[tid] = g_type;
   if (tab_ok && tid < Q.A0 + Q.A1) s_tab[tid] = g_tab;
-  if (tid < epb) s_nalive[tid] = 0;
+  if (tid < epb) { s_nalive[tid] = 0; s_ndead[tid] = 0; }
   for (int i = tid; i < epb * (Ne - N); i += blockDim.x) {   // key padding: never a candidate
     const int e = i / (Ne - N), j = N + (i - e * (Ne - N));
     skx[e * Ne + j] = CUDART_INF_F;
     sky[e * Ne + j] = CUDART_INF_F;
   }
+  int rho_own = li;
   if (active) {
     int rho = li;
     if (FUSED) {
@@ -181,7 +197,13 @@ tc_small_v2_kernel(const __grid_constant__ TcParams P, const __grid_constant__ F
         if (p == my_pol) rho = row_base[p] + le * Q.policy_size[p] + my_slot;
     }
     s_rho[rho] = (uint16_t)((le << 7) | a);
+    rho_own = rho;
+    // last step's neighbour ids of this agent, for whichever thread works on it later
+#pragma unroll
+    for (int p = 0; p < kHistIds; p++)
+      s_hist[(size_t)li * kHistIds + p] = (unsigned char)min(max(pnr[p], 0), 127);
   }
+  (void)rho_own;
   if (active && a == 0) {
     const int t = g_t + 1;   // :391-393
     P.timestep[env] = t;
@@ -259,11 +281,14 @@ tc_small_v2_kernel(const __grid_constant__ TcParams P, const __grid_constant__ F
     P.loc_x[gi] = x; P.loc_y[gi] = y; P.speed[gi] = sp;
     P.direction[gi] = dir; P.acceleration[gi] = acc; P.edge_pen[gi] = ep;
     spos[li] = make_float2(x, y);
-    skx[le * Ne + a] = alive ? x : CUDART_INF_F;
-    sky[le * Ne + a] = alive ? y : CUDART_INF_F;
+    // alive agents take the env's first slots, dead ones the last (any order inside each
+    // group: results do not depend on which thread works on which agent)
+    const int slot = alive ? atomicAdd(&s_nalive[le], 1) : N - 1 - atomicAdd(&s_ndead[le], 1);
+    s_perm[le * N + slot] = (unsigned char)a;
+    skx[le * Ne + slot] = alive ? x : CUDART_INF_F;
+    sky[le * Ne + slot] = alive ? y : CUDART_INF_F;
     ssp[li] = sp; sacc[li] = acc; sdir[li] = dir;
     salive[li] = alive;
-    if (alive) atomicAdd(&s_nalive[le], 1);
     float r = 0.0f;          // :283-291 reward initialisation (0 + edge + step)
     if (alive) { r += ep; r += P.step_rewards[a]; }
     srew[li] = r;
@@ -275,19 +300,27 @@ tc_small_v2_kernel(const __grid_constant__ TcParams P, const __grid_constant__ F
   const int t_env = active ? s_t[le] : 0;
   const float2 *epos = spos + le * N;
   const int *ealive = salive + le * N;
+  // from here on thread (le, j = a) works on the agent in slot j of its env
+  const int n_alive = active ? s_nalive[le] : 0;
+  const int aw = active ? (int)s_perm[le * N + a] : 0;
+  const bool alive_w = active && (a < n_alive);
+  const int liw = le * N + aw;
+  const int giw = env * N + aw;
+  const int nsc = (n_alive + 15) & ~15;            // alive agents fill key slots [0, n_alive)
+  const unsigned char *perm = s_perm + le * N;
+  uint32_t R[kListLen];
+  int kk = 0;
+  const bool net_ok = (K + 2 <= kListLen);
+  const uint32_t idmask = (1u << P.id_bits) - 1u;
   {
-    uint32_t R[kListLen];
-    int kk = 0;
     bool suspect = false;
-    const uint32_t idmask = (1u << P.id_bits) - 1u;
-    const bool net_ok = (K + 2 <= kListLen);
-    if (active && alive) {
-      const int nv = s_nalive[le] - 1;            // alive others
+    if (alive_w) {
+      const int nv = n_alive - 1;                 // alive others
       kk = min(nv, K);
       if (net_ok) {
         // fast path: branch-free top-16 of packed (squared distance | id) keys.  Dead
         // agents sit at +inf and sort last; self has key (0 | a).
-        const float2 pa = epos[a];
+        const float2 pa = epos[aw];
         const float *kx = skx + le * Ne, *ky = sky + le * Ne;
         uint32_t r0, r1, r2, r3, r4, r5, r6, r7, r8, r9, r10, r11, r12, r13, r14, r15;
         const uint32_t pad_key = 0x7f800000u | idmask;
@@ -307,8 +340,8 @@ tc_small_v2_kernel(const __grid_constant__ TcParams P, const __grid_constant__ F
 #pragma unroll
           for (int p = 0; p < kListLen - 2; p++) {
             if (p < K) {
-              const int b = min(max(pnr[p], 0), N - 1);
-              if (b != a && ealive[b]) {
+              const int b = min((int)s_hist[(size_t)liw * kHistIds + p], N - 1);
+              if (b != aw && ealive[b]) {
                 const float2 pb = epos[b];
                 tau = fmaxf(tau, sqdist(pa.x, pa.y, pb.x, pb.y));
                 seen++;
@@ -328,9 +361,9 @@ tc_small_v2_kernel(const __grid_constant__ TcParams P, const __grid_constant__ F
             const uint4 *ky4 = reinterpret_cast<const uint4 *>(ky);
             float mo_a = CUDART_INF_F, mo_b = CUDART_INF_F;
 #define WDB_SCAN_WORD(W, M)                                                          \
-            if (W * 32 < N) {                                                        \
+            if (W * 32 < nsc) {                                                      \
               scan_16<0>(M, mo_a, mo_b, kx4 + W * 8, ky4 + W * 8, pax2, pay2, tau);  \
-              if (W * 32 + 16 < N)                                                   \
+              if (W * 32 + 16 < nsc)                                                 \
                 scan_16<16>(M, mo_a, mo_b, kx4 + W * 8 + 4, ky4 + W * 8 + 4, pax2, pay2, tau); \
             }
             WDB_SCAN_WORD(0, m0) WDB_SCAN_WORD(1, m1) WDB_SCAN_WORD(2, m2) WDB_SCAN_WORD(3, m3)
@@ -395,7 +428,7 @@ tc_small_v2_kernel(const __grid_constant__ TcParams P, const __grid_constant__ F
           // rare (first step after a reset, list over/underflow): out-of-line so that the
           // hot path stays small in the instruction cache
           uint32_t out[kListLen];
-          network_top16(pa, kx, ky, N, idmask, out);
+          network_top16(pa, kx, ky, nsc, idmask, out);
           r0 = out[0]; r1 = out[1]; r2 = out[2]; r3 = out[3]; r4 = out[4]; r5 = out[5];
           r6 = out[6]; r7 = out[7]; r8 = out[8]; r9 = out[9]; r10 = out[10]; r11 = out[11];
           r12 = out[12]; r13 = out[13]; r14 = out[14]; r15 = out[15];
@@ -414,7 +447,7 @@ tc_small_v2_kernel(const __grid_constant__ TcParams P, const __grid_constant__ F
         // dx*dx+dy*dy nor the reference's float(sqrt(double)) can reorder or tie them)
         // and floor_out clears the K-th winner by the same margin.
         const int m = min(n_have, K + 1);
-        if ((int)(R[0] & idmask) != a) suspect = true;     // a co-located agent sorted first
+        if ((int)(R[0] & idmask) != a) suspect = true;     // (self sits in key slot j = a)
         float es[kListLen];
         bool misordered = false;
         {
@@ -423,8 +456,8 @@ tc_small_v2_kernel(const __grid_constant__ TcParams P, const __grid_constant__ F
           for (int i = 1; i < kListLen; i++) {
             es[i] = CUDART_INF_F;
             if (i <= m) {
-              const float2 pb = epos[R[i] & idmask];
-              es[i] = sqdist(pa.x, pa.y, pb.x, pb.y);
+              const int c = (int)(R[i] & idmask);              // key slot of the winner
+              es[i] = sqdist(pa.x, pa.y, kx[c], ky[c]);
               misordered |= !(es[i] > prev);
               prev = es[i];
             }
@@ -471,20 +504,24 @@ tc_small_v2_kernel(const __grid_constant__ TcParams P, const __grid_constant__ F
             if (!(rest - xk > rest * 1.9073486328125e-06f)) suspect = true;
           }
         }
+        // key slots -> agent ids
+#pragma unroll
+        for (int i = 1; i < kListLen; i++)
+          if (i <= kk) R[i] = (uint32_t)perm[min((int)(R[i] & idmask), N - 1)];
       } else {
         suspect = true;
       }
     }
     WDB_MARK(9)   // verified
-    if (P.force_exact && active && alive) suspect = true;
+    if (P.force_exact && alive_w) suspect = true;
     // exact path: the warp resolves its suspect agents one at a time, cooperatively
     unsigned todo = __ballot_sync(0xffffffffu, suspect);
     while (todo) {
       const int Lx = __ffs(todo) - 1;
       todo &= todo - 1;
-      const int ax = __shfl_sync(0xffffffffu, a, Lx);
+      const int ax = __shfl_sync(0xffffffffu, aw, Lx);
       const int lex = __shfl_sync(0xffffffffu, le, Lx);
-      const int gix = __shfl_sync(0xffffffffu, gi, Lx);
+      const int gix = __shfl_sync(0xffffffffu, giw, Lx);
       float *d;
       int *ids;
       if (P.scratch_in_smem) {
@@ -516,38 +553,42 @@ tc_small_v2_kernel(const __grid_constant__ TcParams P, const __grid_constant__ F
         if (i <= kk) idcol[(i - 1) * kWarp] = (uint16_t)(R[i] & idmask);
     }
 
-    if (active) s_kk[li] = alive ? (unsigned char)kk : (unsigned char)255;
-    if (active && alive && net_ok) {
-      int *nn = P.nearest + (long long)gi * K;                    // :202-211
+    if (alive_w && net_ok) {
+      int *nn = P.nearest + (long long)giw * K;                   // :202-211
 #pragma unroll
       for (int i = 1; i < kListLen; i++)
         if (i <= kk) nn[i - 1] = (int)(R[i] & idmask);
     }
   }
 
+  // policy / slot / tile row of the agent this thread works on
+  int pol_w = 0, slot_w = 0, np_w = 0, rho_w = liw;
+  if (FUSED && active) {
+    pol_w = Q.agent_policy[aw];
+    slot_w = Q.agent_slot[aw];
+#pragma unroll
+    for (int p = 0; p < kMaxPolicies; p++)
+      if (p == pol_w) { np_w = Q.policy_size[p]; rho_w = row_base[p] + le * np_w + slot_w; }
+  }
   // bookkeeping words needed after the reward phase
   int done_prev = 0, steps_prev = 0;
   float run_prev = 0.0f;
-  long long pi_slot = 0;
+  const long long pi_slot = (long long)env * np_w + slot_w;
   if (FUSED && active) {
     done_prev = P.done[env];
     if (a == 0 && Q.step_running_sum) steps_prev = Q.step_running_sum[env];
 #pragma unroll
-    for (int p = 0; p < kMaxPolicies; p++) {
-      if (p == my_pol) {
-        pi_slot = (long long)env * Q.policy_size[p] + my_slot;
-        if (Q.reward_running_sum[p]) run_prev = Q.reward_running_sum[p][pi_slot];
-      }
-    }
+    for (int p = 0; p < kMaxPolicies; p++)
+      if (p == pol_w && Q.reward_running_sum[p]) run_prev = Q.reward_running_sum[p][pi_slot];
   }
 
   // ------------------------------------------------------------------ rewards / tags (:259-349)
-  float r = active ? srew[li] : 0.0f;
-  const bool is_runner = active && (stype[a] == 0);
-  if (is_runner && alive) {                                  // :296-338
+  float r = active ? srew[liw] : 0.0f;
+  const bool is_runner = active && (stype[aw] == 0);
+  if (is_runner && alive_w) {                                // :296-338
     float min_dist = L * sqrt(2.0);
     int nearest_tagger = -1;
-    const float2 pa = epos[a];
+    const float2 pa = epos[aw];
     const int ntag = *s_ntag;
     float min_s = CUDART_INF_F;
     for (int q = 0; q < ntag; q++) {
@@ -569,7 +610,7 @@ tc_small_v2_kernel(const __grid_constant__ TcParams P, const __grid_constant__ F
         r += P.tag_penalty;
         atomicAdd(&srew[le * N + nearest_tagger], P.tag_reward);
         if (P.runner_exits) {
-          P.alive[gi] = 0;
+          P.alive[giw] = 0;
           atomicSub(&s_nrun[le], 1);
         }
         if (P.stats) atomicAdd(&P.stats[1], 1);
@@ -577,11 +618,11 @@ tc_small_v2_kernel(const __grid_constant__ TcParams P, const __grid_constant__ F
     }
     if (t_env == P.episode_length) r += P.end_reward;        // :334-337
   }
-  __syncthreads();   // barrier 2: tag credits / runner counts final; neighbour ids visible
+  __syncthreads();   // barrier 2: tag credits / runner counts final
   int done_now = 0;
   if (active) {
-    r = (stype[a] == 1) ? srew[li] : r;
-    P.rewards[gi] = r;
+    r = (stype[aw] == 1) ? srew[liw] : r;
+    P.rewards[giw] = r;
     const int nr = s_nrun[le];
     done_now = (t_env == P.episode_length || nr == 0) ? 1 : 0;   // :341-348
     if (a == 0) {
@@ -611,7 +652,7 @@ tc_small_v2_kernel(const __grid_constant__ TcParams P, const __grid_constant__ F
       const int d = done_now | (done_prev > 0 ? 1 : 0);
 #pragma unroll
       for (int p = 0; p < kMaxPolicies; p++) {
-        if (p == my_pol) {
+        if (p == pol_w) {
           if (Q.rewards_batch[p]) Q.rewards_batch[p][pi_slot] = r;
           if (Q.reward_running_sum[p]) {
             const float run = run_prev + r;
@@ -628,16 +669,16 @@ tc_small_v2_kernel(const __grid_constant__ TcParams P, const __grid_constant__ F
   }
 
   // ------------------------------------------------------------------ observations (:29-256)
-  // chunk by chunk: a warp assembles RPW rows x K neighbours per pass
+  // the tile holds `chunk_rows` rows at a time; every thread assembles the row of the agent it
+  // works on in the pass that row belongs to (dead agents: an all-zero row, :121-139)
   {
     const double diag = sqrt(2.0) * L;                // :94
     const double inv_diag = 1.0 / diag;
     const float vnorm = P.max_speed + kEpsilon;       // :101
     const float two_pi = kTwoPi, inv_two_pi = 1.0f / kTwoPi;
     const bool unit_v = (vnorm == 1.0f);
-    const int RPW = kWarp / K;
-    const int lane_r = lane / K, lane_p = lane - lane_r * K;
-    const bool item_lane = lane_r < RPW;
+    const uint16_t *idcol =
+        reinterpret_cast<const uint16_t *>(s_scr + (size_t)warp * P.scr_warp_bytes) + lane;
     const int R_chunk = V.chunk_rows;
     bool tma_pending = false;
     for (int c0 = 0; c0 < total_rows; c0 += R_chunk) {
@@ -647,35 +688,35 @@ tc_small_v2_kernel(const __grid_constant__ TcParams P, const __grid_constant__ F
         if (tid == 0 && tma_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncthreads();
       }
-      for (int rb = warp * RPW; rb < rows_c; rb += nwarps * RPW) {
-        const int rr = rb + lane_r;
-        if (item_lane && rr < rows_c) {
-          const int code = s_rho[c0 + rr];
-          const int le2 = code >> 7, a2 = code & 127;
-          const int li2 = le2 * N + a2;
-          const int kk2 = s_kk[li2];
-          float *orow = s_tile + rr * F;
-          float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f, f4 = 0.f, f5 = 0.f, f6 = 0.f;
-          if (lane_p < kk2 && kk2 != 255) {
-            const uint16_t *col = reinterpret_cast<const uint16_t *>(
-                s_scr + (size_t)(li2 >> 5) * P.scr_warp_bytes) + (li2 & 31);
-            const int b = col[lane_p * kWarp];
-            const int lb = le2 * N + b;
-            const float2 pa = spos[li2], pb = spos[lb];
-            f0 = div_by_const_f64(pb.x - pa.x, diag, inv_diag);           // :214-250
-            f1 = div_by_const_f64(pb.y - pa.y, diag, inv_diag);
-            const float dsp = ssp[lb] - ssp[li2], dac = sacc[lb] - sacc[li2];
-            f2 = unit_v ? dsp : dsp / vnorm;
-            f3 = unit_v ? dac : dac / vnorm;
-            f4 = div_by_two_pi(sdir[lb] - sdir[li2], two_pi, inv_two_pi);
-            f5 = stype[b];
-            f6 = salive[lb];
+      if (active && rho_w >= c0 && rho_w < c0 + rows_c) {
+        float *orow = s_tile + (rho_w - c0) * F;
+        if (!alive_w) {
+          for (int f = 0; f < F; f++) orow[f] = 0.0f;
+        } else {
+          for (int p = kk; p < K; p++) {
+#pragma unroll
+            for (int f = 0; f < 7; f++) orow[f * K + p] = 0.0f;
           }
-          orow[0 * K + lane_p] = f0; orow[1 * K + lane_p] = f1; orow[2 * K + lane_p] = f2;
-          orow[3 * K + lane_p] = f3; orow[4 * K + lane_p] = f4; orow[5 * K + lane_p] = f5;
-          orow[6 * K + lane_p] = f6;
-          if (lane_p == 0)                                                  // :251-253
-            orow[7 * K] = (kk2 != 255) ? static_cast<float>(s_t[le2]) / P.episode_length : 0.0f;
+          const float2 pa = epos[aw];
+          const float spa = ssp[liw], acca = sacc[liw], dira = sdir[liw];
+#define WDB_FEATURES(UNIT, UNROLL)                                                  \
+          _Pragma(UNROLL)                                                           \
+          for (int p = 0; p < kk; p++) {                                            \
+            const int b = (int)idcol[p * kWarp];                                    \
+            const int lb = le * N + b;                          /* :214-250 */      \
+            const float2 pb = epos[b];                                              \
+            orow[0 * K + p] = div_by_const_f64(pb.x - pa.x, diag, inv_diag);        \
+            orow[1 * K + p] = div_by_const_f64(pb.y - pa.y, diag, inv_diag);        \
+            const float dsp = ssp[lb] - spa, dac = sacc[lb] - acca;                 \
+            orow[2 * K + p] = UNIT ? dsp : dsp / vnorm;                             \
+            orow[3 * K + p] = UNIT ? dac : dac / vnorm;                             \
+            orow[4 * K + p] = div_by_two_pi(sdir[lb] - dira, two_pi, inv_two_pi);   \
+            orow[5 * K + p] = stype[b];                                             \
+            orow[6 * K + p] = ealive[b];                                            \
+          }
+          if (unit_v) { WDB_FEATURES(true, "unroll 2") } else { WDB_FEATURES(false, "unroll 1") }
+#undef WDB_FEATURES
+          orow[7 * K] = static_cast<float>(t_env) / P.episode_length;   // :251-253
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -845,8 +886,11 @@ int tc_v2_launch(TcParams &P, const FusedParams *Qp, cudaStream_t st) {
   int bits = 1;
   while ((1 << bits) < N) bits++;
   P.id_bits = bits;
+  // (mirror of the kernel's carve-up: scratch, s_rho, s_perm, s_hist, s_ndead)
   const size_t fixed = tc_small_bytes(epb, N) + warp_bytes * nwarps + (size_t)((EN + 7) & ~7) * 2 +
-                       (size_t)((EN + 15) & ~15);
+                       (size_t)((EN + 15) & ~15) +
+                       (((size_t)EN * kHistIds + 15) & ~(size_t)15) +
+                       (size_t)((epb + 3) & ~3) * 4;
   const size_t budget = (size_t)(227 * 1024) / minb - 1024;     // minb CTAs per SM
   if (fixed + 32ull * F * 4 > budget) return (int)cudaErrorInvalidValue;
   int chunk = (int)((budget - fixed) / (4ull * F)) & ~3;

@@ -724,6 +724,19 @@ class CUDALogController:
                 _P(data_manager.device_data(name)), int(shape[1]), feature_dim, int(step),
                 int(data_manager.meta_info("episode_length")), int(env_id)), "log_one_step")
 
+    def log_tensor_one_step(self, log, data, step, env_id=0):
+        """Copy env `env_id`'s slice of `data` ([n_envs, ...], any 32-bit dtype) into row `step`
+        of the device-side log `log` ([n_steps, ...]) with the log kernel -- the device ring
+        Trainer.fetch_episode_states records an episode in (no `_for_log` registration needed)."""
+        assert data.is_cuda and log.is_cuda and data.element_size() == 4 and log.dtype == data.dtype
+        assert data.is_contiguous() and log.is_contiguous()
+        assert 0 <= step < log.shape[0] and 0 <= env_id < data.shape[0]
+        per_env = int(np.prod(data.shape[1:])) if data.dim() > 1 else 1
+        assert int(np.prod(log.shape[1:])) == per_env if log.dim() > 1 else per_env == 1
+        _libmod.check(_libmod.load().wdb_log_one_step(
+            _stream(), _P(log), _P(data), per_env, 1, int(step), int(log.shape[0]) - 1,
+            int(env_id)), "log_one_step")
+
     def _update_log_mask(self, data_manager, step):
         _libmod.check(_libmod.load().wdb_update_log_mask(
             _stream(), _P(data_manager.device_data("_log_mask_")), int(step),

@@ -12,17 +12,24 @@ from warp_drive_b200 import lib as _lib
 class FusedPolicyForward:
     @staticmethod
     def supported(model):
-        """Two hidden layers of equal width (multiple of 32, <= 256), two softmax heads."""
+        """Two hidden layers of equal width (multiple of 32, <= 256), one or two softmax heads."""
         try:
             if getattr(model, "is_deterministic", True) or len(model.fc) != 2:
                 return False
             dims = list(model.fc_dims)
-            if dims[0] != dims[1] or len(model.output_dims) != 2:
+            if dims[0] != dims[1] or len(model.output_dims) not in (1, 2):
                 return False
+            from warp_drive_b200.utils.spaces import Box
+
+            # Dict observations may carry an action mask the module applies to the logits
+            space = getattr(model, "observation_space", None)
+            if getattr(model, "action_mask", None) is not None or (
+                    space is not None and not isinstance(space, Box)):
+                return False
+            heads = [int(a) for a in model.output_dims] + [0]
             L = _lib.load()
             return L.wdb_mlp_blob_bytes(int(model.flattened_obs_size), int(dims[0]),
-                                        int(model.output_dims[0]),
-                                        int(model.output_dims[1])) > 0
+                                        heads[0], heads[1]) > 0
         except Exception:  # noqa: BLE001
             return False
 
@@ -31,7 +38,8 @@ class FusedPolicyForward:
         self.model = model
         self.F = int(model.flattened_obs_size)
         self.H = int(model.fc_dims[0])
-        self.A0, self.A1 = (int(a) for a in model.output_dims)
+        heads = [int(a) for a in model.output_dims] + [0]
+        self.A0, self.A1 = heads[0], heads[1]          # A1 == 0: single-head policy
         self.lib = _lib.load()
         nbytes = int(self.lib.wdb_mlp_blob_bytes(self.F, self.H, self.A0, self.A1))
         dev = next(model.parameters()).device
@@ -42,10 +50,12 @@ class FusedPolicyForward:
         """Re-pack the module's current parameters (call after every optimizer step)."""
         m = self.model
         l1, l2 = m.fc["0"][0], m.fc["1"][0]
-        h0, h1 = m.policy_head[0], m.policy_head[1]
-        ts = [l1.weight, l1.bias, l2.weight, l2.bias, h0.weight, h0.bias, h1.weight, h1.bias,
+        h0 = m.policy_head[0]
+        h1 = m.policy_head[1] if self.A1 > 0 else None
+        ts = [l1.weight, l1.bias, l2.weight, l2.bias, h0.weight, h0.bias,
+              h1.weight if h1 is not None else None, h1.bias if h1 is not None else None,
               m.vf_head.weight, m.vf_head.bias]
-        ts = [t.detach().float().contiguous() for t in ts]
+        ts = [t.detach().float().contiguous() if t is not None else None for t in ts]
         _lib.check(self.lib.wdb_mlp_pack_weights(
             _lib.stream_ptr(), _lib.ptr(self.blob), *[_lib.ptr(t) for t in ts],
             self.F, self.H, self.A0, self.A1), "mlp_pack_weights")

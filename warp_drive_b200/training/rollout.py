@@ -89,9 +89,11 @@ class RolloutEngine:
         # ---- tensor-core forward (tcgen05 MLP kernel) for the fused path
         self.fused_forward = {}
         self.obs_tiles = {}
-        if self.fused is not None and use_fused_forward and forward_dtype is None:
+        if self.sa is None and use_fused_forward and forward_dtype is None and not self.continuous:
             from warp_drive_b200.training.models.fused_forward import FusedPolicyForward
 
+            # (also on the generic multi-launch path: gridworld, classic control with a policy
+            #  too large for the whole-rollout kernel, envs with reset pools ...)
             if all(FusedPolicyForward.supported(m) for m in self.models.values()):
                 self.fused_forward = {p: FusedPolicyForward(self.models[p]) for p in self.policies}
                 self._probs = {p: [torch.empty((self.E, len(self.policy_map[p]), h), device=dev)
@@ -100,7 +102,8 @@ class RolloutEngine:
                 # the fused env step itself (and by pack_obs whenever cur_obs changes outside it)
                 # (off by default: measured at config 2, the env step's extra pass costs what
                 #  the forward saves -- see DESIGN.md 3.2)
-                if (use_obs_tiles and int(getattr(env_wrapper, "blocks_per_env", 1) or 1) == 1
+                if (use_obs_tiles and self.fused is not None
+                        and int(getattr(env_wrapper, "blocks_per_env", 1) or 1) == 1
                         and not getattr(env_wrapper.env, "use_full_observation", False)):
                     self.obs_tiles = {
                         p: torch.zeros(self.fused_forward[p].tiles_bytes(
@@ -285,7 +288,14 @@ class RolloutEngine:
             obs_p = obs if self.covers_all[p] else obs.index_select(1, self.ids[p])
             if t >= 0:
                 self._tensor(f"{_PROCESSED_OBSERVATIONS}_batch_{p}")[t].copy_(obs_p)
-            probs = self._forward(model, obs_p)
+            if self.fused_forward:
+                # tcgen05 forward straight into the persistent probability buffers
+                bufs = self._probs[p]
+                self.fused_forward[p](obs_p.contiguous(), bufs[0],
+                                      bufs[1] if len(bufs) > 1 else None)
+                probs = bufs
+            else:
+                probs = self._forward(model, obs_p)
             if self.combined is None:
                 out = probs
             else:

@@ -439,9 +439,79 @@ class Trainer:
     def fetch_episode_states(self, list_of_states=None, env_id=0, include_rewards_actions=False,
                              include_probabilities=False):
         """Play one episode of env `env_id` with the current policies and return the
-        per-timestep values of the requested device arrays
-        (trainer_base.py:689-792).  Uses the generic (multi-launch) step so that every
-        array is materialised each step."""
+        per-timestep values of the requested device arrays (trainer_base.py:689-792).
+
+        The episode is logged ON THE DEVICE: every requested array has a [T + 1, ...] ring in
+        HBM that `wdb_log_one_step` (the CUDALogController kernel, function_manager.py:295-422)
+        fills with env `env_id`'s slice after each step, the done flag of that env is logged
+        the same way, and the host pulls everything ONCE after the last step (the reference
+        pulls every whole [E, ...] array to the host every timestep)."""
+        from warp_drive_b200.managers.function_manager import CUDALogController
+
+        assert 0 <= env_id < self.num_envs
+        assert isinstance(list_of_states, list) and list_of_states
+        dm = self.cuda_envs.cuda_data_manager
+        self.cuda_envs.reset_all_envs()
+        self.engine.resync_observations()
+        T = self.cuda_envs.episode_length
+        logger = CUDALogController(self.cuda_envs.cuda_function_manager)
+
+        def ring(name, steps):
+            t = dm.data_on_device_via_torch(name)
+            fill = float("nan") if t.dtype.is_floating_point else 0
+            return torch.full((steps,) + tuple(t.shape[1:]), fill, dtype=t.dtype, device=t.device)
+
+        rings = {name: ring(name, T + 1) for name in list_of_states}
+        for name in list_of_states:
+            logger.log_tensor_one_step(rings[name], dm.data_on_device_via_torch(name), 0, env_id)
+        extra = {}
+        if include_rewards_actions:
+            extra = {_ACTIONS: ring(_ACTIONS, T), _REWARDS: ring(_REWARDS, T)}
+        done_ring = torch.zeros(T, dtype=torch.int32, device=dm.device)
+        prob_rings = None
+        fused, self.engine.fused = self.engine.fused, None
+        sa, self.engine.sa = self.engine.sa, None
+        try:
+            for t in range(T):
+                with torch.no_grad():
+                    probs = self.engine.evaluate_policies(-1)
+                    self.engine.sample_actions(probs, -1)
+                    self.cuda_envs.step_all_envs()
+                for name in list_of_states:
+                    logger.log_tensor_one_step(rings[name], dm.data_on_device_via_torch(name),
+                                               t + 1, env_id)
+                for name, r in extra.items():
+                    logger.log_tensor_one_step(r, dm.data_on_device_via_torch(name), t, env_id)
+                logger.log_tensor_one_step(done_ring, dm.data_on_device_via_torch("_done_"), t,
+                                           env_id)
+                if include_probabilities:
+                    if prob_rings is None:
+                        prob_rings = [torch.zeros((T,) + tuple(p.shape[1:]), device=p.device)
+                                      for p in probs]
+                    for r, p in zip(prob_rings, probs):
+                        logger.log_tensor_one_step(r, p.contiguous(), t, env_id)
+            # ---- the one device -> host transfer of the episode
+            done_host = done_ring.cpu().numpy()
+            ended = np.nonzero(done_host)[0]
+            n_steps = int(ended[0]) + 1 if len(ended) else T
+            out = {name: rings[name][: n_steps + 1].cpu().numpy().astype(np.float32)
+                   for name in list_of_states}
+            for name, r in extra.items():
+                out[name] = r[:n_steps].cpu().numpy().astype(np.float32)
+            if include_probabilities:
+                host = [r[:n_steps].cpu().numpy() for r in prob_rings]
+                out["probabilities"] = [[h[t] for h in host] for t in range(n_steps)]
+        finally:
+            self.engine.fused = fused
+            self.engine.sa = sa
+            self.cuda_envs.reset_all_envs()
+            self.engine.resync_observations()
+        return out
+
+    def _fetch_episode_states_host_pull(self, list_of_states=None, env_id=0, include_rewards_actions=False,
+                             include_probabilities=False):
+        """The reference-shaped implementation (one host pull of every whole [E, ...] array
+        per timestep, trainer_base.py:689-792); kept as the checker of fetch_episode_states."""
         assert 0 <= env_id < self.num_envs
         assert isinstance(list_of_states, list) and list_of_states
         dm = self.cuda_envs.cuda_data_manager
