@@ -675,13 +675,11 @@ def run_config3(args):
 
 
 # ----------------------------------------------------------------------------- --mode train
-def run_train_mode(args):
-    """One 'step' = one rollout timestep INSIDE full training iterations: T-step rollout ->
-    A2C/PPO update of both policies (forward + backward over the [T, E, Np, F] batch, returns
-    scan kernel, Adam) -> ONE flat NCCL all-reduce (mean) of all gradients
-    (training/utils/distributed.py; reference: DDP over gloo, trainer_a2c.py:137-146).
-    At --gpus 8 with 2000 envs per GPU this is BASELINE.json configs[4] (16000 envs sharded
-    over 8 x B200, PPO + NCCL gradient all-reduce)."""
+def train_iteration_stats(args, world, rank, local_rank, n_iters, reps, warm_iters=3):
+    """Full training iterations on this rank's process group (already initialised): T-step
+    rollout -> A2C/PPO update of both policies (fused loss kernel, cuBLAS forward/backward, flat
+    Adam) -> ONE in-place NCCL all-reduce (mean) of the flat gradient arena.  Returns
+    (elapsed_ms_per_rep list, phase medians, all-reduce us list, gradient elements, E, N, T)."""
     import copy
 
     import torch
@@ -692,20 +690,9 @@ def run_train_mode(args):
     from warp_drive_b200.envs.tag_continuous import TagContinuous
     from warp_drive_b200.training.trainer import Trainer
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    assert world == args.gpus
     torch.backends.cuda.matmul.allow_tf32 = True
     torch.backends.cudnn.allow_tf32 = True
     E, T = args.envs, args.train_steps
-    K = args.steps
-    n_iters = max(1, K // T)
-    K = n_iters * T
     with open(os.path.join(ROOT, "warp_drive_b200", "training", "run_configs",
                            "tag_continuous.yaml"), encoding="utf8") as fp:
         cfg = yaml.safe_load(fp)
@@ -750,55 +737,88 @@ def run_train_mode(args):
         if ev:
             ev[2].record()
 
-    for i in range(max(3, math.ceil(args.warmup / T))):
+    for i in range(warm_iters):
         iteration(i)
+    torch.cuda.synchronize()
     ar_events.clear()
-    reps = args.reps if args.reps > 0 else 5
     rep_ms, phases = [], []
-    with ClockSampler(local_rank) as clocks:
-        for _ in range(reps):
-            evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n_iters)]
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            barrier()
-            a.record()
-            for i in range(n_iters):
-                iteration(1000 + i, evs[i])
-            b.record()
-            barrier()
-            t = torch.tensor([a.elapsed_time(b)], device="cuda", dtype=torch.float64)
-            if world > 1:
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            rep_ms.append(float(t.item()))
-            phases += [(e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])) for e in evs]
-    elapsed_ms = sorted(rep_ms)[len(rep_ms) // 2]
-    value = world * E * N * K / (elapsed_ms / 1000.0)
+    for _ in range(reps):
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n_iters)]
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a.record()
+        for i in range(n_iters):
+            iteration(1000 + i, evs[i])
+        b.record()
+        barrier()
+        t = torch.tensor([a.elapsed_time(b)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        rep_ms.append(float(t.item()))
+        phases += [(e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])) for e in evs]
     ar_us = sorted(a.elapsed_time(b) * 1e3 for a, b in ar_events) if ar_events else []
     n_grad = sum(p.numel() for p in trainer._trained_params())
+    roll = sorted(p[0] for p in phases)[len(phases) // 2]
+    upd = sorted(p[1] for p in phases)[len(phases) // 2]
+    del trainer, wrapper
+    torch.cuda.empty_cache()
+    return rep_ms, roll, upd, ar_us, n_grad, E, N, T
+
+
+def train_summary(rep_ms, roll, upd, ar_us, n_grad, E, N, T, n_iters, world, algo):
+    elapsed_ms = sorted(rep_ms)[len(rep_ms) // 2]
+    it_ms = elapsed_ms / n_iters
+    return {
+        "algorithm": algo, "rollout_steps_per_iteration": T,
+        "agent_steps_per_sec": world * E * N * T * n_iters / (elapsed_ms / 1000.0),
+        "iteration_ms": it_ms, "rollout_ms": roll, "update_ms": upd,
+        "allreduce_us_median": ar_us[len(ar_us) // 2] if ar_us else None,
+        "allreduce_us_max": ar_us[-1] if ar_us else None,
+        "allreduce_share_of_iteration": (ar_us[len(ar_us) // 2] / 1e3 / it_ms) if ar_us else 0.0,
+        "gradient_elements": n_grad, "gradient_bytes": 4 * n_grad,
+        "collective": "ONE in-place NCCL all-reduce (sum) of the flat gradient arena of all "
+                      "policies + divide by world size, per iteration; no collective on the "
+                      "rollout path (env replicas are independent)",
+        "limiter": ("update: cuBLAS TF32 forward + backward over the "
+                    f"[{T}, {E}, Np, 71] batches + fused loss kernel + flat Adam"
+                    if upd > roll else "rollout"),
+    }
+
+
+def run_train_mode(args):
+    """--mode train: one 'step' = one rollout timestep INSIDE full training iterations.  At
+    --gpus 8 with 2000 envs per GPU this is BASELINE.json configs[4] (16000 envs sharded over
+    8 x B200, PPO + NCCL gradient all-reduce)."""
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    assert world == args.gpus
+    T = args.train_steps
+    n_iters = max(1, args.steps // T)
+    K = n_iters * T
+    reps = args.reps if args.reps > 0 else 5
+    with ClockSampler(local_rank) as clocks:
+        stats = train_iteration_stats(args, world, rank, local_rank, n_iters, reps,
+                                      warm_iters=max(3, math.ceil(args.warmup / T)))
+    rep_ms, roll, upd, ar_us, n_grad, E, N, T = stats
     if rank == 0:
-        roll = sorted(p[0] for p in phases)[len(phases) // 2]
-        upd = sorted(p[1] for p in phases)[len(phases) // 2]
-        it_ms = elapsed_ms / n_iters
+        tr = train_summary(*stats, n_iters, world, args.algo)
+        elapsed_ms = sorted(rep_ms)[len(rep_ms) // 2]
         line = {
-            "metric": "agent_steps_per_sec", "mode": "train", "value": value,
+            "metric": "agent_steps_per_sec", "mode": "train", "value": tr["agent_steps_per_sec"],
             "unit": "agent-steps/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / K, "ms_per_step_reps": [m / K for m in rep_ms],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": dict(workload_config(E, N), mode="train",
                                                 algorithm=args.algo, rollout_steps=T),
-            "train": {
-                "iteration_ms": it_ms, "rollout_ms": roll, "update_ms": upd,
-                "allreduce_us_median": ar_us[len(ar_us) // 2] if ar_us else None,
-                "allreduce_us_max": ar_us[-1] if ar_us else None,
-                "allreduce_share_of_iteration": (ar_us[len(ar_us) // 2] / 1e3 / it_ms)
-                if ar_us else 0.0,
-                "gradient_elements": n_grad, "gradient_bytes": 4 * n_grad,
-                "collective": "one flat NCCL all-reduce (sum) of every trained parameter's "
-                              "gradient + divide by world size, per iteration; no collective "
-                              "on the rollout path (env replicas are independent)",
-                "limiter": "update (torch autograd forward + backward over the "
-                           f"[{T}, {E}, Np, 71] batches)" if upd > roll else "rollout",
-            },
-            "clocks": dict(clocks.summary(), window="timed region"),
+            "train": tr, "clocks": dict(clocks.summary(), window="timed region"),
             "gpu_launches": None,
         }
         print(json.dumps(line))
@@ -826,6 +846,9 @@ def main():
     ap.add_argument("--train-steps", type=int, default=10,
                     help="--mode train: rollout timesteps per training iteration")
     ap.add_argument("--algo", default="PPO", choices=["A2C", "PPO"])
+    ap.add_argument("--skip-train-probe", action="store_true",
+                    help="config 2: do not append the short training-iteration measurement "
+                         "(rollout + update + NCCL gradient all-reduce) to the line")
     ap.add_argument("--blocks-per-env", type=int, default=0,
                     help="config 4: CTAs per env (cluster size), default 2")
     ap.add_argument("--no-graph", action="store_true")
@@ -957,6 +980,17 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * E * N / (float(t.item()) / 1000.0)
 
+    # ---- training-iteration probe (all ranks: it contains the one collective of the path,
+    # the NCCL gradient all-reduce): a few full iterations, reported next to the rollout number
+    train_probe = None
+    if args.config == 2 and not args.skip_train_probe:
+        try:
+            stats = train_iteration_stats(args, world, rank, local_rank, n_iters=3, reps=3,
+                                          warm_iters=2)
+            train_probe = train_summary(*stats, 3, world, args.algo)
+        except Exception as err:  # noqa: BLE001
+            train_probe = {"error": f"{type(err).__name__}: {err}"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -1040,6 +1074,8 @@ def main():
                                  "agents that needed the exact tie-resolution path"},
         "roofline": roofline,
     }
+    if train_probe is not None:
+        line["train"] = train_probe
     # ---- same-box GPU anchor: the reference's own CUDA kernels on this GPU (N=1 only)
     if world == 1 and not args.skip_ref_gpu:
         try:

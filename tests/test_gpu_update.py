@@ -117,8 +117,8 @@ def test_flat_adam_matches_torch_adam_with_clipping():
 
 
 def test_cartpole_learns_with_the_fused_rollout_and_update(tmp_path):
-    """Learning assertion: 'Mean episodic steps' of CartPole rises over 30 training iterations
-    (whole-rollout kernel + fused loss + flat Adam)."""
+    """Learning assertion: 'Mean episodic steps' of CartPole rises while training with the
+    whole-rollout kernel + fused loss + flat Adam (a random policy balances ~22 steps)."""
     import yaml
 
     from warp_drive_b200.env_wrapper import EnvWrapper
@@ -129,8 +129,9 @@ def test_cartpole_learns_with_the_fused_rollout_and_update(tmp_path):
     with open(os.path.join(root, "warp_drive_b200", "training", "run_configs",
                            "single_cartpole.yaml"), encoding="utf8") as fp:
         cfg = yaml.safe_load(fp)
-    E, T, iters = 256, 64, 30
+    E, T, iters = 256, 64, 150
     cfg["env"].update(episode_length=200, reset_pool_size=64)
+    cfg["policy"]["shared"].update(lr=0.01, entropy_coeff=0.01)
     cfg["trainer"].update(num_envs=E, train_batch_size=E * T, num_episodes=10 ** 6, seed=3)
     cfg["saving"].update(basedir=str(tmp_path), metrics_log_freq=10 ** 9,
                          model_params_save_freq=10 ** 9)
@@ -149,5 +150,6 @@ def test_cartpole_learns_with_the_fused_rollout_and_update(tmp_path):
         tr.engine.episodic_step_sum.zero_()
         tr.engine.num_completed_episodes.zero_()
         tr.engine.episodic_reward_sum["shared"].zero_()
-    first, last = np.mean(means[:5]), np.mean(means[-5:])
-    assert last > 1.3 * first, (first, last, means)
+    # (iteration 0 is a logging iteration: the trainer itself clears the counters there)
+    first, last = np.mean(means[1:6]), np.mean(means[-5:])
+    assert last > 1.5 * first, (first, last, [round(m, 1) for m in means[::10]])

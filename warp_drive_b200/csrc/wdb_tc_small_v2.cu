@@ -807,7 +807,7 @@ tc_small_v2_kernel(const __grid_constant__ TcParams P, const __grid_constant__ F
   }
 }
 
-int g_tc_v2_threads = 320;   // wdb_set_option("tc_v2_threads", 320 | 224)
+int g_tc_v2_threads = 320;   // wdb_set_option("tc_v2_threads", 320 | 224 | 128)
 
 template <bool FUSED, int MAXT, int MINB>
 int v2_launch_t(const TcParams &P, const FusedParams &Q, const V2Params &V, int grid, int block,
@@ -844,7 +844,7 @@ int tc_v2_set_option(const char *name, int value, bool *handled) {
     return 0;
   }
   if (is("tc_v2_threads")) {
-    if (value != 320 && value != 224) return (int)cudaErrorInvalidValue;
+    if (value != 320 && value != 224 && value != 128) return (int)cudaErrorInvalidValue;
     g_tc_v2_threads = value;
     return 0;
   }
@@ -866,7 +866,7 @@ bool tc_v2_eligible(const TcParams &P, const FusedParams *Q) {
 int tc_v2_launch(TcParams &P, const FusedParams *Qp, cudaStream_t st) {
   const int N = P.N, K = P.K, F = 7 * K + 1;
   const int budget_threads = g_tc_v2_threads;
-  const int minb = budget_threads == 320 ? 3 : 4;
+  const int minb = budget_threads == 320 ? 3 : (budget_threads == 224 ? 4 : 7);
   int epb = N >= budget_threads ? 1 : budget_threads / N;
   if (epb > P.n_envs) epb = P.n_envs;
   const int block = round_up(epb * N, 32);
@@ -907,10 +907,12 @@ int tc_v2_launch(TcParams &P, const FusedParams *Qp, cudaStream_t st) {
   FusedParams Q = {};
   if (Qp) Q = *Qp;
   if (Qp)
-    return minb == 3 ? v2_launch_t<true, 320, 3>(P, Q, V, grid, block, smem, st)
-                     : v2_launch_t<true, 224, 4>(P, Q, V, grid, block, smem, st);
-  return minb == 3 ? v2_launch_t<false, 320, 3>(P, Q, V, grid, block, smem, st)
-                   : v2_launch_t<false, 224, 4>(P, Q, V, grid, block, smem, st);
+    return minb == 3   ? v2_launch_t<true, 320, 3>(P, Q, V, grid, block, smem, st)
+           : minb == 4 ? v2_launch_t<true, 224, 4>(P, Q, V, grid, block, smem, st)
+                       : v2_launch_t<true, 128, 7>(P, Q, V, grid, block, smem, st);
+  return minb == 3   ? v2_launch_t<false, 320, 3>(P, Q, V, grid, block, smem, st)
+         : minb == 4 ? v2_launch_t<false, 224, 4>(P, Q, V, grid, block, smem, st)
+                     : v2_launch_t<false, 128, 7>(P, Q, V, grid, block, smem, st);
 }
 
 }  // namespace wdb
