@@ -1,7 +1,8 @@
 // wdb_sa_rollout.cu -- the WHOLE T-step rollout of a discrete-action single-agent env
 // (CartPole, MountainCar, Acrobot; BASELINE config 3: CartPole x 10 000 replicas) in ONE
 // launch: policy forward -> categorical sample -> env.step -> reward / done bookkeeping ->
-// done-masked reset -> push to the training batch, T times, one thread per env replica.
+// done-masked reset -> push to the training batch, T times; eight lanes share one env replica
+// (the forward pass is split over them, lane 0 does the serial part of the timestep).
 //
 // Replaces, per timestep, the reference's TrainerBase._generate_rollout_batch body
 // (warp_drive/training/trainers/trainer_base.py:383-428): FullyConnected.forward
@@ -15,9 +16,9 @@
 // Why no tensor cores: the policies of these envs are tiny (single_cartpole.yaml: 4 -> 32 ->
 // 32 -> 2, 1.3 K weights).  A 128-row tcgen05 tile would run K = 4 / 32 MMAs at a few percent
 // of the tensor pipe and cost three launches per step; the whole network fits shared memory,
-// every thread evaluates its own replica's forward in float32 (closer to the float32 torch
+// every env's forward is evaluated in float32 by its lane group (closer to the float32 torch
 // forward the update recomputes than a bf16 MMA would be), and env replicas never interact,
-// so nothing has to leave the thread between timesteps.  Larger policies (H > 64) keep the
+// so nothing has to leave the SM between timesteps.  Larger policies (H > 64) keep the
 // per-step path (tcgen05 forward + fused step).
 //
 // Per timestep and env (order = the reference's): obs -> batch[t]; probs = softmax(MLP(obs));
@@ -33,7 +34,10 @@ using namespace wdb;
 namespace {
 
 constexpr int kSaThreads = 64;
-constexpr int kSaMaxWidth = 64;     // widest layer (and observation) held per thread
+constexpr int kSaGroup = 8;         // lanes that share one env replica's forward pass
+constexpr int kSaEnvsPerCta = kSaThreads / kSaGroup;
+constexpr int kSaMaxWidth = 64;     // widest layer (and observation) held per env
+constexpr int kSaPitch = kSaMaxWidth + 1;  // activation row pitch (odd: no bank conflicts)
 constexpr int kSaMaxWeights = 11 * 1024;   // floats of shared memory for the policy
 
 __device__ __forceinline__ int sa_search(const float *cdf, float p, int r) {
@@ -47,176 +51,206 @@ __device__ __forceinline__ int sa_search(const float *cdf, float p, int r) {
   return left > r ? r : left;
 }
 
+// Thread layout: kSaGroup = 8 consecutive lanes own one env replica.  The forward pass is
+// split over the group (lane `sub` computes output neurons sub, sub + 8, ... of every layer;
+// each neuron still accumulates bias + w[0] x[0] + w[1] x[1] + ... in that order, so the
+// result does not depend on the split); activations travel through a per-env shared-memory
+// row, the weights sit TRANSPOSED in shared memory (Wt[i][j]: the lanes of a group read
+// consecutive words, the groups of a warp the same words).  Lane 0 of the group then does the
+// serial part of the timestep -- softmax, sample, physics, bookkeeping, reset -- so the
+// dependent chain per timestep is ~1/7 of a one-thread-per-env layout and eight times as many
+// warps are in flight.  All control flow is warp-uniform (groups past n_envs compute on
+// clamped indices and skip their stores).
 __global__ void __launch_bounds__(kSaThreads)
 sa_rollout_kernel(const __grid_constant__ wdb_sa_rollout R) {
-  extern __shared__ float s_w[];               // all layers: [W0 | b0 | W1 | b1 | ...]
+  extern __shared__ float s_w[];               // per layer: [Wt (in x out) | b (out)]
   const int n_layers = R.n_hidden + 1;
-  {
-    int off = 0;
-    for (int l = 0; l < n_layers; l++) {
-      const int in = R.dims[l], out = R.dims[l + 1];
-      for (int i = threadIdx.x; i < in * out; i += blockDim.x) s_w[off + i] = R.w[l][i];
-      off += in * out;
-      for (int i = threadIdx.x; i < out; i += blockDim.x) s_w[off + i] = R.b[l][i];
-      off += out;
+  int w_floats = 0;
+  for (int l = 0; l < n_layers; l++) {
+    const int in = R.dims[l], out = R.dims[l + 1];
+    for (int i = threadIdx.x; i < in * out; i += blockDim.x) {
+      const int j = i / in, k = i - j * in;    // W[j][k] (nn.Linear: [out, in]) -> Wt[k][j]
+      s_w[w_floats + k * out + j] = R.w[l][i];
     }
+    for (int i = threadIdx.x; i < out; i += blockDim.x) s_w[w_floats + in * out + i] = R.b[l][i];
+    w_floats += in * out + out;
   }
+  float *s_act = s_w + w_floats;               // [kSaEnvsPerCta][2][kSaPitch]
   __syncthreads();
-  const int env = blockIdx.x * blockDim.x + threadIdx.x;
-  if (env >= R.n_envs) return;
+  const int sub = threadIdx.x & (kSaGroup - 1);
+  const int env_local = threadIdx.x / kSaGroup;
+  const int env_raw = blockIdx.x * kSaEnvsPerCta + env_local;
+  const bool live = env_raw < R.n_envs;
+  const int env = live ? env_raw : R.n_envs - 1;
+  const bool lead = live && sub == 0;
   const int E = R.n_envs, F = R.dims[0], A = R.dims[n_layers], S = R.state_dim;
-  const RngHeader rh = R.rng_state ? *reinterpret_cast<const RngHeader *>(R.rng_state)
-                                   : RngHeader{0ull, 0ull};
-  unsigned long long rng_off = R.rng_state ? rng_offsets(R.rng_state)[env] : 0ull;
-  RngHeader ph = {0ull, 0ull};
-  unsigned long long pool_off = 0;
-  if (R.pool_rng) {
-    ph = *reinterpret_cast<const RngHeader *>(R.pool_rng);
-    pool_off = rng_offsets(R.pool_rng)[env];
-  }
-  float run = R.reward_running_sum ? R.reward_running_sum[env] : 0.0f;
-  int steps_run = R.step_running_sum ? R.step_running_sum[env] : 0;
-  int tstep = R.env_timestep[env];
-  int done_flag = R.done[env];
+  float *buf0 = s_act + (env_local * 2 + 0) * kSaPitch;
+  float *buf1 = s_act + (env_local * 2 + 1) * kSaPitch;
 
-  float xa[kSaMaxWidth], xb[kSaMaxWidth];
-  for (int t = 0; t < R.n_steps; t++) {
-    // ---- observation -> batch slot t (processed_observations_batch, model_base.py:181-200)
-    const float *obs = R.observations + (size_t)env * F;
-    for (int i = 0; i < F; i++) xa[i] = obs[i];
-    if (R.obs_batch) {
-      float *ob = R.obs_batch + ((size_t)t * E + env) * F;
-      for (int i = 0; i < F; i++) ob[i] = xa[i];
+  RngHeader rh = {0ull, 0ull}, ph = {0ull, 0ull};
+  unsigned long long rng_off = 0, pool_off = 0;
+  float run = 0.0f;
+  int steps_run = 0, tstep = 0, done_flag = 0;
+  if (lead) {
+    if (R.rng_state) {
+      rh = *reinterpret_cast<const RngHeader *>(R.rng_state);
+      rng_off = rng_offsets(R.rng_state)[env];
     }
-    // ---- policy forward (fully_connected.py:51-89): Linear + ReLU hidden layers, softmax head
-    float *cur = xa, *nxt = xb;
+    if (R.pool_rng) {
+      ph = *reinterpret_cast<const RngHeader *>(R.pool_rng);
+      pool_off = rng_offsets(R.pool_rng)[env];
+    }
+    run = R.reward_running_sum ? R.reward_running_sum[env] : 0.0f;
+    steps_run = R.step_running_sum ? R.step_running_sum[env] : 0;
+    tstep = R.env_timestep[env];
+    done_flag = R.done[env];
+  }
+
+  for (int t = 0; t < R.n_steps; t++) {
+    // ---- observation -> activation row 0 and batch slot t (model_base.py:181-200)
+    {
+      const float *obs = R.observations + (size_t)env * F;
+      float *ob = R.obs_batch ? R.obs_batch + ((size_t)t * E + env) * F : nullptr;
+      for (int i = sub; i < F; i += kSaGroup) {
+        const float x = obs[i];
+        buf0[i] = x;
+        if (ob && live) ob[i] = x;
+      }
+    }
+    __syncwarp();
+    // ---- policy forward (fully_connected.py:51-89): Linear + ReLU hidden layers, linear head
+    float *cur = buf0, *nxt = buf1;
     int off = 0;
     for (int l = 0; l < n_layers; l++) {
       const int in = R.dims[l], out = R.dims[l + 1];
-      const float *Wl = s_w + off, *bl = Wl + in * out;
-      for (int j = 0; j < out; j++) {
+      const float *Wt = s_w + off, *bl = Wt + in * out;
+      for (int j = sub; j < out; j += kSaGroup) {
         float acc = bl[j];
-        const float *wr = Wl + j * in;
-        for (int i = 0; i < in; i++) acc = fmaf(wr[i], cur[i], acc);
+        for (int i = 0; i < in; i++) acc = fmaf(Wt[i * out + j], cur[i], acc);
         nxt[j] = (l < n_layers - 1) ? fmaxf(acc, 0.0f) : acc;
       }
       off += in * out + out;
+      __syncwarp();
       float *tmp = cur; cur = nxt; nxt = tmp;
     }
-    // softmax over the A logits in cur[] (torch.softmax: subtract the max, exp, normalise)
-    float mx = cur[0];
-    for (int i = 1; i < A; i++) mx = fmaxf(mx, cur[i]);
-    float z = 0.0f;
-    for (int i = 0; i < A; i++) { cur[i] = expf(cur[i] - mx); z += cur[i]; }
-    for (int i = 0; i < A; i++) cur[i] = cur[i] / z;
-    if (R.probs_batch) {
-      float *pb = R.probs_batch + ((size_t)t * E + env) * A;
-      for (int i = 0; i < A; i++) pb[i] = cur[i];
-    }
-    // ---- categorical sample (core/random.cu:51-85): u in (0, 1], float32 CDF, binary search
-    float u;
-    if (R.uniforms) {
-      u = R.uniforms[(size_t)t * E + env];
-    } else {
-      u = u32_to_uniform(rng_draw4(rh, (unsigned long long)env, rng_off).x);
-      rng_off++;
-    }
-    int action;
-    if (R.use_argmax) {
-      action = 0;
-      float best = cur[0];
-      for (int i = 1; i < A; i++) if (best < cur[i]) { best = cur[i]; action = i; }
-    } else {
-      float c = cur[0];
-      for (int i = 1; i < A; i++) { c = cur[i] + c; cur[i] = c; }
-      action = sa_search(cur, u, A - 1);
-    }
-    R.sampled_actions[env] = action;
-    if (R.actions_batch) R.actions_batch[(size_t)t * E + env] = action;
-
-    // ---- env step: the stand-alone step kernels' own physics functions
-    tstep += 1;
-    float reward = 0.0f;
-    int terminated = 0, done_code = 0;
-    float *st = R.state + (size_t)env * S;
-    float *ow = R.observations + (size_t)env * F;
-    if (R.env_kind == WDB_SA_CARTPOLE) {
-      const float *p = R.env_params;      // gravity, masspole, total_mass, length,
-      const float4 n = cartpole_physics(*reinterpret_cast<const float4 *>(st), action, p[0], p[1],
-                                        p[2], p[3], p[4], p[5], p[6]);   // polemass_length,
-      *reinterpret_cast<float4 *>(st) = n;                               // force_mag, tau,
-      *reinterpret_cast<float4 *>(ow) = n;                               // theta_thr, x_thr
-      terminated = cartpole_terminated(n, p[7], p[8]) ? 1 : 0;
-      reward = 1.0f;
-      done_code = (tstep == R.episode_length || terminated) ? 1 : 0;
-    } else if (R.env_kind == WDB_SA_MOUNTAIN_CAR) {
-      const float *p = R.env_params;      // min_position, max_position, max_speed,
-      const float2 n = mountain_car_physics(*reinterpret_cast<const float2 *>(st), action, p[0],
-                                            p[1], p[2], p[3], p[4], p[5], p[6], &terminated);
-      *reinterpret_cast<float2 *>(st) = n;     // goal_position, goal_velocity, force, gravity
-      *reinterpret_cast<float2 *>(ow) = n;
-      reward = -1.0f;
-      done_code = (tstep == R.episode_length) ? 1 : (terminated ? 2 : 0);   // :66-70
-    } else {                              // WDB_SA_ACROBOT
-      float o6[6];
-      *reinterpret_cast<float4 *>(st) =
-          acrobot_physics(*reinterpret_cast<const float4 *>(st), action, o6, &reward, &terminated);
-#pragma unroll
-      for (int i = 0; i < 6; i++) ow[i] = o6[i];
-      done_code = (tstep == R.episode_length || terminated) ? 1 : 0;
-    }
-    R.rewards[env] = reward;
-    // the reference's done flag is sticky until a reset clears it
-    if (done_code) done_flag = done_code;
-
-    // ---- bookkeeping (trainer_base.py:514-601): batch slots, running episodic sums
-    if (R.rewards_batch) R.rewards_batch[(size_t)t * E + env] = reward;
-    if (R.done_batch) R.done_batch[(size_t)t * E + env] = done_flag;
-    run += reward;
-    steps_run += 1;
-    if (done_flag > 0) {
-      if (R.episodic_reward_sum) atomicAdd(R.episodic_reward_sum, run);
-      if (R.episodic_step_sum) atomicAdd(R.episodic_step_sum, (unsigned long long)steps_run);
-      if (R.num_completed) atomicAdd(R.num_completed, 1ull);
-      run = 0.0f;
-      steps_run = 0;
-    }
-
-    // ---- done-masked reset (core/reset.cu:9-75, pool_reset.py:15-52)
-    if (done_flag > 0 && R.reset_done_envs) {
-      int n_pool = 0;
-      for (int arr = 0; arr < R.n_reset_arrays; arr++) {
-        const wdb_reset_desc d = R.reset_table[arr];
-        const long long words = d.bytes_per_env >> 2;
-        long long src_row = env;
-        if (d.pool_rows > 0) {
-          const float pr = u32_to_uniform(
-              rng_draw4(ph, (unsigned long long)env, pool_off + n_pool).x);
-          long long row = (long long)(pr * (float)d.pool_rows);
-          if (row >= d.pool_rows) row = d.pool_rows - 1;
-          src_row = row;
-          n_pool++;
-        }
-        uint32_t *dst = reinterpret_cast<uint32_t *>(
-            reinterpret_cast<char *>(d.dst) + (long long)env * d.bytes_per_env);
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(
-            reinterpret_cast<const char *>(d.ref) + src_row * d.bytes_per_env);
-        for (long long i = 0; i < words; i++) dst[i] = src[i];
+    if (lead) {
+      // softmax over the A logits in cur[] (torch.softmax: subtract the max, exp, normalise)
+      float mx = cur[0];
+      for (int i = 1; i < A; i++) mx = fmaxf(mx, cur[i]);
+      float z = 0.0f;
+      for (int i = 0; i < A; i++) { cur[i] = expf(cur[i] - mx); z += cur[i]; }
+      for (int i = 0; i < A; i++) cur[i] = cur[i] / z;
+      if (R.probs_batch) {
+        float *pb = R.probs_batch + ((size_t)t * E + env) * A;
+        for (int i = 0; i < A; i++) pb[i] = cur[i];
       }
-      pool_off += n_pool;
-      done_flag = 0;
-      tstep = 0;
+      // ---- categorical sample (core/random.cu:51-85): u in (0, 1], float32 CDF, binary search
+      float u;
+      if (R.uniforms) {
+        u = R.uniforms[(size_t)t * E + env];
+      } else {
+        u = u32_to_uniform(rng_draw4(rh, (unsigned long long)env, rng_off).x);
+        rng_off++;
+      }
+      int action;
+      if (R.use_argmax) {
+        action = 0;
+        float best = cur[0];
+        for (int i = 1; i < A; i++) if (best < cur[i]) { best = cur[i]; action = i; }
+      } else {
+        float c = cur[0];
+        for (int i = 1; i < A; i++) { c = cur[i] + c; cur[i] = c; }
+        action = sa_search(cur, u, A - 1);
+      }
+      R.sampled_actions[env] = action;
+      if (R.actions_batch) R.actions_batch[(size_t)t * E + env] = action;
+
+      // ---- env step: the stand-alone step kernels' own physics functions
+      tstep += 1;
+      float reward = 0.0f;
+      int terminated = 0, done_code = 0;
+      float *st = R.state + (size_t)env * S;
+      float *ow = R.observations + (size_t)env * F;
+      if (R.env_kind == WDB_SA_CARTPOLE) {
+        const float *p = R.env_params;      // gravity, masspole, total_mass, length,
+        const float4 n = cartpole_physics(*reinterpret_cast<const float4 *>(st), action, p[0],
+                                          p[1], p[2], p[3], p[4], p[5], p[6]);
+        *reinterpret_cast<float4 *>(st) = n;     // polemass_length, force_mag, tau,
+        *reinterpret_cast<float4 *>(ow) = n;     // theta_threshold_radians, x_threshold
+        terminated = cartpole_terminated(n, p[7], p[8]) ? 1 : 0;
+        reward = 1.0f;
+        done_code = (tstep == R.episode_length || terminated) ? 1 : 0;
+      } else if (R.env_kind == WDB_SA_MOUNTAIN_CAR) {
+        const float *p = R.env_params;      // min_position, max_position, max_speed,
+        const float2 n = mountain_car_physics(*reinterpret_cast<const float2 *>(st), action, p[0],
+                                              p[1], p[2], p[3], p[4], p[5], p[6], &terminated);
+        *reinterpret_cast<float2 *>(st) = n;     // goal_position, goal_velocity, force, gravity
+        *reinterpret_cast<float2 *>(ow) = n;
+        reward = -1.0f;
+        done_code = (tstep == R.episode_length) ? 1 : (terminated ? 2 : 0);   // :66-70
+      } else {                              // WDB_SA_ACROBOT
+        float o6[6];
+        *reinterpret_cast<float4 *>(st) = acrobot_physics(*reinterpret_cast<const float4 *>(st),
+                                                          action, o6, &reward, &terminated);
+#pragma unroll
+        for (int i = 0; i < 6; i++) ow[i] = o6[i];
+        done_code = (tstep == R.episode_length || terminated) ? 1 : 0;
+      }
+      R.rewards[env] = reward;
+      // the reference's done flag is sticky until a reset clears it
+      if (done_code) done_flag = done_code;
+
+      // ---- bookkeeping (trainer_base.py:514-601): batch slots, running episodic sums
+      if (R.rewards_batch) R.rewards_batch[(size_t)t * E + env] = reward;
+      if (R.done_batch) R.done_batch[(size_t)t * E + env] = done_flag;
+      run += reward;
+      steps_run += 1;
+      if (done_flag > 0) {
+        if (R.episodic_reward_sum) atomicAdd(R.episodic_reward_sum, run);
+        if (R.episodic_step_sum) atomicAdd(R.episodic_step_sum, (unsigned long long)steps_run);
+        if (R.num_completed) atomicAdd(R.num_completed, 1ull);
+        run = 0.0f;
+        steps_run = 0;
+      }
+
+      // ---- done-masked reset (core/reset.cu:9-75, pool_reset.py:15-52)
+      if (done_flag > 0 && R.reset_done_envs) {
+        int n_pool = 0;
+        for (int arr = 0; arr < R.n_reset_arrays; arr++) {
+          const wdb_reset_desc d = R.reset_table[arr];
+          const long long words = d.bytes_per_env >> 2;
+          long long src_row = env;
+          if (d.pool_rows > 0) {
+            const float pr = u32_to_uniform(
+                rng_draw4(ph, (unsigned long long)env, pool_off + n_pool).x);
+            long long row = (long long)(pr * (float)d.pool_rows);
+            if (row >= d.pool_rows) row = d.pool_rows - 1;
+            src_row = row;
+            n_pool++;
+          }
+          uint32_t *dst = reinterpret_cast<uint32_t *>(
+              reinterpret_cast<char *>(d.dst) + (long long)env * d.bytes_per_env);
+          const uint32_t *src = reinterpret_cast<const uint32_t *>(
+              reinterpret_cast<const char *>(d.ref) + src_row * d.bytes_per_env);
+          for (long long i = 0; i < words; i++) dst[i] = src[i];
+        }
+        pool_off += n_pool;
+        done_flag = 0;
+        tstep = 0;
+      }
     }
-    // the state / observation rows are re-read from global memory next timestep (the reset
-    // may have rewritten them through another pointer type)
-    asm volatile("" ::: "memory");
+    // the group's other lanes read the observation row lane 0 just wrote (global memory)
+    __threadfence_block();
+    __syncwarp();
   }
-  R.env_timestep[env] = tstep;
-  R.done[env] = done_flag;
-  if (R.rng_state && !R.uniforms) rng_offsets(R.rng_state)[env] = rng_off;
-  if (R.pool_rng) rng_offsets(R.pool_rng)[env] = pool_off;
-  if (R.reward_running_sum) R.reward_running_sum[env] = run;
-  if (R.step_running_sum) R.step_running_sum[env] = steps_run;
+  if (lead) {
+    R.env_timestep[env] = tstep;
+    R.done[env] = done_flag;
+    if (R.rng_state && !R.uniforms) rng_offsets(R.rng_state)[env] = rng_off;
+    if (R.pool_rng) rng_offsets(R.pool_rng)[env] = pool_off;
+    if (R.reward_running_sum) R.reward_running_sum[env] = run;
+    if (R.step_running_sum) R.step_running_sum[env] = steps_run;
+  }
 }
 
 }  // namespace
@@ -252,7 +286,7 @@ WDB_API int wdb_single_agent_rollout(void *stream, const wdb_sa_rollout *r) {
   long long total = 0;
   for (int l = 0; l <= r->n_hidden; l++)
     total += (long long)r->dims[l] * r->dims[l + 1] + r->dims[l + 1];
-  const size_t smem = (size_t)total * sizeof(float);
+  const size_t smem = ((size_t)total + (size_t)kSaEnvsPerCta * 2 * kSaPitch) * sizeof(float);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(sa_rollout_kernel,
@@ -260,7 +294,7 @@ WDB_API int wdb_single_agent_rollout(void *stream, const wdb_sa_rollout *r) {
     if (e != cudaSuccess) return (int)e;
     configured = smem;
   }
-  const int grid = (r->n_envs + kSaThreads - 1) / kSaThreads;
+  const int grid = (r->n_envs + kSaEnvsPerCta - 1) / kSaEnvsPerCta;
   sa_rollout_kernel<<<grid, kSaThreads, smem, as_stream(stream)>>>(*r);
   return finish_launch();
 }

@@ -58,8 +58,9 @@ struct WideParams {
   int nbins;        // x-bins (power of two <= 64); bin `nbins` holds the dead agents
   int npad;         // sorted planes length: round_up(N, 16), all +inf behind the alive agents
   int sw;           // staging row pitch in floats (odd)
-  int fpp;          // feature planes per staging pass (7: one pass ... 2: four passes)
-  int o_idcol;      // byte offset of the id columns inside a warp's scratch (stage follows)
+  int fpp;          // feature planes per staging pass (7: one pass ... 1: seven passes)
+  int o_idcol;      // byte offset of the id columns inside a warp's scratch
+  int o_rowptr;     // ... of the 32 x 2 destination row pointers (the staging rows follow)
   int use_window;   // 0: scan every alive agent (A/B switch)
   // byte offsets into dynamic shared memory (identical in every CTA: DSMEM addressing)
   int o_pos, o_sp, o_acc, o_dir, o_alive, o_cross, o_type, o_kx, o_ky, o_sid, o_tag,
@@ -661,6 +662,15 @@ tc_wide_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Fused
     }
     const float spa = ssp[a2], acca = sacc[a2], dira = sdir[a2];
     const bool unit_v = (vnorm == 1.0f);
+    // destination rows of the warp's 32 agents, once, in the warp's scratch (read back as
+    // broadcasts by the copy-out loops) + who is there / alive as ballot masks
+    float **rowptr = reinterpret_cast<float **>(s_scr + W.o_rowptr);
+    rowptr[2 * lane] = dst_obs;
+    rowptr[2 * lane + 1] = dst_pol;
+    const unsigned have_mask = __ballot_sync(full, have);
+    const unsigned alive_mask = __ballot_sync(full, alive);
+    const int n_rows = __popc(have_mask);          // `have` lanes are a prefix of the warp
+    __syncwarp();
 #pragma unroll 1
     for (int f_lo = 0; f_lo < 7; f_lo += W.fpp) {
       const int f_hi = min(7, f_lo + W.fpp);
@@ -668,38 +678,34 @@ tc_wide_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Fused
       const int c0 = f_lo * K;
       const int width = (f_hi - f_lo) * K + (last ? 1 : 0);
       if (alive) {
-        for (int p = 0; p < K; p++) {
-          const bool valid = p < kk;
-          int b = 0;
-          if (valid) {
-            b = net_ok ? (int)idcol[p * kWarp] : nn[p];
-            if (f_lo == 0 && net_ok) nn[p] = b;                           // :202-211
-          }
-          float *col = srow + p;
-          for (int f = f_lo; f < f_hi; f++) {                              // :214-250
-            float v = 0.0f;
-            if (valid) {
-              if (f == 0) v = div_by_const_f64(pos[b].x - pa.x, diag, inv_diag);
-              else if (f == 1) v = div_by_const_f64(pos[b].y - pa.y, diag, inv_diag);
-              else if (f == 2) { const float d = ssp[b] - spa; v = unit_v ? d : d / vnorm; }
-              else if (f == 3) { const float d = sacc[b] - acca; v = unit_v ? d : d / vnorm; }
-              else if (f == 4) v = div_by_two_pi(sdir[b] - dira, two_pi, inv_two_pi);
-              else if (f == 5) v = stype[b];
-              else v = salive[b];
-            }
-            col[(f - f_lo) * K] = v;
-          }
+        // one straight loop over the neighbours per feature plane of this pass (:214-250)
+#define WDB_PLANE(FI, EXPR)                                                         \
+        if (f_lo <= FI && FI < f_hi) {                                              \
+          float *col = srow + (FI - f_lo) * K;                                      \
+          for (int p = 0; p < K; p++) {                                             \
+            float v = 0.0f;                                                         \
+            if (p < kk) {                                                           \
+              const int b = net_ok ? (int)idcol[p * kWarp] : nn[p];                 \
+              if (FI == 0 && net_ok) nn[p] = b;                 /* :202-211 */      \
+              v = EXPR;                                                             \
+            }                                                                       \
+            col[p] = v;                                                             \
+          }                                                                         \
         }
+        WDB_PLANE(0, div_by_const_f64(pos[b].x - pa.x, diag, inv_diag))
+        WDB_PLANE(1, div_by_const_f64(pos[b].y - pa.y, diag, inv_diag))
+        WDB_PLANE(2, (unit_v ? ssp[b] - spa : (ssp[b] - spa) / vnorm))
+        WDB_PLANE(3, (unit_v ? sacc[b] - acca : (sacc[b] - acca) / vnorm))
+        WDB_PLANE(4, div_by_two_pi(sdir[b] - dira, two_pi, inv_two_pi))
+        WDB_PLANE(5, (float)stype[b])
+        WDB_PLANE(6, (float)salive[b])
+#undef WDB_PLANE
         if (last) srow[(7 - f_lo) * K] = static_cast<float>(t_env) / P.episode_length;  // :251-253
       }
       __syncwarp();
-      for (int r = 0; r < kWarp; r++) {
-        const bool r_have = __shfl_sync(full, (int)have, r) != 0;
-        if (!r_have) break;                       // `have` lanes are a prefix of the warp
-        const bool r_alive = __shfl_sync(full, (int)alive, r) != 0;
-        const unsigned long long d0 = __shfl_sync(full, (unsigned long long)dst_obs, r);
-        const unsigned long long d1 = __shfl_sync(full, (unsigned long long)dst_pol, r);
-        float *o0 = reinterpret_cast<float *>(d0), *o1 = reinterpret_cast<float *>(d1);
+      for (int r = 0; r < n_rows; r++) {
+        const bool r_alive = (alive_mask >> r) & 1u;
+        float *o0 = rowptr[2 * r], *o1 = rowptr[2 * r + 1];
         const float *src = stage + r * SW;
         for (int c = lane; c < width; c += kWarp) {
           const float v = r_alive ? src[c] : 0.0f;    // dead agents: an all-zero row (:121-139)
@@ -947,11 +953,11 @@ int tc_wide_launch(TcParams &P, const FusedParams *Qp, int blocks_per_env, cudaS
   int want_ctas = 1024 / block;
   if (want_ctas < 1) want_ctas = 1;
   if (want_ctas > 8) want_ctas = 8;
-  static const int kFpp[4] = {7, 4, 3, 2};
+  static const int kFpp[5] = {7, 4, 3, 2, 1};
   bool fits = false;
   for (; want_ctas >= 1 && !fits; want_ctas--) {
     const size_t budget = (size_t)(227 * 1024) / want_ctas - 1024;
-    for (int t = 0; t < 4 && !fits; t++) {
+    for (int t = 0; t < 5 && !fits; t++) {
       const int fpp = g_tc_wide_fpp ? g_tc_wide_fpp : kFpp[t];
       int width = 1;                       // widest pass: planes x K (+ the time column)
       for (int f_lo = 0; f_lo < 7; f_lo += fpp) {
@@ -978,7 +984,8 @@ int tc_wide_launch(TcParams &P, const FusedParams *Qp, int blocks_per_env, cudaS
       W.o_rightmin = take(4 * (NB1 + 1)); W.o_misc = take(4 * M_COUNT);
       W.o_tab = take(4 * (Qp ? Qp->A0 + Qp->A1 : 1));
       W.o_idcol = 0;
-      W.stage_warp_bytes = align_up(id_bytes, 16);          // offset of the staging rows
+      W.o_rowptr = align_up(id_bytes, 16);
+      W.stage_warp_bytes = W.o_rowptr + 32 * 2 * 8;          // offset of the staging rows
       int stage_bytes = 4 * 32 * sw;
       if (P.use_full_obs && !Qp) stage_bytes = 16;
       int region = W.stage_warp_bytes + stage_bytes;
