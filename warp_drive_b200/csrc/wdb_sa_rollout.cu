@@ -64,10 +64,13 @@ __device__ __forceinline__ int sa_search(const float *cdf, float p, int r) {
 __global__ void __launch_bounds__(kSaThreads)
 sa_rollout_kernel(const __grid_constant__ wdb_sa_rollout R) {
   extern __shared__ float s_w[];               // per layer: [Wt (in x out) | b (out)]
+  __shared__ int s_dims[8];                    // layer widths (dynamic indexing of the kernel
+  if (threadIdx.x < 5) s_dims[threadIdx.x] = R.dims[threadIdx.x];   // parameter goes through
+  __syncthreads();                             // local memory: do it once)
   const int n_layers = R.n_hidden + 1;
   int w_floats = 0;
   for (int l = 0; l < n_layers; l++) {
-    const int in = R.dims[l], out = R.dims[l + 1];
+    const int in = s_dims[l], out = s_dims[l + 1];
     for (int i = threadIdx.x; i < in * out; i += blockDim.x) {
       const int j = i / in, k = i - j * in;    // W[j][k] (nn.Linear: [out, in]) -> Wt[k][j]
       s_w[w_floats + k * out + j] = R.w[l][i];
@@ -83,7 +86,7 @@ sa_rollout_kernel(const __grid_constant__ wdb_sa_rollout R) {
   const bool live = env_raw < R.n_envs;
   const int env = live ? env_raw : R.n_envs - 1;
   const bool lead = live && sub == 0;
-  const int E = R.n_envs, F = R.dims[0], A = R.dims[n_layers], S = R.state_dim;
+  const int E = R.n_envs, F = s_dims[0], A = s_dims[n_layers], S = R.state_dim;
   float *buf0 = s_act + (env_local * 2 + 0) * kSaPitch;
   float *buf1 = s_act + (env_local * 2 + 1) * kSaPitch;
 
@@ -122,12 +125,29 @@ sa_rollout_kernel(const __grid_constant__ wdb_sa_rollout R) {
     float *cur = buf0, *nxt = buf1;
     int off = 0;
     for (int l = 0; l < n_layers; l++) {
-      const int in = R.dims[l], out = R.dims[l + 1];
+      const int in = s_dims[l], out = s_dims[l + 1];
       const float *Wt = s_w + off, *bl = Wt + in * out;
-      for (int j = sub; j < out; j += kSaGroup) {
-        float acc = bl[j];
-        for (int i = 0; i < in; i++) acc = fmaf(Wt[i * out + j], cur[i], acc);
-        nxt[j] = (l < n_layers - 1) ? fmaxf(acc, 0.0f) : acc;
+      // this lane's output neurons sub, sub + 8, ... in blocks of four that accumulate side
+      // by side: one broadcast load of x[i] feeds four independent FMA chains (each neuron
+      // still sums bias, w[0] x[0], w[1] x[1], ... in that order)
+      for (int jb = sub; jb < out; jb += 4 * kSaGroup) {
+        const int last = out - 1;                       // clamp: lanes past `out` re-read a valid word
+        const int j0 = jb, j1 = min(jb + kSaGroup, last), j2 = min(jb + 2 * kSaGroup, last),
+                  j3 = min(jb + 3 * kSaGroup, last);
+        float a0 = bl[j0], a1 = bl[j1], a2 = bl[j2], a3 = bl[j3];
+        const float *wr = Wt;
+        for (int i = 0; i < in; i++, wr += out) {
+          const float x = cur[i];
+          a0 = fmaf(wr[j0], x, a0);
+          a1 = fmaf(wr[j1], x, a1);
+          a2 = fmaf(wr[j2], x, a2);
+          a3 = fmaf(wr[j3], x, a3);
+        }
+        const bool hidden = l < n_layers - 1;
+        nxt[j0] = hidden ? fmaxf(a0, 0.0f) : a0;
+        if (jb + kSaGroup < out) nxt[jb + kSaGroup] = hidden ? fmaxf(a1, 0.0f) : a1;
+        if (jb + 2 * kSaGroup < out) nxt[jb + 2 * kSaGroup] = hidden ? fmaxf(a2, 0.0f) : a2;
+        if (jb + 3 * kSaGroup < out) nxt[jb + 3 * kSaGroup] = hidden ? fmaxf(a3, 0.0f) : a3;
       }
       off += in * out + out;
       __syncwarp();

@@ -235,7 +235,9 @@ tc_wide_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Fused
           g1 = Q.probs1[p] + grow * Q.A1;
         }
       }
-      float *row = stage + lane;                    // the staging area is free in this phase
+      // lane-strided CDF row in the warp's scratch (ids / row pointers / staging rows all
+      // come later; the host sizes the scratch for A x 32 floats)
+      float *row = reinterpret_cast<float *>(s_scr) + lane;
       act0 = sample_row_strided(row, g0, Q.A0, u0);
       act1 = sample_row_strided(row, g1, Q.A1, u1);
       if (Q.actions_out) *reinterpret_cast<int2 *>(Q.actions_out + 2ll * gi) = make_int2(act0, act1);
@@ -965,11 +967,7 @@ int tc_wide_launch(TcParams &P, const FusedParams *Qp, int blocks_per_env, cudaS
         const int w = (f_hi - f_lo) * K + (f_hi == 7 ? 1 : 0);
         if (w > width) width = w;
       }
-      int sw = width | 1;
-      if (Qp) {       // the staging rows also hold the lane-strided CDF while sampling
-        if (sw < Qp->A0) sw = Qp->A0 | 1;
-        if (sw < Qp->A1) sw = Qp->A1 | 1;
-      }
+      const int sw = width | 1;
       W.sw = sw; W.fpp = fpp;
       int off = 0;
       auto take = [&](int bytes) { const int o = off; off = align_up(off + bytes, 16); return o; };
@@ -990,6 +988,10 @@ int tc_wide_launch(TcParams &P, const FusedParams *Qp, int blocks_per_env, cudaS
       if (P.use_full_obs && !Qp) stage_bytes = 16;
       int region = W.stage_warp_bytes + stage_bytes;
       if (region < list_bytes) region = list_bytes;
+      if (Qp) {       // the whole scratch holds the lane-strided CDF rows while sampling
+        const int amax = Qp->A0 > Qp->A1 ? Qp->A0 : Qp->A1;
+        if (region < 128 * amax) region = 128 * amax;
+      }
       W.scr_warp_bytes = align_up(region, 16);
       W.o_scr = take(W.scr_warp_bytes * nw);
       W.o_stage = W.o_scr;
