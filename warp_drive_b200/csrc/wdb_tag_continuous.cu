@@ -445,16 +445,19 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
             asm("mov.b64 %0, {%1, %1};" : "=l"(pay2) : "f"(pa.y));
             const uint4 *kx4 = reinterpret_cast<const uint4 *>(kx);
             const uint4 *ky4 = reinterpret_cast<const uint4 *>(ky);
-            float mo_a = CUDART_INF_F, mo_b = CUDART_INF_F;
+            // mark with tau * (1 + 2^-17): everything left OUT of the mask is then farther than
+            // m_out = that inflated threshold, which is the only thing the verification needs
+            // to know about the rest (no running minimum inside the scan)
+            const float tau_m = tau * 1.00000762939453125f;
 #define WDB_SCAN_WORD(W, M)                                                          \
             if (W * 32 < N) {                                                        \
-              scan_16<0>(M, mo_a, mo_b, kx4 + W * 8, ky4 + W * 8, pax2, pay2, tau);  \
+              scan_16_nm<0>(M, kx4 + W * 8, ky4 + W * 8, pax2, pay2, tau_m);         \
               if (W * 32 + 16 < N)                                                   \
-                scan_16<16>(M, mo_a, mo_b, kx4 + W * 8 + 4, ky4 + W * 8 + 4, pax2, pay2, tau); \
+                scan_16_nm<16>(M, kx4 + W * 8 + 4, ky4 + W * 8 + 4, pax2, pay2, tau_m); \
             }
             WDB_SCAN_WORD(0, m0) WDB_SCAN_WORD(1, m1) WDB_SCAN_WORD(2, m2) WDB_SCAN_WORD(3, m3)
 #undef WDB_SCAN_WORD
-            m_out = fminf(mo_a, mo_b);
+            m_out = tau_m;
           }
           WDB_MARK(6)   // scan done
           const int cnt = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
@@ -483,23 +486,21 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
                          | (uint32_t)b;                                             \
     c##i = (hbase + i < cnt) ? key : pad_key;                                       \
   }
-#pragma unroll 1
-            for (int hbase = 0; hbase < kHistCap; hbase += kListLen) {
-              if (hbase >= cnt) break;
+            {
+              const int hbase = 0;
               WDB_REP16(WDB_HKEY)
               WDB_SORT16(c)
-              if (hbase == 0) {
-                r0 = c0; r1 = c1; r2 = c2; r3 = c3; r4 = c4; r5 = c5; r6 = c6; r7 = c7;
-                r8 = c8; r9 = c9; r10 = c10; r11 = c11; r12 = c12; r13 = c13; r14 = c14;
-                r15 = c15;
-              } else {
-                // 17..32 candidates: merge, keeping the 16 smallest (half-cleaner + merger)
-                r0 = min(r0, c15); r1 = min(r1, c14); r2 = min(r2, c13); r3 = min(r3, c12);
-                r4 = min(r4, c11); r5 = min(r5, c10); r6 = min(r6, c9); r7 = min(r7, c8);
-                r8 = min(r8, c7); r9 = min(r9, c6); r10 = min(r10, c5); r11 = min(r11, c4);
-                r12 = min(r12, c3); r13 = min(r13, c2); r14 = min(r14, c1); r15 = min(r15, c0);
-                WDB_BITONIC_MERGE16(r)
-              }
+              r0 = c0; r1 = c1; r2 = c2; r3 = c3; r4 = c4; r5 = c5; r6 = c6; r7 = c7;
+              r8 = c8; r9 = c9; r10 = c10; r11 = c11; r12 = c12; r13 = c13; r14 = c14;
+              r15 = c15;
+            }
+            // candidates 17..32: inserted one at a time (see WDB_INSERT16)
+#pragma unroll 1
+            for (int e = kListLen; e < cnt; e++) {
+              const int b = min((int)lst[e * kWarp], N - 1);
+              const uint32_t key = (__float_as_uint(sqdist(pa.x, pa.y, kx[b], ky[b])) & ~idmask)
+                                   | (uint32_t)b;
+              WDB_INSERT16(r, key)
             }
 #undef WDB_HKEY
             have = true;

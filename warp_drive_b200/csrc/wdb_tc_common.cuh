@@ -338,6 +338,60 @@ __device__ __forceinline__ void scan_16(uint32_t &m, float &mo_a, float &mo_b, c
   scan_pair<BIT0 + 14>(m, mo_a, mo_b, X3.z, X3.w, Y3.z, Y3.w, pax2, pay2, tau);
 }
 
+// The same scan WITHOUT the running minimum of the unmarked candidates: callers that mark with
+// a threshold inflated by 2^-17 know that everything left out is farther than that threshold,
+// which is all the verification needs (9 instead of 11 instructions per candidate pair).
+template <int BIT>
+__device__ __forceinline__ void scan_pair_nm(uint32_t &m, uint32_t x_lo, uint32_t x_hi,
+                                             uint32_t y_lo, uint32_t y_hi,
+                                             unsigned long long pax2, unsigned long long pay2,
+                                             float tau) {
+  asm("{\n\t"
+      ".reg .b64 x2, y2, dx, dy, sq;\n\t"
+      ".reg .f32 lo, hi;\n\t"
+      ".reg .pred p, q;\n\t"
+      "mov.b64 x2, {%1, %2};\n\t"
+      "mov.b64 y2, {%3, %4};\n\t"
+      "sub.f32x2 dx, %5, x2;\n\t"
+      "sub.f32x2 dy, %6, y2;\n\t"
+      "mul.f32x2 sq, dx, dx;\n\t"
+      "fma.rn.f32x2 sq, dy, dy, sq;\n\t"
+      "mov.b64 {lo, hi}, sq;\n\t"
+      "setp.le.f32 p, lo, %7;\n\t"
+      "setp.le.f32 q, hi, %7;\n\t"
+      "@p or.b32 %0, %0, %8;\n\t"
+      "@q or.b32 %0, %0, %9;\n\t"
+      "}"
+      : "+r"(m)
+      : "r"(x_lo), "r"(x_hi), "r"(y_lo), "r"(y_hi), "l"(pax2), "l"(pay2), "f"(tau),
+        "n"(1u << BIT), "n"(2u << BIT));
+}
+template <int BIT0>
+__device__ __forceinline__ void scan_16_nm(uint32_t &m, const uint4 *kx4, const uint4 *ky4,
+                                           unsigned long long pax2, unsigned long long pay2,
+                                           float tau) {
+  const uint4 X0 = kx4[0], Y0 = ky4[0], X1 = kx4[1], Y1 = ky4[1];
+  const uint4 X2 = kx4[2], Y2 = ky4[2], X3 = kx4[3], Y3 = ky4[3];
+  scan_pair_nm<BIT0 + 0>(m, X0.x, X0.y, Y0.x, Y0.y, pax2, pay2, tau);
+  scan_pair_nm<BIT0 + 2>(m, X0.z, X0.w, Y0.z, Y0.w, pax2, pay2, tau);
+  scan_pair_nm<BIT0 + 4>(m, X1.x, X1.y, Y1.x, Y1.y, pax2, pay2, tau);
+  scan_pair_nm<BIT0 + 6>(m, X1.z, X1.w, Y1.z, Y1.w, pax2, pay2, tau);
+  scan_pair_nm<BIT0 + 8>(m, X2.x, X2.y, Y2.x, Y2.y, pax2, pay2, tau);
+  scan_pair_nm<BIT0 + 10>(m, X2.z, X2.w, Y2.z, Y2.w, pax2, pay2, tau);
+  scan_pair_nm<BIT0 + 12>(m, X3.x, X3.y, Y3.x, Y3.y, pax2, pay2, tau);
+  scan_pair_nm<BIT0 + 14>(m, X3.z, X3.w, Y3.z, Y3.w, pax2, pay2, tau);
+}
+
+// Insert one key into the ascending named-register list v0..v15, dropping the largest:
+// 16 (min, max) pairs.  A handful of candidates beyond 16 cost far less this way than a second
+// 16-key sort + bitonic merge -- which a warp used to run whenever ANY of its lanes overflowed.
+#define WDB_INS1(V, i) { const uint32_t lo_ = min(V##i, nk_); nk_ = max(V##i, nk_); V##i = lo_; }
+#define WDB_INSERT16(V, KEY)                                                        \
+  { uint32_t nk_ = (KEY);                                                           \
+    WDB_INS1(V, 0) WDB_INS1(V, 1) WDB_INS1(V, 2) WDB_INS1(V, 3) WDB_INS1(V, 4) WDB_INS1(V, 5)   \
+    WDB_INS1(V, 6) WDB_INS1(V, 7) WDB_INS1(V, 8) WDB_INS1(V, 9) WDB_INS1(V, 10) WDB_INS1(V, 11) \
+    WDB_INS1(V, 12) WDB_INS1(V, 13) WDB_INS1(V, 14) WDB_INS1(V, 15) }
+
 // MAXT = 320: the common geometry (EPB * N <= 320 threads, two CTAs per SM, <= 96
 // registers per thread); MAXT = 1024: one env of up to 1024 agents per CTA.
 // Branch-free top-16 of ALL candidates (packed squared-distance | id keys), 16 at a time:
