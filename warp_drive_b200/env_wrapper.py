@@ -179,11 +179,42 @@ class EnvWrapper:
         assert self.env_backend != "cpu"
         dm = self.cuda_data_manager
         cur = torch.cuda.current_stream()
-        dm.data_on_device_via_torch("sampled_actions").copy_(host_actions, non_blocking=True)
-        self.env.step()
         if not hasattr(self, "_copy_streams") or len(self._copy_streams) < n_copy_streams:
             self._copy_streams = [torch.cuda.Stream() for _ in range(n_copy_streams)]
             self._copy_events = [torch.cuda.Event() for _ in range(n_copy_streams)]
+        actions_d = dm.data_on_device_via_torch("sampled_actions")
+        E = self.n_envs
+        total = sum(dm.data_on_device_via_torch(k).numel() * dm.data_on_device_via_torch(k)
+                    .element_size() for k in host_out)
+        if (hasattr(self.env, "step_env_range") and n_copy_streams > 1 and E >= n_copy_streams
+                and total >= min_split_bytes
+                and all(dm.data_on_device_via_torch(k).shape[0] == E for k in host_out)):
+            # env replicas are independent: group g's actions go up, its envs step and its
+            # results come down on stream g, so the copies of one group overlap the step of
+            # the next (the PCIe link stays busy while the SMs work)
+            ready = torch.cuda.Event()
+            ready.record(cur)
+            per = -(-E // n_copy_streams)
+            for g in range(n_copy_streams):
+                e0, e1 = g * per, min(E, (g + 1) * per)
+                if e0 >= e1:
+                    continue
+                st = self._copy_streams[g]
+                st.wait_event(ready)
+                with torch.cuda.stream(st):
+                    actions_d[e0:e1].copy_(host_actions[e0:e1], non_blocking=True)
+                    self.env.step_env_range(e0, e1)
+                    for name, host in host_out.items():
+                        host[e0:e1].copy_(dm.data_on_device_via_torch(name)[e0:e1],
+                                          non_blocking=True)
+                self._copy_events[g].record(st)
+            self.env.timestep += 1
+            for ev in self._copy_events[:n_copy_streams]:
+                cur.wait_event(ev)
+            cur.synchronize()
+            return
+        actions_d.copy_(host_actions, non_blocking=True)
+        self.env.step()
         stepped = torch.cuda.Event()
         stepped.record(cur)
         for name, host in host_out.items():

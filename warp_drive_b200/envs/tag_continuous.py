@@ -36,6 +36,13 @@ _STEP_ARGS = [
 ]
 
 
+# arguments of the device step that carry one row per env replica
+_PER_ENV_ARGS = {"loc_x", "loc_y", "speed", "direction", "acceleration",
+                 "edge_hit_reward_penalty", "still_in_the_game", _OBSERVATIONS, _ACTIONS,
+                 "neighbor_distances", "neighbor_ids_sorted_by_distance", "nearest_neighbor_ids",
+                 _REWARDS, "num_runners", "_done_", "_timestep_"}
+
+
 class TagContinuous(CUDAEnvironmentContext):
     name = "TagContinuous"
 
@@ -345,6 +352,28 @@ class TagContinuous(CUDAEnvironmentContext):
         return d
 
     # ------------------------------------------------------------------ step
+    def step_env_range(self, e0, e1):
+        """Device step of the env replicas [e0, e1) only, on the current stream (replicas are
+        independent; the caller accounts for `timestep`).  Used by
+        EnvWrapper.step_with_host_buffers to overlap the host copies of one group of envs with
+        the step of the next."""
+        dm = self.cuda_data_manager
+        n_all = int(dm.meta_info("n_envs"))
+        assert 0 <= e0 < e1 <= n_all and self.env_backend != "cpu"
+        args = []
+        for arg in _STEP_ARGS:
+            if isinstance(arg, tuple):
+                args.append(dm.meta_info(arg[0]))
+            elif arg in ("neighbor_distances", "neighbor_ids_sorted_by_distance") and \
+                    not self.allocate_reference_scratch:
+                args.append(None)
+            elif arg in _PER_ENV_ARGS:
+                args.append(dm.data_on_device_via_torch(arg)[e0:e1])
+            else:
+                args.append(dm.device_data(arg))
+        self.cuda_step(*args, block=self.cuda_function_manager.block,
+                       grid=self.cuda_function_manager.grid, n_envs=e1 - e0)
+
     def step(self, actions=None):
         self.timestep += 1
         if self.env_backend != "cpu":

@@ -40,12 +40,15 @@ def _stream():
 # ------------------------------------------------------------------------------ adapters
 # Each adapter receives the reference kernel's positional arguments.
 
-def _k_tag_continuous_step(fm, a, block, grid):
+def _k_tag_continuous_step(fm, a, block, grid, n_envs=None):
     # CudaTagContinuousStep(...) -- tag_continuous_step_pycuda.cu:351-385
+    # n_envs: step only that many replicas (the per-env arrays passed are slices: env replicas
+    # are independent, EnvWrapper.step_with_host_buffers pipelines groups of them)
     assert len(a) == 33, f"CudaTagContinuousStep takes 33 arguments, got {len(a)}"
     L = _libmod.load()
     _libmod.check(L.wdb_tag_continuous_step(
-        _stream(), fm._num_envs, int(_scalar(a[31])), fm._blocks_per_env,
+        _stream(), fm._num_envs if n_envs is None else int(n_envs), int(_scalar(a[31])),
+        fm._blocks_per_env,
         _P(a[0]), _P(a[1]), _P(a[2]), _P(a[3]), _P(a[4]), _P(a[5]), _P(a[6]),
         float(_scalar(a[7])), float(_scalar(a[8])), _P(a[9]), _P(a[10]),
         float(_scalar(a[11])), int(_scalar(a[12])), _P(a[13]), int(_scalar(a[14])),
@@ -239,7 +242,9 @@ class KernelFunction:
         self.name = name
         self._adapter = adapter
 
-    def __call__(self, *args, block=None, grid=None, **_ignored):
+    def __call__(self, *args, block=None, grid=None, n_envs=None, **_ignored):
+        if n_envs is not None:
+            return self._adapter(self._fm, args, block, grid, n_envs=n_envs)
         return self._adapter(self._fm, args, block, grid)
 
     def __getitem__(self, launch_config):
