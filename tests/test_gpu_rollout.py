@@ -231,7 +231,8 @@ def test_step_with_host_buffers_matches_pull():
     for _ in range(4):
         acts = rs.randint(0, 21, tuple(dma.get_shape("sampled_actions"))).astype(np.int32)
         wa.step_with_host_buffers(torch.from_numpy(acts).pin_memory(), host_out, n_copy_streams=3,
-                                  min_split_bytes=1024)   # force the split-copy path
+                                  min_split_bytes=1024,    # force the split-copy path
+                                  pipeline_env_groups=bool(_ % 2))   # and the grouped pipeline
         dmb.data_on_device_via_torch("sampled_actions").copy_(torch.from_numpy(acts))
         wb.step_all_envs()
         for k in names:

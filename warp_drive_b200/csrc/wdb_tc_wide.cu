@@ -705,14 +705,21 @@ tc_wide_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Fused
         if (last) srow[(7 - f_lo) * K] = static_cast<float>(t_env) / P.episode_length;  // :251-253
       }
       __syncwarp();
-      for (int r = 0; r < n_rows; r++) {
-        const bool r_alive = (alive_mask >> r) & 1u;
-        float *o0 = rowptr[2 * r], *o1 = rowptr[2 * r + 1];
-        const float *src = stage + r * SW;
-        for (int c = lane; c < width; c += kWarp) {
-          const float v = r_alive ? src[c] : 0.0f;    // dead agents: an all-zero row (:121-139)
-          if (o0) o0[c0 + c] = v;
-          if (o1) o1[c0 + c] = v;
+      {
+        // copy-out: the lanes walk the n_rows x width elements of this pass linearly (row, col
+        // advance incrementally), so narrow passes keep all 32 lanes busy
+        const int total = n_rows * width;
+        const int drow = kWarp / width, dcol = kWarp - drow * width;
+        int row = lane / width, col = lane - row * width;
+        for (int e = lane; e < total; e += kWarp) {
+          const bool r_alive = (alive_mask >> row) & 1u;
+          float *o0 = rowptr[2 * row], *o1 = rowptr[2 * row + 1];
+          const float v = r_alive ? stage[row * SW + col] : 0.0f;   // dead agents: zero rows
+          if (o0) o0[c0 + col] = v;                                  // (:121-139)
+          if (o1) o1[c0 + col] = v;
+          row += drow;
+          col += dcol;
+          if (col >= width) { col -= width; row++; }
         }
       }
       __syncwarp();

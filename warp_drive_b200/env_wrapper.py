@@ -166,7 +166,7 @@ class EnvWrapper:
         return self.env.step(actions)
 
     def step_with_host_buffers(self, host_actions, host_out, n_copy_streams=4,
-                               min_split_bytes=8 << 20):
+                               min_split_bytes=8 << 20, pipeline_env_groups=False):
         """One env.step() for a HOST-side policy: pinned `host_actions` -> device, step,
         then `observations` / `rewards` / `_done_` -> the pinned tensors in `host_out`
         ({name: pinned CPU tensor}).  The large observation copy is split over
@@ -186,7 +186,11 @@ class EnvWrapper:
         E = self.n_envs
         total = sum(dm.data_on_device_via_torch(k).numel() * dm.data_on_device_via_torch(k)
                     .element_size() for k in host_out)
-        if (hasattr(self.env, "step_env_range") and n_copy_streams > 1 and E >= n_copy_streams
+        # pipeline_env_groups: measured on B200 at config 2 (60 MB of observations per step)
+        # the grouped pipeline is NOT faster than one step + a 4-way split copy (1.29 vs 1.27 ms
+        # per step, and less stable): the PCIe link is the bound either way.  Kept as an option.
+        if (pipeline_env_groups and hasattr(self.env, "step_env_range") and n_copy_streams > 1
+                and E >= n_copy_streams
                 and total >= min_split_bytes
                 and all(dm.data_on_device_via_torch(k).shape[0] == E for k in host_out)):
             # env replicas are independent: group g's actions go up, its envs step and its
