@@ -143,7 +143,7 @@ class ClockSampler:
 
 
 def build_engine(n_envs, seed, graph_steps, use_graph=True, forward_dtype=None,
-                 fused_forward=True, obs_tiles=False):
+                 fused_forward=True, obs_tiles=False, pair_forward=False):
     import torch
 
     from warp_drive_b200.env_wrapper import EnvWrapper
@@ -173,7 +173,8 @@ def build_engine(n_envs, seed, graph_steps, use_graph=True, forward_dtype=None,
     engine = RolloutEngine(wrapper, models, policy_map, sampler, graph_steps,
                            use_cuda_graph=use_graph, forward_dtype=forward_dtype,
                            write_observations=False, stats=stats,
-                           use_fused_forward=fused_forward, use_obs_tiles=obs_tiles)
+                           use_fused_forward=fused_forward, use_obs_tiles=obs_tiles,
+                           use_pair_forward=pair_forward)
     engine.stats = stats
     return wrapper, engine, sampler, policy_map
 
@@ -245,10 +246,11 @@ def time_dominant_kernel(wrapper, engine, iters=30):
                                 obs_next_tiles=engine.obs_tiles or None)
             if i >= 3:
                 ev[i - 3][1].record()
+        wide = active_blocks_per_env() > 1 or engine.env_wrapper.n_agents > 320
         name = ("tag_continuous_kernel<true> (fused sample+step+push+reset)"
-                if active_blocks_per_env() == 1 else
+                if not wide else
                 f"tc_wide_kernel<true> (fused sample+step+push+reset, cluster of "
-                f"{active_blocks_per_env()} CTAs per env)")
+                f"{active_blocks_per_env()} CTA(s) per env)")
         nbytes = BYTES_FUSED
     torch.cuda.synchronize()
     ms = sorted(a.elapsed_time(b) for a, b in ev)
@@ -861,6 +863,11 @@ def main():
     ap.add_argument("--obs-tiles", action="store_true",
                     help="A/B switch: the env step also emits the bf16 MMA-ready copy of the "
                          "observations and the forward reads that (wdb_mlp_policy_forward_tiles)")
+    ap.add_argument("--pair-forward", action="store_true",
+                    help="A/B switch: both policies' forwards in ONE launch "
+                         "(wdb_mlp_policy_forward_pair; add WDB_OPTIONS=pdl=1 for programmatic "
+                         "dependent launches) instead of one launch per policy on two streams; "
+                         "measured slower, see scripts/ab_forward_modes.py")
     ap.add_argument("--copy-streams", type=int, default=4,
                     help="streams the e2e observation D2H copy is split over")
     ap.add_argument("--reps", type=int, default=0,
@@ -911,7 +918,8 @@ def main():
     wrapper, engine, sampler, policy_map = build_engine(
         args.envs, seed=1234 + rank, graph_steps=T, use_graph=not args.no_graph,
         forward_dtype=torch.bfloat16 if args.forward_precision == "bf16" else None,
-        fused_forward=not args.torch_forward, obs_tiles=args.obs_tiles)
+        fused_forward=not args.torch_forward, obs_tiles=args.obs_tiles,
+        pair_forward=args.pair_forward)
     E, N = wrapper.n_envs, wrapper.n_agents
 
     def barrier():
@@ -1069,6 +1077,7 @@ def main():
         "gpu_launches": int(my_launches),
         "kernel_stats": {"exact_tie_path_agents": stats_timed[0], "tags": stats_timed[1],
                          "history_path_fallbacks": stats_timed[2],
+                         "window_network_path_agents": stats_timed[3],
                          "agent_steps": E * N * K * reps,
                          "note": "device counters of the fused kernel over the timed region: "
                                  "agents that needed the exact tie-resolution path"},

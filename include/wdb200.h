@@ -133,7 +133,9 @@ int wdb_tag_gridworld_step(void *stream, int n_envs, int n_agents, int *loc_x,
  * neighbor_distances / neighbor_ids_sorted_by_distance are the reference's O(N^2)
  * global scratch; they may be NULL (the B200 kernel keeps the sweep on chip).
  * stats (optional, device int[4]): [0] += agents that took the exact tie-resolution
- * path, [1] += tags. */
+ * path, [1] += tags, [2] += agents whose threshold scan had no usable candidate list
+ * (full sorting network), [3] += agents whose candidate list overflowed (cluster kernel:
+ * sorting network over the x-window only). */
 int wdb_tag_continuous_step(
     void *stream, int n_envs, int n_agents, int blocks_per_env, float *loc_x,
     float *loc_y, float *speed, float *direction, float *acceleration,
@@ -215,6 +217,12 @@ typedef struct wdb_tc_rollout {
   int n_reset_arrays;
   const float *obs_at_reset;         /* [E, N, F]: source of obs_next for envs that reset */
   int reset_done_envs;               /* 0: leave done envs alone (done stays set) */
+  int launch_after_forward;          /* 1: the kernel launched just before this one on `stream`
+                                      * is this step's policy forward (and the one before that
+                                      * the previous env step): with the "pdl" option on, the
+                                      * launch is programmatically dependent on it -- the state
+                                      * prologue overlaps the forward's tail, the probabilities
+                                      * are read after griddepcontrol.wait.  0: plain launch. */
 } wdb_tc_rollout;
 
 int wdb_tag_continuous_rollout_step(void *stream, const wdb_tc_env *env,
@@ -325,6 +333,25 @@ int wdb_mlp_pack_weights(void *stream, void *blob, const float *w1, const float 
 int wdb_mlp_policy_forward(void *stream, const void *blob, int F, int H, int A0, int A1,
                            const float *obs, long long rows, float *probs0, float *probs1,
                            float *values /* may be NULL */);
+/* Two policies in ONE launch (the rollout of a two-policy env: tag_continuous runners and
+ * taggers): CTAs [0, grid - ctas_b) run policy 0, the last ctas_b CTAs policy 1, each
+ * persistent over its own 128-row tiles.  ctas_b = 0 picks the split from the row counts.
+ * flags: WDB_MLP_WEIGHTS_STABLE = neither blob was written by the kernel launched just before
+ * this one on `stream` (true for every rollout step but the first after a weight re-pack): with
+ * the "pdl" option on, the launch is a programmatic dependent launch and the weight load then
+ * overlaps the tail of that previous kernel. */
+#define WDB_MLP_WEIGHTS_STABLE 1
+typedef struct wdb_mlp_pair {
+  const void *blob[2];
+  int F[2], H[2], A0[2], A1[2];
+  const float *obs[2];
+  long long rows[2];
+  float *probs0[2], *probs1[2], *values[2];   /* values may be NULL */
+  int ctas_b;
+  int flags;
+} wdb_mlp_pair;
+int wdb_mlp_policy_forward_pair(void *stream, const wdb_mlp_pair *pair);
+
 /* The same forward fed from the bf16 copy of the observations in A-operand layout: 128-row
  * tiles, each one contiguous block (canonical K-major layout, K padded to a multiple of 16
  * with zeros) that the kernel fetches with one TMA bulk copy.  wdb_mlp_pack_obs builds it

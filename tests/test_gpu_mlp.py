@@ -162,3 +162,36 @@ def test_single_head_policy_on_the_tensor_cores():
         assert (p0.sum(-1) - 1).abs().max() < 1e-4
         assert (p0 - q0).abs().max().item() < 2e-2
         assert ((v - qv).abs() / (1 + qv.abs())).max().item() < 5e-2
+
+
+@pytest.mark.parametrize("shapes", [((71, 256, 21, 21, 2000 * 100), (71, 256, 21, 21, 2000 * 5)),
+                                    ((71, 256, 21, 21, 300), (36, 64, 21, 21, 5000)),
+                                    ((15, 32, 4, 4, 77), (200, 128, 30, 10, 130))])
+@pytest.mark.parametrize("stable", [False, True])
+def test_pair_forward_equals_two_single_forwards(shapes, stable):
+    """wdb_mlp_policy_forward_pair runs two policies in one grid (CTAs split between them):
+    every CTA executes the same code on the same tiles as in the single launches, so the
+    outputs are IDENTICAL bit for bit; also back to back (programmatic dependent launches
+    overlapping each other's tails) and with a forced split."""
+    from warp_drive_b200.training.models.fused_forward import FusedPolicyForward, forward_pair
+
+    fw, obs, single = [], [], []
+    for i, (F, H, A0, A1, rows) in enumerate(shapes):
+        torch.manual_seed(31 * F + H + i)
+        m = _Model(F, H, A0, A1).cuda()
+        f = FusedPolicyForward(m)
+        o = torch.randn(rows, F, device="cuda")
+        p0 = torch.full((rows, A0), -1.0, device="cuda")
+        p1 = torch.full((rows, A1), -1.0, device="cuda")
+        f(o, p0, p1, None)
+        fw.append(f); obs.append(o); single.append((p0, p1))
+    torch.cuda.synchronize()
+    for ctas_b in (0, 1, 40):
+        outs = [[torch.full_like(t, -2.0) for t in pr] for pr in single]
+        for _ in range(3):      # back-to-back launches: each may start under the previous one
+            forward_pair(fw[0], fw[1], obs[0], obs[1], outs[0], outs[1], ctas_b=ctas_b,
+                         weights_stable=stable)
+        torch.cuda.synchronize()
+        for w in range(2):
+            for k in range(2):
+                assert torch.equal(outs[w][k], single[w][k]), (ctas_b, w, k)

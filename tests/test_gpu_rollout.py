@@ -187,6 +187,40 @@ def test_engine_cuda_graph_matches_eager(fused):
     assert int(ea.num_completed_episodes) == int(eb.num_completed_episodes)
 
 
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_pair_forward_and_programmatic_launches_change_nothing(use_graph):
+    """The optional launch mode (both policies' forwards in ONE launch, forward and env step
+    chained by programmatic dependent launches that overlap each other's head and tail) must
+    fill the batch exactly like the default plain serialised launches with one forward per
+    policy: enough envs that every SM is busy, several rollouts with episode resets in between."""
+    from warp_drive_b200 import lib as wlib
+
+    L = wlib.load()
+    E, T = 3000, 6
+    assert L.wdb_set_option(b"pdl", 1) == 0
+    try:
+        wa, ea, pm = _engine(E, T, use_graph, True, use_pair_forward=True)
+        for _ in range(8):
+            ea.rollout()
+        torch.cuda.synchronize()
+    finally:
+        L.wdb_set_option(b"pdl", 0)
+    wb, eb, _ = _engine(E, T, use_graph, True, use_pair_forward=False)
+    for _ in range(8):
+        eb.rollout()
+    torch.cuda.synchronize()
+    names = ["done_flags_batch"]
+    for p in pm:
+        names += [f"processed_observations_batch_{p}", f"sampled_actions_batch_{p}",
+                  f"rewards_batch_{p}"]
+    names += list(STATE)
+    for name in names:
+        ta = wa.cuda_data_manager.data_on_device_via_torch(name)
+        tb = wb.cuda_data_manager.data_on_device_via_torch(name)
+        assert torch.equal(ta, tb), name
+    assert int(ea.num_completed_episodes) == int(eb.num_completed_episodes) > 0
+
+
 def test_engine_fused_matches_unfused_batches():
     """Fused single-launch timestep vs the generic multi-launch path, same models, same
     RNG seed: identical training batches (both draw u from the same Philox streams:

@@ -79,14 +79,17 @@ def test_wide_1024_agents_vs_oracle(wdb_lib, blocks, tc_history, window):  # noq
         base._BPE = 1
 
 
+@pytest.mark.parametrize("grid", [64.0, 20.0])
 @pytest.mark.parametrize("blocks", [2, 4])
-def test_wide_1024_agents_bit_exact_vs_reference_multiblock(wdb_lib, blocks, tc_history):  # noqa: F811
+def test_wide_1024_agents_bit_exact_vs_reference_multiblock(wdb_lib, blocks, tc_history, grid):  # noqa: F811
     """BASELINE config 4 size against the REFERENCE kernel in its own multi-block mode
     (wkBlocksPerEnv = 2 / 4): bit-equality of state, observations and neighbour ids over a
-    free-running rollout -- no rank-wise tie escape."""
+    free-running rollout -- no rank-wise tie escape.  grid = 20: ten times config 4's agent
+    density, so the candidate list of the threshold scan overflows all the time and the
+    window-limited network path (stats[3]) carries the selection."""
     from oracle import ref_cuda
 
-    E, N, K, n_taggers, grid = 2, 1024, 10, 24, 64.0
+    E, N, K, n_taggers = 2, 1024, 10, 24
     if not ref_cuda.available(E, N, blocks):
         pytest.fail(f"oracle/_ref/ref_E{E}_N{N}_B{blocks}.fatbin was not shipped")
     cfg, st0 = base._tc_synthetic(N, n_taggers, K, E, grid, seed=N)
@@ -125,6 +128,8 @@ def test_wide_1024_agents_bit_exact_vs_reference_multiblock(wdb_lib, blocks, tc_
             b_st["num_runners"].copy_(a_st["num_runners"])
             b_st["_done_"].copy_(a_st["_done_"])
         assert tags > 0
+        if tc_history and grid < 64.0:
+            assert int(stats[3]) > 0, "the window-limited network path never ran"
     finally:
         base._BPE = 1
 

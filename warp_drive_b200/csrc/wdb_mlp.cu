@@ -39,6 +39,13 @@ using namespace wdb;
 namespace {
 
 constexpr int kTileM = 128;
+constexpr int kMlpWeightsStable = 1;   // wdb_mlp_policy_forward_pair flags
+__device__ __forceinline__ void griddep_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void griddep_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 #ifndef WDB_MLP_WORKERS
 #define WDB_MLP_WORKERS 384
 #endif
@@ -228,11 +235,16 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t tmem_lane_base, uint32_
 // padded with zeros -- written by wdb_mlp_pack_obs or by the env-step kernel's epilogue): a
 // tile is then ONE 16-byte-aligned contiguous block that the TMA drops into the staging
 // buffer, and the whole fp32 obs path (4-byte loads, conversion, scatter) disappears.
+// `bid` / `gdim`: this CTA's index and the CTA count of ITS policy (the pair kernel runs two
+// policies side by side in one grid).  flags & kMlpWeightsStable: the weight blob was not
+// written by the grid this launch programmatically depends on, so its TMA load may start
+// before griddepcontrol.wait (see the PDL note at launch_forward_pair).
 template <bool TILES>
-__global__ void __launch_bounds__(kThreads, 1)
-mlp_forward_kernel(const unsigned char *__restrict__ blob, const void *__restrict__ input,
-                   long long rows, float *__restrict__ probs0, float *__restrict__ probs1,
-                   float *__restrict__ values) {
+__device__ __forceinline__ void
+mlp_forward_body(const unsigned char *__restrict__ blob, const void *__restrict__ input,
+                 long long rows, float *__restrict__ probs0, float *__restrict__ probs1,
+                 float *__restrict__ values, const unsigned bid, const unsigned gdim,
+                 const int flags) {
   const float *obs = reinterpret_cast<const float *>(input);
   const unsigned char *tiles = reinterpret_cast<const unsigned char *>(input);
   extern __shared__ __align__(128) unsigned char smem[];
@@ -281,6 +293,10 @@ mlp_forward_kernel(const unsigned char *__restrict__ blob, const void *__restric
   const uint32_t tmem_base = *s_tmem;
   const uint32_t tmem_lane = tmem_base + ((uint32_t)(quad * 32) << 16);   // this warp's lanes
 
+  // Programmatic dependent launch: everything above overlapped the tail of the previous grid
+  // in the stream.  Nothing that grid wrote is read before griddepcontrol.wait; our own
+  // dependents are released only AFTER our wait, so "previous grid complete" is transitive.
+  if (!(flags & kMlpWeightsStable)) griddep_wait();
   if (tid == 0) {                                         // weights: TMA bulk copies
     mbar_expect_tx(bar_w, (uint32_t)w_bytes);
     uint32_t off = 0;
@@ -290,6 +306,9 @@ mlp_forward_kernel(const unsigned char *__restrict__ blob, const void *__restric
       off += n;
     }
   }
+
+  if (flags & kMlpWeightsStable) griddep_wait();
+  griddep_launch_dependents();
 
   const long long n_tiles = (rows + kTileM - 1) / kTileM;
   // A-tile build: a warp task = 8 rows x 4 k-chunks (chunk = 8 consecutive k = one 16-byte
@@ -331,7 +350,7 @@ mlp_forward_kernel(const unsigned char *__restrict__ blob, const void *__restric
       }
     }
   };
-  if (!TILES && single_batch && warp < kWarps && (long long)blockIdx.x < n_tiles) load_batch(blockIdx.x, 0);
+  if (!TILES && single_batch && warp < kWarps && (long long)bid < n_tiles) load_batch(bid, 0);
 
   const uint32_t idesc_h = make_idesc(kTileM, H);
   const uint32_t idesc_o = make_idesc(kTileM, N3);
@@ -359,9 +378,9 @@ mlp_forward_kernel(const unsigned char *__restrict__ blob, const void *__restric
     mbar_wait(bar_w, 0);
     bar_sync(2, kThreads);                                // first A operand in TMEM
     fence_after();
-    if (lane == 0 && (long long)blockIdx.x < n_tiles) issue_l1();
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const bool has_next = tile + gridDim.x < n_tiles;
+    if (lane == 0 && (long long)bid < n_tiles) issue_l1();
+    for (long long tile = bid; tile < n_tiles; tile += gdim) {
+      const bool has_next = tile + gdim < n_tiles;
       bar_sync(2, kThreads);                              // hidden activations of layer 1 packed
       fence_after();
       if (lane == 0) {
@@ -439,11 +458,11 @@ mlp_forward_kernel(const unsigned char *__restrict__ blob, const void *__restric
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     };
 
-    if ((long long)blockIdx.x < n_tiles) {
-      if (TILES) request_tile(blockIdx.x);
-      build_a(blockIdx.x);
-      if (!TILES && single_batch && (long long)blockIdx.x + gridDim.x < n_tiles)
-        load_batch((long long)blockIdx.x + gridDim.x, 0);
+    if ((long long)bid < n_tiles) {
+      if (TILES) request_tile(bid);
+      build_a(bid);
+      if (!TILES && single_batch && (long long)bid + gdim < n_tiles)
+        load_batch((long long)bid + gdim, 0);
     }
     fence_before();
     bar_arrive(2, kThreads);                              // first A operand ready
@@ -521,12 +540,12 @@ mlp_forward_kernel(const unsigned char *__restrict__ blob, const void *__restric
     const bool deferred = overlap_l1;
     uint32_t phase = 0;
     long long prev_tile = -1;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, phase ^= 1) {
-      const bool has_next = tile + gridDim.x < n_tiles;
+    for (long long tile = bid; tile < n_tiles; tile += gdim, phase ^= 1) {
+      const bool has_next = tile + gdim < n_tiles;
       MLP_MARK(0)   // tile start
       if (TILES && has_next) {
         bar_sync(1, kWorkers);                             // everyone is done with the staging buffer
-        request_tile(tile + gridDim.x);                    // lands during epilogue 1 / layer 2
+        request_tile(tile + gdim);                    // lands during epilogue 1 / layer 2
       }
 
       // ---- layer 1 epilogue
@@ -539,7 +558,7 @@ mlp_forward_kernel(const unsigned char *__restrict__ blob, const void *__restric
       MLP_MARK(2)
 
       // ---- while the tensor core runs layer 2: next tile's A operand, previous tile's output
-      if (has_next) build_a(tile + gridDim.x);
+      if (has_next) build_a(tile + gdim);
       MLP_MARK(3)
       if (deferred && prev_tile >= 0) {
         if (!has_next && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -556,8 +575,8 @@ mlp_forward_kernel(const unsigned char *__restrict__ blob, const void *__restric
       bar_arrive(2, kThreads);
       MLP_MARK(6)
       // (the ~12k loads of a tile take a while to queue: do it while layer 3 runs)
-      if (!TILES && has_next && single_batch && tile + 2 * (long long)gridDim.x < n_tiles)
-        load_batch(tile + 2 * (long long)gridDim.x, 0);
+      if (!TILES && has_next && single_batch && tile + 2 * (long long)gdim < n_tiles)
+        load_batch(tile + 2 * (long long)gdim, 0);
       MLP_MARK(4)
 
       if (!deferred) {
@@ -583,6 +602,32 @@ mlp_forward_kernel(const unsigned char *__restrict__ blob, const void *__restric
   if (warp == 0)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
                  ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+}
+
+template <bool TILES>
+__global__ void __launch_bounds__(kThreads, 1)
+mlp_forward_kernel(const unsigned char *__restrict__ blob, const void *__restrict__ input,
+                   long long rows, float *__restrict__ probs0, float *__restrict__ probs1,
+                   float *__restrict__ values, int flags) {
+  mlp_forward_body<TILES>(blob, input, rows, probs0, probs1, values, blockIdx.x, gridDim.x, flags);
+}
+
+// Two policies in ONE grid: CTAs [0, split) run policy A, the rest policy B (each persistent
+// over its own tiles).  Replaces the fork / join of two launches on two streams.
+struct MlpPairArgs {
+  const unsigned char *blob[2];
+  const float *obs[2];
+  long long rows[2];
+  float *probs0[2], *probs1[2], *values[2];
+  unsigned split;
+  int flags;
+};
+__global__ void __launch_bounds__(kThreads, 1)
+mlp_forward_pair_kernel(const __grid_constant__ MlpPairArgs a) {
+  const int w = blockIdx.x >= a.split ? 1 : 0;
+  mlp_forward_body<false>(a.blob[w], a.obs[w], a.rows[w], a.probs0[w], a.probs1[w], a.values[w],
+                          w ? blockIdx.x - a.split : blockIdx.x,
+                          w ? gridDim.x - a.split : a.split, a.flags);
 }
 
 // ---- weight packing: fp32 nn.Linear weights [out, in] -> bf16 canonical K-major tiles ------
@@ -659,6 +704,9 @@ WDB_API int wdb_debug_mlp_clocks(long long *host_out) {
 // wdb_set_option("mlp_max_ctas", n): CTAs (= SMs, one persistent CTA each) the NEXT forward
 // launches may use; 0 = all.  Lets two policies' forwards run side by side on disjoint SMs.
 int g_mlp_max_ctas = 0;
+namespace wdb {
+int g_pdl = 0;            // wdb_set_option("pdl", 0/1): programmatic dependent launches (A/B: slower)
+}
 
 WDB_API long long wdb_mlp_blob_bytes(int F, int H, int A0, int A1) {
   if (!mlp_shape_ok(F, H, A0, A1)) return -1;
@@ -719,7 +767,69 @@ int launch_forward(void *stream, const void *blob, int F, int H, int A0, int A1,
   const int sm_budget = (g_mlp_max_ctas > 0 && g_mlp_max_ctas < kNumSMs) ? g_mlp_max_ctas : kNumSMs;
   const int grid = (int)min((long long)sm_budget, n_tiles);
   mlp_forward_kernel<TILES><<<grid, kThreads, smem, as_stream(stream)>>>(
-      reinterpret_cast<const unsigned char *>(blob), input, rows, probs0, probs1, values);
+      reinterpret_cast<const unsigned char *>(blob), input, rows, probs0, probs1, values, 0);
+  return finish_launch();
+}
+
+// Launch with the programmatic-stream-serialization attribute when the "pdl" option is on:
+// the grid may start while the previous kernel of the stream drains; the kernels order
+// themselves with griddepcontrol.wait (under stream capture this becomes a programmatic edge
+// of the CUDA graph).
+int launch_forward_pair(void *stream, const wdb_mlp_pair &p) {
+  MlpPairArgs a = {};
+  size_t smem = 0;
+  long long tiles[2];
+  for (int w = 0; w < 2; w++) {
+    if (!p.blob[w] || !p.obs[w] || !p.probs0[w] || (p.A1[w] > 0 && !p.probs1[w]) || p.rows[w] <= 0)
+      return (int)cudaErrorInvalidValue;
+    if (!mlp_shape_ok(p.F[w], p.H[w], p.A0[w], p.A1[w])) return (int)cudaErrorInvalidValue;
+    const MlpHeader hd = make_header(p.F[w], p.H[w], p.A0[w], p.A1[w]);
+    const size_t need = mlp_smem_bytes(hd);
+    if (need > smem) smem = need;
+    a.blob[w] = reinterpret_cast<const unsigned char *>(p.blob[w]);
+    a.obs[w] = p.obs[w];
+    a.rows[w] = p.rows[w];
+    a.probs0[w] = p.probs0[w]; a.probs1[w] = p.probs1[w]; a.values[w] = p.values[w];
+    tiles[w] = (p.rows[w] + kTileM - 1) / kTileM;
+  }
+  if (smem > 227 * 1024) return (int)cudaErrorInvalidValue;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(mlp_forward_pair_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = smem;
+  }
+  int cb = p.ctas_b;
+  if (cb <= 0) {
+    // cost in tile-times: the slower of the two shares (the smaller share's tiles run ~1.3x
+    // slower: fewer CTAs keep its weights hot in L2)
+    double best = 1e30;
+    for (int k = 1; k < kNumSMs; k++) {
+      const double ca = (double)((tiles[0] + kNumSMs - k - 1) / (kNumSMs - k));
+      const double cbt = (double)((tiles[1] + k - 1) / k);
+      const double cost = tiles[0] >= tiles[1] ? fmax(ca, 1.3 * cbt) : fmax(1.3 * ca, cbt);
+      if (cost < best) { best = cost; cb = k; }
+    }
+  }
+  if (cb >= kNumSMs) cb = kNumSMs - 1;
+  long long ca = kNumSMs - cb;
+  if (ca > tiles[0]) ca = tiles[0];
+  if (cb > tiles[1]) cb = (int)tiles[1];
+  a.split = (unsigned)ca;
+  a.flags = p.flags;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(ca + cb), 1, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = as_stream(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, mlp_forward_pair_kernel, a);
+  if (e != cudaSuccess) return (int)e;
   return finish_launch();
 }
 
@@ -771,6 +881,11 @@ WDB_API int wdb_mlp_policy_forward(void *stream, const void *blob, int F, int H,
                                    const float *obs, long long rows, float *probs0,
                                    float *probs1, float *values) {
   return launch_forward<false>(stream, blob, F, H, A0, A1, obs, rows, probs0, probs1, values);
+}
+
+WDB_API int wdb_mlp_policy_forward_pair(void *stream, const wdb_mlp_pair *pair) {
+  if (!pair) return (int)cudaErrorInvalidValue;
+  return launch_forward_pair(stream, *pair);
 }
 
 WDB_API int wdb_mlp_policy_forward_tiles(void *stream, const void *blob, int F, int H, int A0,

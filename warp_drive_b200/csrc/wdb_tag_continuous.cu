@@ -145,9 +145,9 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
   int p_off0[kMaxPolicies], p_off1[kMaxPolicies];   // float offset of the block's first row
   uint32_t tma_mask = 0;   // bit 2p / 2p+1: block (p, head) travels by TMA
   const uint32_t mbar = smem_u32(s_mbar);
+  uint32_t t_src_lead[2 * kMaxPolicies], t_dst[2 * kMaxPolicies], t_span[2 * kMaxPolicies];
   if (FUSED) {
     uint32_t slot = 0;                                // byte offset of the next slot in s_tile
-    uint32_t t_src_lead[2 * kMaxPolicies], t_dst[2 * kMaxPolicies], t_span[2 * kMaxPolicies];
 #pragma unroll
     for (int p = 0; p < kMaxPolicies; p++) {
 #pragma unroll
@@ -171,27 +171,6 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
       }
     }
     if (tid == 0) mbar_init(mbar, 1);      // (includes the init fence; waiters sync below)
-    if (tid == 0 && tma_mask) {
-      uint32_t total = 0;
-#pragma unroll
-      for (int q = 0; q < 2 * kMaxPolicies; q++)
-        if (tma_mask & (1u << q)) total += t_span[q];
-      mbar_expect_tx(mbar, total);
-#pragma unroll
-      for (int p = 0; p < kMaxPolicies; p++) {
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-          const int q = 2 * p + h;
-          if (tma_mask & (1u << q)) {
-            const int np = Q.policy_size[p];
-            const int A = h ? Q.A1 : Q.A0;
-            const char *g = reinterpret_cast<const char *>(h ? Q.probs1[p] : Q.probs0[p]) +
-                            4ll * env0 * np * A - t_src_lead[q];
-            tma_load_1d(smem_u32(s_tile) + t_dst[q], g, t_span[q], mbar);
-          }
-        }
-      }
-    }
   }
 
   // ------------------------------------------------------------------ phase 0
@@ -237,6 +216,36 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
   float g_tab = 0.f;
   if (tab_ok && tid < Q.A0 + Q.A1)
     g_tab = tid < Q.A0 ? P.acc_actions[tid] : P.turn_actions[tid - Q.A0];
+
+  if (FUSED) {
+    // Programmatic dependent launch (option "pdl"): this grid may have started while the policy
+    // forward was still running.  Everything above read only what the PREVIOUS env step wrote
+    // (complete: the forward released us after its own griddepcontrol.wait); the probabilities
+    // are requested only now.  A no-op when launched without the attribute.
+    griddep_wait();
+    if (tid == 0 && tma_mask) {
+      uint32_t total = 0;
+#pragma unroll
+      for (int q = 0; q < 2 * kMaxPolicies; q++)
+        if (tma_mask & (1u << q)) total += t_span[q];
+      mbar_expect_tx(mbar, total);
+#pragma unroll
+      for (int p = 0; p < kMaxPolicies; p++) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int q = 2 * p + h;
+          if (tma_mask & (1u << q)) {
+            const int np = Q.policy_size[p];
+            const int A = h ? Q.A1 : Q.A0;
+            const char *g = reinterpret_cast<const char *>(h ? Q.probs1[p] : Q.probs0[p]) +
+                            4ll * env0 * np * A - t_src_lead[q];
+            tma_load_1d(smem_u32(s_tile) + t_dst[q], g, t_span[q], mbar);
+          }
+        }
+      }
+    }
+    griddep_launch_dependents();
+  }
 
   if (tid < N) {
     stype[tid] = g_type;
@@ -435,32 +444,42 @@ tag_continuous_kernel(const __grid_constant__ TcParams P, const __grid_constant_
             }
           }
           // neighbours that left the game shrink the list: widen the disc accordingly
-          if (seen < kk) tau *= 1.0f + 0.45f * (float)(kk - seen);
+          if (seen < kk) tau *= 1.0f + 0.9f * (float)(kk - seen);
           if (seen == 0) tau = -1.0f;
           WDB_MARK(5)   // tau known
           uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+          int cnt = 0;
           {
             unsigned long long pax2, pay2;
             asm("mov.b64 %0, {%1, %1};" : "=l"(pax2) : "f"(pa.x));
             asm("mov.b64 %0, {%1, %1};" : "=l"(pay2) : "f"(pa.y));
             const uint4 *kx4 = reinterpret_cast<const uint4 *>(kx);
             const uint4 *ky4 = reinterpret_cast<const uint4 *>(ky);
-            // mark with tau * (1 + 2^-17): everything left OUT of the mask is then farther than
-            // m_out = that inflated threshold, which is the only thing the verification needs
-            // to know about the rest (no running minimum inside the scan)
-            const float tau_m = tau * 1.00000762939453125f;
+            // At most two passes: a list that came out too long (> kHistCap) or too short
+            // (< kk + 1) is retried once with a smaller / larger disc before the sorting network
+            // over all candidates has to run (any threshold is safe, see `hist_ok`).
+#pragma unroll 1
+            for (int pass = 0; pass < 2; pass++) {
+              // mark with tau * (1 + 2^-17): everything left OUT of the mask is then farther
+              // than m_out = that inflated threshold, which is the only thing the verification
+              // needs to know about the rest (no running minimum inside the scan)
+              const float tau_m = tau * 1.00000762939453125f;
+              m0 = m1 = m2 = m3 = 0;
 #define WDB_SCAN_WORD(W, M)                                                          \
-            if (W * 32 < N) {                                                        \
-              scan_16_nm<0>(M, kx4 + W * 8, ky4 + W * 8, pax2, pay2, tau_m);         \
-              if (W * 32 + 16 < N)                                                   \
-                scan_16_nm<16>(M, kx4 + W * 8 + 4, ky4 + W * 8 + 4, pax2, pay2, tau_m); \
-            }
-            WDB_SCAN_WORD(0, m0) WDB_SCAN_WORD(1, m1) WDB_SCAN_WORD(2, m2) WDB_SCAN_WORD(3, m3)
+              if (W * 32 < N) {                                                      \
+                scan_16_nm<0>(M, kx4 + W * 8, ky4 + W * 8, pax2, pay2, tau_m);       \
+                if (W * 32 + 16 < N)                                                 \
+                  scan_16_nm<16>(M, kx4 + W * 8 + 4, ky4 + W * 8 + 4, pax2, pay2, tau_m); \
+              }
+              WDB_SCAN_WORD(0, m0) WDB_SCAN_WORD(1, m1) WDB_SCAN_WORD(2, m2) WDB_SCAN_WORD(3, m3)
 #undef WDB_SCAN_WORD
-            m_out = tau_m;
+              m_out = tau_m;
+              cnt = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
+              if (tau < 0.0f || (cnt >= kk + 1 && cnt <= kHistCap)) break;
+              tau = (cnt > kHistCap) ? tau * (20.0f / (float)cnt) : tau * 2.5f;
+            }
           }
           WDB_MARK(6)   // scan done
-          const int cnt = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
           const bool hist_ok = (cnt >= kk + 1) && (cnt <= kHistCap);   // self + >= kk others
           if (hist_ok) {
             // candidate ids -> this lane's column of the per-warp byte list (rows are kWarp
@@ -1052,7 +1071,18 @@ int launch_t(const TcParams &P, const FusedParams &Q, const LaunchPlan &plan, cu
                          cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     configured = plan.smem;
   }
-  tag_continuous_kernel<FUSED, MAXT><<<plan.grid, plan.block, plan.smem, st>>>(P, Q);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)plan.grid, 1, 1);
+  cfg.blockDim = dim3((unsigned)plan.block, 1, 1);
+  cfg.dynamicSmemBytes = plan.smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (FUSED && Q.pdl && g_pdl) ? 1 : 0;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, tag_continuous_kernel<FUSED, MAXT>, P, Q);
+  if (e != cudaSuccess) return (int)e;
   return finish_launch();
 }
 
@@ -1120,6 +1150,7 @@ WDB_API int wdb_set_option(const char *name, int value) {
   if (is("tc_history")) { g_tc_history = value ? 1 : 0; return 0; }
   if (is("tc_force_exact")) { g_tc_force_exact = value ? 1 : 0; return 0; }
   if (is("tc_wide_single")) { g_tc_wide_single = value ? 1 : 0; return 0; }
+  if (is("pdl")) { g_pdl = value ? 1 : 0; return 0; }
   if (is("mlp_max_ctas")) {
     if (value < 0) return (int)cudaErrorInvalidValue;
     g_mlp_max_ctas = value;
@@ -1239,6 +1270,7 @@ WDB_API int wdb_tag_continuous_rollout_step(void *stream, const wdb_tc_env *env,
   Q.episodic_step_sum = ro->episodic_step_sum; Q.num_completed = ro->num_completed_episodes;
   Q.reset_table = ro->reset_table; Q.n_reset = ro->n_reset_arrays;
   Q.obs_at_reset = ro->obs_at_reset; Q.do_reset = ro->reset_done_envs;
+  Q.pdl = ro->launch_after_forward;
   if (Q.do_reset && Q.n_reset > 0 && !Q.reset_table) return (int)cudaErrorInvalidValue;
   if (env->blocks_per_env > 1) {
     for (int p = 0; p < Q.n_policies; p++)

@@ -85,9 +85,11 @@ struct FusedParams {
   int n_reset;
   const float *obs_at_reset;        // [E, N, F] (for obs_next of envs that reset)
   int do_reset;
+  int pdl;                          // host only: launch programmatically dependent on the forward
 };
 
 // launch of the cluster kernel (wdb_tc_wide.cu); `fused` may be NULL (step-only)
+extern int g_pdl;                   // wdb_set_option("pdl", 0/1), wdb_mlp.cu
 int tc_wide_launch(TcParams &P, const FusedParams *fused, int blocks_per_env, cudaStream_t st);
 int tc_wide_set_option(const char *name, int value, bool *handled);
 // second-generation small-env kernel (wdb_tc_small_v2.cu), wdb_set_option("tc_variant", 2)
@@ -99,6 +101,14 @@ extern int g_tc_history, g_tc_force_exact, g_tc_wide_single;
 }  // namespace wdb
 
 namespace {
+
+// programmatic dependent launch (no-ops in a grid launched without the attribute)
+__device__ __forceinline__ void griddep_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void griddep_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 
 // tag_continuous_step_pycuda.cu:7-9
 __constant__ float kTwoPi = 6.283185308;

@@ -207,6 +207,10 @@ tc_wide_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Fused
     }
   }
   if (FUSED) {
+    // programmatic dependent launch: the state loads above overlapped the forward's tail, the
+    // probabilities are read from here on (a no-op without the launch attribute)
+    griddep_wait();
+    griddep_launch_dependents();
     // categorical sampling of both heads (core/random.cu:51-85); one Philox block per agent,
     // the stream of the agent id: identical draws to the small-env kernel and the sampler
     float u0 = 0.f, u1 = 0.f;
@@ -438,30 +442,44 @@ tc_wide_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Fused
           seen++;
         }
       }
-      if (seen < kk) t *= 1.0f + 0.45f * (float)(kk - seen);
+      if (seen < kk) t *= 1.0f + 0.9f * (float)(kk - seen);
       if (seen > 0) tau = t;
     }
-    // ---- warp-uniform x-window of bins
+    // ---- threshold scan over a warp-uniform x-window of bins, at most two passes: a lane
+    // whose candidate list came out too long (> kWideCap) or too short (< kk + 1) retries once
+    // with a smaller / larger disc before the branch-free network has to run.  ANY threshold is
+    // safe: the verification below only uses "everything not in the list is farther than
+    // m_out".
     int cnt = 0;
     float m_out = CUDART_INF_F;
-    bool hist = alive && net_ok && tau >= 0.0f;
+    bool hist = false;
+    // first-pass overflow whose retry failed: the K nearest still lie inside the FIRST window,
+    // so the network runs over that window only
+    bool overflow = false;
+    int win_lo = 0, win_n = 0, cnt0 = 0;
+    float m_edge0 = CUDART_INF_F;
     {
-      int blo = 0x7fffffff, bhi = -1;
-      if (hist) {
-        const float rad = sqrtf(tau) * 1.000001f + 1e-30f;
-        blo = wide_bin(fmaxf(pa.x - rad, 0.0f), binscale, nbins);
-        bhi = wide_bin(fminf(pa.x + rad, L), binscale, nbins);
-      }
-      int wlo = __reduce_min_sync(full, blo), whi = __reduce_max_sync(full, bhi);
-      if (!W.use_window && whi >= 0) { wlo = 0; whi = nbins - 1; }
-      if (whi >= 0) {        // at least one lane scans
+      bool want = alive && net_ok && tau >= 0.0f;
+      bool over0 = false;
+      unsigned long long pax2, pay2;
+      asm("mov.b64 %0, {%1, %1};" : "=l"(pax2) : "f"(pa.x));
+      asm("mov.b64 %0, {%1, %1};" : "=l"(pay2) : "f"(pa.y));
+#pragma unroll 1
+      for (int pass = 0; pass < 2; pass++) {
+        int blo = 0x7fffffff, bhi = -1;
+        if (want) {
+          const float rad = sqrtf(tau) * 1.000001f + 1e-30f;
+          blo = wide_bin(fmaxf(pa.x - rad, 0.0f), binscale, nbins);
+          bhi = wide_bin(fminf(pa.x + rad, L), binscale, nbins);
+        }
+        int wlo = __reduce_min_sync(full, blo), whi = __reduce_max_sync(full, bhi);
+        if (whi < 0) break;                      // no lane scans (warp-uniform)
+        if (!W.use_window) { wlo = 0; whi = nbins - 1; }
         const int lo16 = binbase[wlo] & ~15;
         const int hi16 = min((binbase[whi + 1] + 15) & ~15, W.npad);
-        unsigned long long pax2, pay2;
-        asm("mov.b64 %0, {%1, %1};" : "=l"(pax2) : "f"(pa.x));
-        asm("mov.b64 %0, {%1, %1};" : "=l"(pay2) : "f"(pa.y));
         float mo_a = CUDART_INF_F, mo_b = CUDART_INF_F;
-        const float tau_s = hist ? tau : -1.0f;          // lanes without a threshold mark nothing
+        const float tau_s = want ? tau : -1.0f;          // the other lanes mark nothing
+        int c = 0;
         for (int j = lo16; j < hi16; j += 32) {
           uint32_t m = 0;
           const uint4 *kx4 = reinterpret_cast<const uint4 *>(skx + j);
@@ -469,20 +487,29 @@ tc_wide_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Fused
           scan_16<0>(m, mo_a, mo_b, kx4, ky4, pax2, pay2, tau_s);
           if (j + 16 < hi16) scan_16<16>(m, mo_a, mo_b, kx4 + 4, ky4 + 4, pax2, pay2, tau_s);
           for (; m; m &= m - 1) {
-            if (cnt < kWideCap) lst[cnt * kWarp] = (uint16_t)(j + __ffs(m) - 1);
-            cnt++;
+            if (c < kWideCap) lst[c * kWarp] = (uint16_t)(j + __ffs(m) - 1);
+            c++;
           }
         }
-        if (hist) {
+        bool good = false;
+        if (want) {
           // everything outside the window: bins < wlo lie at or left of leftmax[wlo], bins >
           // whi at or right of rightmin[whi] (empty side: -inf / +inf -> bound +inf).
           // dx = fl(x_self - x_other) is monotone in x_other, fl(dx * dx) in |dx|, and the
           // fused dy * dy + . only adds: a rigorous lower bound of sqdist() for all of them
           const float dl = pa.x - leftmax[wlo], dr = rightmin[whi] - pa.x;
-          m_out = fminf(fminf(mo_a, mo_b), fminf(__fmul_rn(dl, dl), __fmul_rn(dr, dr)));
+          const float m_edge = fminf(__fmul_rn(dl, dl), __fmul_rn(dr, dr));
+          m_out = fminf(fminf(mo_a, mo_b), m_edge);
+          cnt = c;
+          good = (c >= kk + 1) && (c <= kWideCap);
+          if (pass == 0) { over0 = c > kWideCap; cnt0 = c; m_edge0 = m_edge; }
         }
+        if (pass == 0) { win_lo = lo16; win_n = hi16 - lo16; }
+        hist = hist || good;
+        want = want && !good && pass == 0;
+        if (want) tau = (c > kWideCap) ? tau * (20.0f / (float)c) : tau * 2.5f;
       }
-      hist = hist && (cnt >= kk + 1) && (cnt <= kWideCap);
+      overflow = over0 && !hist;
     }
     if (alive && net_ok) {
       const uint32_t pad_key = 0x7f800000u | idmask;
@@ -521,10 +548,19 @@ tc_wide_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Fused
       } else {
         // no usable threshold (first step after a reset, list under/overflow): branch-free
         // top-16 of all alive agents (they are the first n_alive positions of the planes)
-        m_out = CUDART_INF_F;
-        if (P.stats && P.use_history) atomicAdd(&P.stats[2], 1);
+        if (P.stats && P.use_history) atomicAdd(&P.stats[overflow ? 3 : 2], 1);
         uint32_t out[kListLen];
-        network_top16(pa, skx, sky, (n_alive + 15) & ~15, idmask, out);
+        if (overflow) {
+          // every agent within tau (> kWideCap of them, the K nearest included) sits in the
+          // window [win_lo, win_lo + win_n); everything outside is bounded below by m_edge
+          network_top16(pa, skx + win_lo, sky + win_lo, win_n, idmask, out);
+          m_out = m_edge0;
+          n_cand = cnt0 - 1;
+        } else {
+          m_out = CUDART_INF_F;
+          win_lo = 0;
+          network_top16(pa, skx, sky, (n_alive + 15) & ~15, idmask, out);
+        }
         r0 = out[0]; r1 = out[1]; r2 = out[2]; r3 = out[3]; r4 = out[4]; r5 = out[5];
         r6 = out[6]; r7 = out[7]; r8 = out[8]; r9 = out[9]; r10 = out[10]; r11 = out[11];
         r12 = out[12]; r13 = out[13]; r14 = out[14]; r15 = out[15];
@@ -543,7 +579,8 @@ tc_wide_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Fused
       const float floor_out = __uint_as_float(last_key & ~idm);
 #pragma unroll
       for (int i = 0; i < kListLen; i++)
-        R[i] = hist ? (uint32_t)min((int)lst[(R[i] & 31u) * kWarp], W.npad - 1) : (R[i] & idmask);
+        R[i] = hist ? (uint32_t)min((int)lst[(R[i] & 31u) * kWarp], W.npad - 1)
+                    : (R[i] & idmask) + (uint32_t)win_lo;
       // ---- verification on EXACT float32 squared distances of the K+1 nearest (same rules
       // as wdb_tag_continuous.cu: strictly increasing with relative gaps > 2^-19, and
       // everything not examined clears the K-th by the same margin)
@@ -1018,13 +1055,15 @@ int tc_wide_launch(TcParams &P, const FusedParams *Qp, int blocks_per_env, cudaS
   cfg.blockDim = dim3((unsigned)block, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)C;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = (Qp && Qp->pdl && g_pdl) ? 2 : 1;
   cudaError_t e;
   if (Qp) {
     static size_t configured = 0;

@@ -70,8 +70,22 @@ class TcRollout(ctypes.Structure):
         ("done_batch", _fp), ("step_running_sum", _fp),
         ("episodic_step_sum", _fp), ("num_completed_episodes", _fp),
         ("reset_table", _fp), ("n_reset_arrays", _i), ("obs_at_reset", _fp),
-        ("reset_done_envs", _i),
+        ("reset_done_envs", _i), ("launch_after_forward", _i),
     ]
+
+
+class MlpPair(ctypes.Structure):
+    """struct wdb_mlp_pair (include/wdb200.h)."""
+
+    _fields_ = [
+        ("blob", _fp * 2), ("F", _i * 2), ("H", _i * 2), ("A0", _i * 2), ("A1", _i * 2),
+        ("obs", _fp * 2), ("rows", ctypes.c_longlong * 2),
+        ("probs0", _fp * 2), ("probs1", _fp * 2), ("values", _fp * 2),
+        ("ctas_b", _i), ("flags", _i),
+    ]
+
+
+MLP_WEIGHTS_STABLE = 1
 
 
 class SaRollout(ctypes.Structure):
@@ -134,6 +148,7 @@ _SIGNATURES = {
     "wdb_mlp_blob_bytes": (_ll, [_i, _i, _i, _i]),
     "wdb_mlp_pack_weights": (_i, [_vp] * 12 + [_i, _i, _i, _i]),
     "wdb_mlp_policy_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _ll, _vp, _vp, _vp]),
+    "wdb_mlp_policy_forward_pair": (_i, [_vp, ctypes.POINTER(MlpPair)]),
     "wdb_mlp_obs_tiles_bytes": (_ll, [_i, _ll]),
     "wdb_mlp_pack_obs": (_i, [_vp, _vp, _ll, _i, _vp]),
     "wdb_mlp_policy_forward_tiles": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _ll, _vp, _vp, _vp]),

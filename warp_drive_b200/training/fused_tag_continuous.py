@@ -107,7 +107,8 @@ class FusedTagContinuousStep:
         self.ro.num_completed_episodes = _p(num_completed)
 
     def launch(self, probs, actions_batch=None, rewards_batch=None, obs_next=None,
-               done_batch=None, uniforms=None, reset_done_envs=True, obs_next_tiles=None):
+               done_batch=None, uniforms=None, reset_done_envs=True, obs_next_tiles=None,
+               after_forward=False):
         """probs: {policy: [probs_head0 [E,Np,A0], probs_head1 [E,Np,A1]]}; the *_batch /
         obs_next dicts hold this timestep's slots (tensors) per policy, or None."""
         ro = self.ro
@@ -121,5 +122,6 @@ class FusedTagContinuousStep:
         ro.done_batch = _p(done_batch)
         ro.uniforms = _p(uniforms)
         ro.reset_done_envs = int(bool(reset_done_envs))
+        ro.launch_after_forward = int(bool(after_forward))
         _lib.check(self.lib.wdb_tag_continuous_rollout_step(
             _lib.stream_ptr(), self._env_ref, self._ro_ref), "tag_continuous_rollout_step")

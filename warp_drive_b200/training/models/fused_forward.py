@@ -4,6 +4,8 @@ of the 12-kernel torch module call.  The torch module stays the owner of the par
 (training / autograd go through it); this wrapper re-packs them into the kernel's bf16
 layout whenever they changed (`refresh()` after an optimizer step).
 """
+import ctypes
+
 import torch
 
 from warp_drive_b200 import lib as _lib
@@ -89,3 +91,22 @@ class FusedPolicyForward:
             _lib.ptr(tiles), int(rows), _lib.ptr(probs0), _lib.ptr(probs1), _lib.ptr(values)),
             "mlp_policy_forward_tiles")
 
+
+
+def forward_pair(fa, fb, obs_a, obs_b, probs_a, probs_b, ctas_b=0, weights_stable=False):
+    """Both policies' forwards in ONE launch (wdb_mlp_policy_forward_pair): `fa` / `fb` are
+    FusedPolicyForward objects, probs_* = [probs_head0, probs_head1].  weights_stable: neither
+    weight blob was written by the kernel launched just before on this stream."""
+    pair = _lib.MlpPair()
+    for w, (f, obs, pr) in enumerate(((fa, obs_a, probs_a), (fb, obs_b, probs_b))):
+        pair.blob[w] = _lib.ptr(f.blob)
+        pair.F[w], pair.H[w], pair.A0[w], pair.A1[w] = f.F, f.H, f.A0, f.A1
+        pair.obs[w] = _lib.ptr(obs)
+        pair.rows[w] = obs.numel() // f.F
+        pair.probs0[w] = _lib.ptr(pr[0])
+        pair.probs1[w] = _lib.ptr(pr[1] if len(pr) > 1 else None)
+        pair.values[w] = None
+    pair.ctas_b = int(ctas_b)
+    pair.flags = _lib.MLP_WEIGHTS_STABLE if weights_stable else 0
+    _lib.check(fa.lib.wdb_mlp_policy_forward_pair(_lib.stream_ptr(), ctypes.byref(pair)),
+               "mlp_policy_forward_pair")

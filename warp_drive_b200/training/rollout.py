@@ -23,8 +23,9 @@ class RolloutEngine:
     def __init__(self, env_wrapper, models, policy_tag_to_agent_id_map, sampler,
                  batch_size_per_env, use_cuda_graph=True, forward_dtype=None,
                  use_fused_step=True, write_observations=True, stats=None,
-                 use_fused_forward=True, use_obs_tiles=False):
+                 use_fused_forward=True, use_obs_tiles=False, use_pair_forward=False):
         self.env_wrapper = env_wrapper
+        self.use_pair_forward = bool(use_pair_forward)
         self.dm = env_wrapper.cuda_data_manager
         self.models = models
         self.policy_map = policy_tag_to_agent_id_map
@@ -181,7 +182,7 @@ class RolloutEngine:
         probs, _ = model(obs_p)
         return [q.contiguous() for q in probs]
 
-    def _forward_side_by_side(self, obs_in, probs):
+    def _forward_side_by_side(self, obs_in, probs, weights_stable=False):
         """Every policy's fused forward, concurrently: the persistent MLP kernel uses one CTA
         per SM, so the SMs are split between the policies in proportion to their rows and the
         smaller policies run on side streams (fork/join by events, also under graph capture).
@@ -189,7 +190,16 @@ class RolloutEngine:
         during the small policy's single wave."""
         if len(self.policies) == 1:
             self._one_forward(self.policies[0], obs_in, probs)
-            return
+            return False
+        if len(self.policies) == 2 and not self.obs_tiles and self.use_pair_forward:
+            # both policies in ONE launch (CTAs split by tile counts), no fork / join
+            from warp_drive_b200.training.models.fused_forward import forward_pair
+
+            pa, pb = sorted(self.policies,
+                            key=lambda p: -(obs_in[p].numel() // obs_in[p].shape[-1]))
+            forward_pair(self.fused_forward[pa], self.fused_forward[pb], obs_in[pa], obs_in[pb],
+                         probs[pa], probs[pb], weights_stable=weights_stable)
+            return True
         if not hasattr(self, "_fwd_plan"):
             n_sm = torch.cuda.get_device_properties(self.dm.device).multi_processor_count
             rows = {p: obs_in[p].numel() // obs_in[p].shape[-1] for p in self.policies}
@@ -229,6 +239,7 @@ class RolloutEngine:
         self._one_forward(p, obs_in, probs, share[p])
         for ev in joins:
             cur.wait_event(ev)
+        return False
 
     def _one_forward(self, p, obs_in, probs, max_ctas=0):
         if self.obs_tiles:
@@ -263,14 +274,17 @@ class RolloutEngine:
                                          for p in self.policies}
                 obs_next = self._scratch_obs
                 actions_batch = rewards_batch = done_batch = None
+            paired = False
             if self.fused_forward:
                 probs = self._probs
-                self._forward_side_by_side(obs_in, probs)
+                # t > 0: the kernel before this forward is the previous env step, not a weight
+                # re-pack -> the weight load may overlap its tail (programmatic launch)
+                paired = self._forward_side_by_side(obs_in, probs, weights_stable=t > 0)
             else:
                 probs = {p: self._forward(self.models[p], obs_in[p]) for p in self.policies}
             self.fused.launch(probs, actions_batch=actions_batch, rewards_batch=rewards_batch,
                               obs_next=obs_next, done_batch=done_batch, uniforms=uniforms,
-                              obs_next_tiles=self.obs_tiles or None)
+                              obs_next_tiles=self.obs_tiles or None, after_forward=paired)
             if t < 0:
                 for p in self.policies:
                     self.cur_obs[p].copy_(self._scratch_obs[p])
