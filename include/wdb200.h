@@ -316,6 +316,50 @@ typedef struct wdb_sa_rollout {
 int wdb_single_agent_rollout_supported(int n_hidden, const int *dims);
 int wdb_single_agent_rollout(void *stream, const wdb_sa_rollout *rollout);
 
+/* -------------------------------------------------- rollout of ANY env: data movement ---- */
+/* [E, N, W] array of 4-byte elements <-> one dense [E, Np, W] block per policy, every policy
+ * in one launch.  scatter = 0: rows[e, j, :] = full[e, agent_ids[j], :] (the per-policy
+ * observation push of warp_drive/training/trainer_base.py:437-464); scatter = 1: the reverse
+ * (the per-policy probabilities into the [E, N, A] array the sampler reads, :466-512).
+ * agent_ids == NULL: the policy covers agents 0..Np-1 in order. */
+typedef struct wdb_gather_policy {
+  int n_agents;                      /* Np */
+  const int *agent_ids;              /* device [Np] or NULL */
+  void *rows;                        /* [E, Np, W] */
+} wdb_gather_policy;
+typedef struct wdb_gather {
+  int n_envs, n_agents, width, n_policies, scatter;
+  void *full;                        /* [E, N, W] */
+  wdb_gather_policy policy[4];
+} wdb_gather;
+int wdb_gather_policy_rows(void *stream, const wdb_gather *gather);
+
+/* Per-timestep bookkeeping of the rollout (trainer_base.py:514-601, which uses
+ * done_flags.nonzero() and len() on the host): done -> done_batch (raw flag); per policy the
+ * agents' rewards -> rewards_batch, sampled actions -> actions_batch, reward_running_sum += r,
+ * and for done envs episodic_reward_sum += the running sums, which are then cleared;
+ * step_running_sum += 1, for done envs episodic_step_sum += it, cleared, num_completed += 1.
+ * Any pointer may be NULL (that piece is skipped); ONE launch, no host synchronisation. */
+typedef struct wdb_bookkeep_policy {
+  int n_agents;
+  const int *agent_ids;              /* device [Np] or NULL (agents 0..Np-1) */
+  float *rewards_batch;              /* [E, Np] slot t */
+  int *actions_batch;                /* [E, Np, n_heads] slot t */
+  float *reward_running_sum;         /* [E, Np] */
+  float *episodic_reward_sum;        /* scalar */
+} wdb_bookkeep_policy;
+typedef struct wdb_bookkeep {
+  int n_envs, n_agents, n_policies, n_heads;
+  const int *done;                   /* [E] */
+  const float *rewards;              /* [E, N] */
+  const int *actions;                /* [E, N, n_heads] or NULL */
+  int *done_batch;                   /* [E] slot t */
+  int *step_running_sum;             /* [E] */
+  unsigned long long *episodic_step_sum, *num_completed_episodes;
+  wdb_bookkeep_policy policy[4];
+} wdb_bookkeep;
+int wdb_rollout_bookkeep(void *stream, const wdb_bookkeep *bookkeep);
+
 /* ------------------------------------------------------------- policy forward ---- */
 /* Fused policy/value MLP forward on the tensor cores (tcgen05 + TMEM), replacing the
  * rollout-time FullyConnected.forward (warp_drive/training/models/fully_connected.py:51-89):

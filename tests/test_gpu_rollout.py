@@ -344,3 +344,51 @@ def test_config4_agent_count_through_wrapper_and_engine():
     assert nn.min() >= 0 and nn.max() < 1024
     obs = dm.pull_data_from_device("observations")
     assert np.isfinite(obs).all() and (obs[alive == 0] == 0).all()
+
+
+def test_generic_path_native_moves_equal_torch_indexing():
+    """wdb_gather_policy_rows (both directions) and wdb_rollout_bookkeep against the plain torch
+    ops they replace on the generic multi-launch path: 2 policies with interleaved agent ids,
+    2 action heads, several steps with resets so that done envs fold their running sums."""
+    E, T = 37, 5
+    wa, ea, pm = _engine(E, T, False, False)
+    wb, eb, _ = _engine(E, T, False, False)
+    assert ea.fused is None and ea.sa is None
+    dma, dmb = wa.cuda_data_manager, wb.cuda_data_manager
+    # gather / scatter
+    obs = dma.data_on_device_via_torch("observations").view(E, wa.n_agents, -1)
+    rows = {p: torch.zeros((E, len(ids), obs.shape[-1]), device="cuda") for p, ids in pm.items()}
+    ea._move_rows(obs, rows)
+    for p, ids in pm.items():
+        assert torch.equal(rows[p], obs[:, ids]), p
+    back = torch.full_like(obs, -7.0)
+    ea._move_rows(back, rows, scatter=True)
+    assert torch.equal(back, obs)
+    # bookkeeping: identical env trajectories (same seeds), native vs torch bookkeeping
+    n_done = 0
+    for it in range(12):                      # 60 steps > one 40-step episode
+        for t in range(T):
+            for e, book in ((ea, ea.bookkeep), (eb, eb.bookkeep_torch)):
+                with torch.no_grad():
+                    probs = e.evaluate_policies(t)
+                    e.sample_actions(probs, t)
+                    e.env_wrapper.step_all_envs()
+                    book(t)
+                    e.env_wrapper.reset_only_done_envs()
+            n_done += int((dma.data_on_device_via_torch("done_flags_batch")[t] > 0).sum())
+        names = ["done_flags_batch"]
+        for p in pm:
+            names += [f"processed_observations_batch_{p}", f"sampled_actions_batch_{p}",
+                      f"rewards_batch_{p}"]
+        for name in names:
+            assert torch.equal(dma.data_on_device_via_torch(name),
+                               dmb.data_on_device_via_torch(name)), (it, name)
+        assert torch.equal(ea.step_running_sum, eb.step_running_sum)
+        for p in pm:
+            assert torch.equal(ea.reward_running_sum[p], eb.reward_running_sum[p]), p
+    assert n_done >= E
+    assert int(ea.num_completed_episodes) == int(eb.num_completed_episodes) == n_done
+    assert int(ea.episodic_step_sum) == int(eb.episodic_step_sum)
+    for p in pm:
+        a, b = float(ea.episodic_reward_sum[p]), float(eb.episodic_reward_sum[p])
+        assert abs(a - b) <= 1e-4 * max(1.0, abs(b)), (p, a, b)

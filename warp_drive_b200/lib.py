@@ -74,6 +74,37 @@ class TcRollout(ctypes.Structure):
     ]
 
 
+class GatherPolicy(ctypes.Structure):
+    _fields_ = [("n_agents", _i), ("agent_ids", _fp), ("rows", _fp)]
+
+
+class Gather(ctypes.Structure):
+    """struct wdb_gather (include/wdb200.h)."""
+
+    _fields_ = [
+        ("n_envs", _i), ("n_agents", _i), ("width", _i), ("n_policies", _i), ("scatter", _i),
+        ("full", _fp), ("policy", GatherPolicy * 4),
+    ]
+
+
+class BookkeepPolicy(ctypes.Structure):
+    _fields_ = [
+        ("n_agents", _i), ("agent_ids", _fp), ("rewards_batch", _fp), ("actions_batch", _fp),
+        ("reward_running_sum", _fp), ("episodic_reward_sum", _fp),
+    ]
+
+
+class Bookkeep(ctypes.Structure):
+    """struct wdb_bookkeep (include/wdb200.h)."""
+
+    _fields_ = [
+        ("n_envs", _i), ("n_agents", _i), ("n_policies", _i), ("n_heads", _i),
+        ("done", _fp), ("rewards", _fp), ("actions", _fp), ("done_batch", _fp),
+        ("step_running_sum", _fp), ("episodic_step_sum", _fp), ("num_completed_episodes", _fp),
+        ("policy", BookkeepPolicy * 4),
+    ]
+
+
 class MlpPair(ctypes.Structure):
     """struct wdb_mlp_pair (include/wdb200.h)."""
 
@@ -149,6 +180,8 @@ _SIGNATURES = {
     "wdb_mlp_pack_weights": (_i, [_vp] * 12 + [_i, _i, _i, _i]),
     "wdb_mlp_policy_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _ll, _vp, _vp, _vp]),
     "wdb_mlp_policy_forward_pair": (_i, [_vp, ctypes.POINTER(MlpPair)]),
+    "wdb_gather_policy_rows": (_i, [_vp, ctypes.POINTER(Gather)]),
+    "wdb_rollout_bookkeep": (_i, [_vp, ctypes.POINTER(Bookkeep)]),
     "wdb_mlp_obs_tiles_bytes": (_ll, [_i, _ll]),
     "wdb_mlp_pack_obs": (_i, [_vp, _vp, _ll, _i, _vp]),
     "wdb_mlp_policy_forward_tiles": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _ll, _vp, _vp, _vp]),

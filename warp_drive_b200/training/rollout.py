@@ -8,8 +8,11 @@ reference issues ~55 kernel launches and >= 5 host synchronisations per timestep
 a device-side mask), and the whole T-step rollout is captured once in a CUDA graph and
 replayed.
 """
+import ctypes
+
 import torch
 
+from warp_drive_b200 import lib as _lib
 from warp_drive_b200.utils.constants import Constants
 
 _OBSERVATIONS = Constants.OBSERVATIONS
@@ -293,33 +296,74 @@ class RolloutEngine:
     def _tensor(self, name):
         return self.dm.data_on_device_via_torch(name)
 
+    # ---- native data movement of the generic path (csrc/wdb_rollout_generic.cu) ----------
+    def _ids32(self, p):
+        """int32 device copy of the policy's agent ids (None: the policy covers 0..N-1)."""
+        if not hasattr(self, "_ids32_cache"):
+            self._ids32_cache = {q: (None if self.covers_all[q]
+                                     else self.ids[q].to(torch.int32).contiguous())
+                                 for q in self.policies}
+        return self._ids32_cache[p]
+
+    def _move_rows(self, full, rows, scatter=False):
+        """full [E, N, W] <-> rows {policy: [E, Np, W]} (4-byte elements), ONE launch for all
+        policies in `rows` (wdb_gather_policy_rows)."""
+        assert full.is_contiguous() and full.element_size() == 4
+        g = _lib.Gather()
+        g.n_envs, g.n_agents = self.E, self.N
+        g.width = full.numel() // (self.E * self.N)
+        g.n_policies, g.scatter = len(rows), int(bool(scatter))
+        g.full = _lib.ptr(full)
+        for i, (p, r) in enumerate(rows.items()):
+            assert r.is_contiguous() and r.element_size() == 4
+            assert r.numel() == self.E * len(self.policy_map[p]) * g.width, (p, r.shape)
+            io = g.policy[i]
+            io.n_agents = len(self.policy_map[p])
+            io.agent_ids = _lib.ptr(self._ids32(p))
+            io.rows = _lib.ptr(r)
+        _lib.check(_lib.load().wdb_gather_policy_rows(_lib.stream_ptr(), ctypes.byref(g)),
+                   "gather_policy_rows")
+
     def evaluate_policies(self, t):
-        """obs -> per-head probabilities [E, N, A_k] (trainer_a2c.py:159-216)."""
+        """obs -> per-head probabilities [E, N, A_k] (trainer_a2c.py:159-216).  The per-policy
+        observation rows go to the batch slot in one gather launch and the forward reads the
+        slot; the per-policy probabilities return to the sampler's [E, N, A] arrays in one
+        scatter launch per head."""
         obs = self._tensor(_OBSERVATIONS).view(self.E, self.N, -1)
-        out = None
+        if t >= 0:
+            obs_p = {p: self._tensor(f"{_PROCESSED_OBSERVATIONS}_batch_{p}")[t]
+                     for p in self.policies}
+            self._move_rows(obs, obs_p)
+        else:
+            if not hasattr(self, "_obs_scratch"):
+                self._obs_scratch = {
+                    p: torch.empty((self.E, len(self.policy_map[p]), obs.shape[-1]),
+                                   dtype=obs.dtype, device=obs.device)
+                    for p in self.policies if not self.covers_all[p]}
+            obs_p = {p: obs for p in self.policies if self.covers_all[p]}
+            obs_p.update(self._obs_scratch)
+            if self._obs_scratch:
+                self._move_rows(obs, self._obs_scratch)
+        per_policy = {}
         for p in self.policies:
-            model = self.models[p]
-            obs_p = obs if self.covers_all[p] else obs.index_select(1, self.ids[p])
-            if t >= 0:
-                self._tensor(f"{_PROCESSED_OBSERVATIONS}_batch_{p}")[t].copy_(obs_p)
             if self.fused_forward:
                 # tcgen05 forward straight into the persistent probability buffers
                 bufs = self._probs[p]
-                self.fused_forward[p](obs_p.contiguous(), bufs[0],
-                                      bufs[1] if len(bufs) > 1 else None)
-                probs = bufs
+                self.fused_forward[p](obs_p[p], bufs[0], bufs[1] if len(bufs) > 1 else None)
+                per_policy[p] = bufs
             else:
-                probs = self._forward(model, obs_p)
-            if self.combined is None:
-                out = probs
-            else:
-                for k in range(self.n_heads):
-                    self.combined[k].index_copy_(1, self.ids[p], probs[k])
-                out = self.combined
-        return out
+                per_policy[p] = self._forward(self.models[p], obs_p[p].view(
+                    self.E, len(self.policy_map[p]), -1))
+        if self.combined is None:
+            return per_policy[self.policies[0]]
+        for k in range(self.n_heads):
+            self._move_rows(self.combined[k], {p: per_policy[p][k] for p in self.policies},
+                            scatter=True)
+        return self.combined
 
     def sample_actions(self, probs, t, **sample_params):
-        """probs -> sampled_actions (+ per-policy batch push), trainer_base.py:437-512."""
+        """probs -> sampled_actions (trainer_base.py:466-512); the per-policy batch push of the
+        actions happens in bookkeep()."""
         dm = self.dm
         if self.n_heads == 1:
             self.sampler.sample(dm, probs[0], _ACTIONS, write_cum_distr=False, **sample_params)
@@ -328,23 +372,46 @@ class RolloutEngine:
             for k in range(self.n_heads):
                 self.sampler.sample(dm, probs[k], f"{_ACTIONS}_{k}", write_cum_distr=False,
                                     combined=(actions, self.n_heads, k), **sample_params)
-        if t >= 0:
-            actions = self._tensor(_ACTIONS)
-            for p in self.policies:
-                batch = self._tensor(f"{_ACTIONS}_batch_{p}")[t]
-                batch.copy_(actions if self.covers_all[p]
-                            else actions.index_select(1, self.ids[p]))
 
     def bookkeep(self, t):
-        """done / rewards -> batches, running episodic sums without host syncs
-        (trainer_base.py:514-601 uses nonzero()/len())."""
+        """done / rewards / actions -> batches, running episodic sums: ONE launch
+        (wdb_rollout_bookkeep), no host synchronisation (trainer_base.py:514-601 uses
+        nonzero() / len())."""
+        k = _lib.Bookkeep()
+        k.n_envs, k.n_agents, k.n_policies = self.E, self.N, len(self.policies)
+        actions = self._tensor(_ACTIONS) if self.dm.is_data_on_device_via_torch(_ACTIONS) else None
+        k.n_heads = (actions.numel() // (self.E * self.N)) if actions is not None else 0
+        k.done = _lib.ptr(self._tensor("_done_"))
+        k.rewards = _lib.ptr(self._tensor(_REWARDS))
+        k.actions = _lib.ptr(actions)
+        k.done_batch = _lib.ptr(self._tensor(f"{_DONE_FLAGS}_batch")[t]) if t >= 0 else None
+        k.step_running_sum = _lib.ptr(self.step_running_sum)
+        k.episodic_step_sum = _lib.ptr(self.episodic_step_sum)
+        k.num_completed_episodes = _lib.ptr(self.num_completed_episodes)
+        for i, p in enumerate(self.policies):
+            io = k.policy[i]
+            io.n_agents = len(self.policy_map[p])
+            io.agent_ids = _lib.ptr(self._ids32(p))
+            if t >= 0:
+                io.rewards_batch = _lib.ptr(self._tensor(f"{_REWARDS}_batch_{p}")[t])
+                if actions is not None:
+                    io.actions_batch = _lib.ptr(self._tensor(f"{_ACTIONS}_batch_{p}")[t])
+            io.reward_running_sum = _lib.ptr(self.reward_running_sum[p])
+            io.episodic_reward_sum = _lib.ptr(self.episodic_reward_sum[p])
+        _lib.check(_lib.load().wdb_rollout_bookkeep(_lib.stream_ptr(), ctypes.byref(k)),
+                   "rollout_bookkeep")
+
+    def bookkeep_torch(self, t):
+        """The same bookkeeping in plain torch ops (the parity reference of bookkeep() in
+        tests/test_gpu_rollout.py; not used by the engine)."""
         raw_done = self._tensor("_done_")
         rewards = self._tensor(_REWARDS)
         if t >= 0:
-            # the batch keeps the raw flag (MountainCar writes done == 2 at the goal; the
-            # reference's neg/pos sampling tests for == 2)
             self._tensor(f"{_DONE_FLAGS}_batch")[t].copy_(raw_done)
-        # any non-zero flag means "done" (trainer_base.py:534-601 uses done_flags.nonzero())
+            actions = self._tensor(_ACTIONS)
+            for p in self.policies:
+                self._tensor(f"{_ACTIONS}_batch_{p}")[t].copy_(
+                    actions if self.covers_all[p] else actions.index_select(1, self.ids[p]))
         done = (raw_done > 0).to(torch.int32)
         donef = done.to(torch.float32)
         for p in self.policies:
