@@ -781,8 +781,9 @@ def train_summary(rep_ms, roll, upd, ar_us, n_grad, E, N, T, n_iters, world, alg
         "collective": "ONE in-place NCCL all-reduce (sum) of the flat gradient arena of all "
                       "policies + divide by world size, per iteration; no collective on the "
                       "rollout path (env replicas are independent)",
-        "limiter": ("update: cuBLAS TF32 forward + backward over the "
-                    f"[{T}, {E}, Np, 71] batches + fused loss kernel + flat Adam"
+        "limiter": ("update: cuBLAS TF32 GEMMs with fused bias/ReLU/softmax/ReLU-backward "
+                    f"kernels between them over the [{T}, {E}, Np, 71] batches (one autograd "
+                    "node per policy) + fused loss kernel + flat Adam"
                     if upd > roll else "rollout"),
     }
 

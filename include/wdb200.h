@@ -417,6 +417,28 @@ int wdb_discounted_returns(void *stream, const float *rewards, const int *done,
                            const float *values, float *returns, int T, int n_envs,
                            int n_agents, float gamma);
 
+/* Elementwise pieces of the MLP's TRAINING forward / backward (warp_drive/training/models/
+ * fully_connected.py:51-89 under autograd); the GEMMs between them stay on cuBLAS.
+ * wdb_heads_softmax: logits [rows, pitch >= A0 + A1 + 1] (the pitch is padded to a multiple of
+ * 4 floats so that cuBLAS can use its 16-byte-aligned tensor-core kernels; wdb_heads_softmax_backward
+ * zero-fills the padding columns) of the two action heads and the value head
+ * (one GEMM) -> softmax per head into probs0 [rows, A0], probs1 [rows, A1] (A1 may be 0) and
+ * the value column into values [rows].  wdb_heads_softmax_backward: the gradient with respect
+ * to those logits from the gradients of probs / values (NULL = no gradient).
+ * wdb_relu_backward_bias: grad_hidden[r, c] = hidden[r, c] > 0 ? grad_hidden[r, c] : 0 in
+ * place, and per CTA the column sums of the result into partial_bias_grads
+ * [ceil(rows / wdb_relu_backward_bias_rows(rows)), width] (the bias gradient = their sum;
+ * no atomics: deterministic). */
+int wdb_heads_softmax(void *stream, const float *logits, long long rows, int A0, int A1,
+                      int pitch, float *probs0, float *probs1, float *values);
+int wdb_heads_softmax_backward(void *stream, const float *probs0, const float *probs1,
+                               const float *grad_probs0, const float *grad_probs1,
+                               const float *grad_values, long long rows, int A0, int A1,
+                               int pitch, float *grad_logits);
+int wdb_relu_backward_bias_rows(long long rows);
+int wdb_relu_backward_bias(void *stream, float *grad_hidden, const float *hidden,
+                           long long rows, int width, float *partial_bias_grads);
+
 /* Fused A2C / PPO loss (a2c.py:80-130, ppo.py:82-141): ONE backward-in-time scan per (env,
  * agent) computes the bootstrapped returns, advantages, Categorical log-prob and entropy of
  * every head, the loss sums and the gradients of

@@ -1,0 +1,14 @@
+#!/bin/bash
+mkdir -p gpurun_out
+O=gpurun_out/r2u
+timeout 1500 python -m pytest tests/test_gpu_update.py tests/test_gpu_training.py -m gpu -q --tb=short 2>&1 | tail -25 | tee ${O}_tests.log
+timeout 600 python bench.py --mode train --steps 40 --warmup 10 > ${O}_train.json 2> ${O}_train.err
+python - <<'PY'
+import json
+try:
+    d = json.loads(open("gpurun_out/r2u_train.json").read().strip().splitlines()[-1])
+    print("train value", round(d["value"]/1e6,2), "M/s ms/step", d["ms_per_step"], json.dumps(d.get("train"))[:600])
+except Exception as e:
+    print("failed", e); print(open("gpurun_out/r2u_train.err").read()[-2000:])
+PY
+exit 0

@@ -162,3 +162,73 @@ def test_cartpole_learns_with_the_fused_rollout_and_update(tmp_path):
     first = np.mean(means[1:6])
     best = max(np.mean(means[i:i + 10]) for i in range(10, iters - 9))
     assert best > 1.5 * first, (first, best, [round(m, 1) for m in means[::10]])
+
+
+@pytest.mark.parametrize("heads", [(21, 21), (3,)])
+@pytest.mark.parametrize("rows_shape", [(7, 13, 5), (1000,)])
+def test_fused_train_forward_matches_module_autograd(heads, rows_shape):
+    """models/fused_mlp_train.py (bias + ReLU in the GEMM epilogue, one GEMM for all heads,
+    fused softmax / ReLU-backward / bias-gradient kernels) against the plain torch module under
+    autograd: same outputs and the same parameter gradients (float32, sums in another order)."""
+    from test_gpu_mlp import _Model
+
+    F, H = 71, 64
+    torch.manual_seed(5)
+    m = _Model(F, H, heads[0], heads[1] if len(heads) > 1 else 1).cuda()
+    if len(heads) == 1:
+        m.policy_head = torch.nn.ModuleList([m.policy_head[0]])
+        m.output_dims = [heads[0]]
+    m.action_mask = None
+    from warp_drive_b200.training.models import fused_mlp_train
+
+    obs = torch.randn(*rows_shape, F, device="cuda")
+    assert fused_mlp_train.supported(m, obs)
+    g = torch.Generator(device="cuda").manual_seed(1)
+
+    def loss_of(probs, values):
+        out = (values * wv).sum()
+        for p, w in zip(probs, wp):
+            out = out + (p * w).sum()
+        return out
+
+    probs_f, values_f = fused_mlp_train.fused_train_forward(m, obs)
+    wp = [torch.randn(p.shape, device="cuda", generator=g) for p in probs_f]
+    wv = torch.randn(values_f.shape, device="cuda", generator=g)
+    loss_of(probs_f, values_f).backward()
+    grads_f = {n: p.grad.clone() for n, p in m.named_parameters()}
+    m.zero_grad()
+    x = m.fc["1"](m.fc["0"](obs))
+    probs_t = [torch.softmax(h(x), -1) for h in m.policy_head]
+    values_t = m.vf_head(x)[..., 0]
+    loss_of(probs_t, values_t).backward()
+    for a, b in zip(probs_f, probs_t):
+        assert a.shape == b.shape and torch.allclose(a, b, atol=1e-6, rtol=1e-5)
+    assert values_f.shape == values_t.shape and torch.allclose(values_f, values_t, atol=1e-5, rtol=1e-5)
+    for n, p in m.named_parameters():
+        assert torch.allclose(grads_f[n], p.grad, atol=2e-4, rtol=1e-4), (
+            n, float((grads_f[n] - p.grad).abs().max()))
+
+
+def test_trainer_update_uses_the_fused_train_forward(tmp_path):
+    """FullyConnected.forward under autograd goes through the fused node (and stays on the plain
+    module path under no_grad / for models it does not cover)."""
+    from test_gpu_training import _run_config
+    from warp_drive_b200.env_wrapper import EnvWrapper
+    from warp_drive_b200.envs.tag_continuous import TagContinuous
+    from warp_drive_b200.training.trainer import Trainer
+
+    cfg = _run_config("tag_continuous", num_envs=8, train_batch_size=8 * 4, num_episodes=4)
+    cfg["saving"]["basedir"] = str(tmp_path)
+    env = TagContinuous(**cfg["env"])
+    w = EnvWrapper(env, num_envs=8, env_backend="b200")
+    tr = Trainer(w, cfg, {"runner": sorted(env.runners), "tagger": sorted(env.taggers)},
+                 verbose=False)
+    model = tr.models["runner"]
+    obs = torch.randn(4, 8, len(env.runners), model.flattened_obs_size, device="cuda")
+    probs, values = model(obs)
+    node = probs[0].grad_fn                    # the [T, E, Np, A] view of the fused node's output
+    assert node is not None and "FusedMLPTrain" in type(node.next_functions[0][0]).__name__
+    with torch.no_grad():
+        probs_ng, values_ng = model(obs)
+    assert torch.allclose(probs[0], probs_ng[0], atol=1e-6) and torch.allclose(values, values_ng, atol=1e-5)
+    tr.graceful_close()

@@ -92,8 +92,6 @@ tc_small_v2_kernel(const __grid_constant__ TcParams P, const __grid_constant__ F
   int *s_nalive = s_nrun + epb;   // [epb]
   int *s_done = s_nalive + epb;   // [epb]
   int *s_ntag = s_done + epb;     // [4]
-  int *s_rowbase = s_ntag + 4;    // [N] (unused here, keeps tc_small_bytes' layout)
-  int *s_rowstride = s_rowbase + N;
   unsigned char *s_scr = smem_raw + tc_small_bytes(epb, N);
   // v2 extras behind the per-warp scratch: tile row -> (env slot << 7 | agent), working slot
   // -> agent id, last step's neighbour ids per agent, then the observation chunk tile

@@ -512,7 +512,6 @@ tc_wide_kernel(const __grid_constant__ TcParams P, const __grid_constant__ Fused
       overflow = over0 && !hist;
     }
     if (alive && net_ok) {
-      const uint32_t pad_key = 0x7f800000u | idmask;
       uint32_t r0, r1, r2, r3, r4, r5, r6, r7, r8, r9, r10, r11, r12, r13, r14, r15;
       int n_have = min(nv, kListLen - 1);
       int n_cand = nv;

@@ -156,6 +156,138 @@ adam_kernel(float *__restrict__ p, float *__restrict__ g, float *__restrict__ m,
   p[i] = p[i] - (lr / bias1) * (mi / denom);
 }
 
+
+// ---- elementwise pieces of the MLP's training forward / backward (the GEMMs stay on cuBLAS;
+// these replace the separate torch kernels -- and tensor passes -- between them) ------------
+// logits [M, A0 + A1 + 1] (two action heads and the value column of ONE GEMM) -> softmax per
+// head into dense probs0 / probs1, value column into values.  One thread per row: the 32 rows of
+// a warp are one contiguous block, every sector is fetched once and re-used from L1.
+__global__ void __launch_bounds__(256)
+heads_softmax_kernel(const float *__restrict__ z, long long M, int A0, int A1, int ld,
+                     float *__restrict__ p0, float *__restrict__ p1, float *__restrict__ values) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= M) return;
+  const float *row = z + r * ld;
+  for (int h = 0; h < 2; h++) {
+    const int n = h ? A1 : A0;
+    if (n == 0) continue;
+    const float *x = row + (h ? A0 : 0);
+    float *o = (h ? p1 : p0) + r * n;
+    float mx = x[0];
+    for (int j = 1; j < n; j++) mx = fmaxf(mx, x[j]);
+    float sum = 0.0f;
+    for (int j = 0; j < n; j++) sum += expf(x[j] - mx);
+    const float inv = 1.0f / sum;
+    for (int j = 0; j < n; j++) o[j] = expf(x[j] - mx) * inv;
+  }
+  values[r] = row[A0 + A1];
+}
+
+// d(logits) from d(probs): dz_j = p_j (g_j - sum_k g_k p_k) per head; value column = gv
+__global__ void __launch_bounds__(256)
+heads_softmax_backward_kernel(const float *__restrict__ p0, const float *__restrict__ p1,
+                              const float *__restrict__ g0, const float *__restrict__ g1,
+                              const float *__restrict__ gv, long long M, int A0, int A1,
+                              int ld, float *__restrict__ dz) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= M) return;
+  float *row = dz + r * ld;
+  for (int h = 0; h < 2; h++) {
+    const int n = h ? A1 : A0;
+    if (n == 0) continue;
+    const float *p = (h ? p1 : p0) + r * n;
+    const float *g = h ? g1 : g0;
+    float *o = row + (h ? A0 : 0);
+    if (!g) {                                   // this head received no gradient
+      for (int j = 0; j < n; j++) o[j] = 0.0f;
+      continue;
+    }
+    g += r * n;
+    float dot = 0.0f;
+    for (int j = 0; j < n; j++) dot += g[j] * p[j];
+    for (int j = 0; j < n; j++) o[j] = p[j] * (g[j] - dot);
+  }
+  row[A0 + A1] = gv ? gv[r] : 0.0f;
+  for (int j = A0 + A1 + 1; j < ld; j++) row[j] = 0.0f;    // alignment padding of the pitch
+}
+
+// ReLU backward in place + the bias gradient of the layer: dh[r, c] = h[r, c] > 0 ? dh[r, c] : 0,
+// partial[blockIdx.x, c] = sum over this CTA's rows (the caller adds the partials: no atomics,
+// deterministic).  float4 columns: a 256-thread CTA covers 1024 / H whole rows per iteration,
+// four iterations unrolled with all loads ahead of the stores (the kernel is a pure stream:
+// 12 bytes per element, what matters is bytes in flight).
+__global__ void __launch_bounds__(256)
+relu_backward_bias_kernel(float *__restrict__ dh, const float *__restrict__ h, long long M, int H,
+                          int rows_per_cta, float *__restrict__ partial) {
+  const int cpr = H >> 2;                          // float4 columns per row
+  const int rpi = blockDim.x / cpr;                // rows per iteration
+  const int sub = threadIdx.x / cpr, c4 = threadIdx.x - sub * cpr;
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  const long long r1 = min(M, r0 + rows_per_cta);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (sub < rpi) {
+    float4 *d4 = reinterpret_cast<float4 *>(dh);
+    const float4 *h4 = reinterpret_cast<const float4 *>(h);
+    long long r = r0 + sub;
+    for (; r + 3ll * rpi < r1; r += 4ll * rpi) {
+      float4 a[4], g[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const long long i = (r + (long long)u * rpi) * cpr + c4;
+        a[u] = h4[i];
+        g[u] = d4[i];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const long long i = (r + (long long)u * rpi) * cpr + c4;
+        g[u].x = a[u].x > 0.0f ? g[u].x : 0.0f; g[u].y = a[u].y > 0.0f ? g[u].y : 0.0f;
+        g[u].z = a[u].z > 0.0f ? g[u].z : 0.0f; g[u].w = a[u].w > 0.0f ? g[u].w : 0.0f;
+        d4[i] = g[u];
+        acc.x += g[u].x; acc.y += g[u].y; acc.z += g[u].z; acc.w += g[u].w;
+      }
+    }
+    for (; r < r1; r += rpi) {
+      const long long i = r * cpr + c4;
+      const float4 a = h4[i];
+      float4 g = d4[i];
+      g.x = a.x > 0.0f ? g.x : 0.0f; g.y = a.y > 0.0f ? g.y : 0.0f;
+      g.z = a.z > 0.0f ? g.z : 0.0f; g.w = a.w > 0.0f ? g.w : 0.0f;
+      d4[i] = g;
+      acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+    }
+  }
+  // column sums over the CTA's sub-rows (fixed order: deterministic)
+  __shared__ float4 red[256];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  if (sub == 0 && c4 < cpr) {
+    float4 s = red[c4];
+    for (int k = 1; k < rpi; k++) {
+      const float4 v = red[k * cpr + c4];
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    reinterpret_cast<float4 *>(partial)[(long long)blockIdx.x * cpr + c4] = s;
+  }
+}
+
+// same, scalar columns (widths that are not a multiple of 4 / unaligned bases)
+__global__ void __launch_bounds__(256)
+relu_backward_bias_scalar_kernel(float *__restrict__ dh, const float *__restrict__ h, long long M,
+                                 int H, int rows_per_cta, float *__restrict__ partial) {
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  const long long r1 = min(M, r0 + rows_per_cta);
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    float acc = 0.0f;
+    for (long long r = r0; r < r1; r++) {
+      const long long i = r * H + c;
+      const float v = h[i] > 0.0f ? dh[i] : 0.0f;
+      dh[i] = v;
+      acc += v;
+    }
+    partial[(long long)blockIdx.x * H + c] = acc;
+  }
+}
+
 }  // namespace
 
 WDB_API int wdb_pg_loss_and_grads(void *stream, const wdb_pg_loss *l) {
@@ -191,5 +323,52 @@ WDB_API int wdb_adam_step(void *stream, float *params, float *grads, float *exp_
   adam_kernel<<<(int)((n + 255) / 256), 256, 0, as_stream(stream)>>>(
       params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bias1, bias2_sqrt,
       max_grad_norm, grad_sumsq);
+  return finish_launch();
+}
+
+WDB_API int wdb_heads_softmax(void *stream, const float *logits, long long rows, int A0, int A1,
+                              int pitch, float *probs0, float *probs1, float *values) {
+  if (!logits || !probs0 || !values || rows < 1 || A0 < 1 || A1 < 0 || (A1 > 0 && !probs1) ||
+      pitch < A0 + A1 + 1)
+    return (int)cudaErrorInvalidValue;
+  heads_softmax_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, as_stream(stream)>>>(
+      logits, rows, A0, A1, pitch, probs0, probs1, values);
+  return finish_launch();
+}
+
+WDB_API int wdb_heads_softmax_backward(void *stream, const float *probs0, const float *probs1,
+                                       const float *grad_probs0, const float *grad_probs1,
+                                       const float *grad_values, long long rows, int A0, int A1,
+                                       int pitch, float *grad_logits) {
+  if (!probs0 || !grad_logits || rows < 1 || A0 < 1 || A1 < 0 || (A1 > 0 && !probs1) ||
+      pitch < A0 + A1 + 1)
+    return (int)cudaErrorInvalidValue;
+  heads_softmax_backward_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, as_stream(stream)>>>(
+      probs0, probs1, grad_probs0, grad_probs1, grad_values, rows, A0, A1, pitch, grad_logits);
+  return finish_launch();
+}
+
+WDB_API int wdb_relu_backward_bias_rows(long long rows) {
+  // rows handled by one CTA: enough CTAs to fill the GPU several times, few enough partials
+  long long per = (rows + 8 * kNumSMs - 1) / (8 * kNumSMs);
+  if (per < 64) per = 64;
+  return (int)per;
+}
+
+WDB_API int wdb_relu_backward_bias(void *stream, float *grad_hidden, const float *hidden,
+                                   long long rows, int width, float *partial_bias_grads) {
+  if (!grad_hidden || !hidden || !partial_bias_grads || rows < 1 || width < 1)
+    return (int)cudaErrorInvalidValue;
+  const int per = wdb_relu_backward_bias_rows(rows);
+  const long long ctas = (rows + per - 1) / per;
+  const bool vec = (width % 4 == 0) && (width / 4 <= 256) &&
+                   ((reinterpret_cast<uintptr_t>(grad_hidden) | reinterpret_cast<uintptr_t>(hidden) |
+                     reinterpret_cast<uintptr_t>(partial_bias_grads)) & 15) == 0;
+  if (vec)
+    relu_backward_bias_kernel<<<(unsigned)ctas, 256, 0, as_stream(stream)>>>(
+        grad_hidden, hidden, rows, width, per, partial_bias_grads);
+  else
+    relu_backward_bias_scalar_kernel<<<(unsigned)ctas, 256, 0, as_stream(stream)>>>(
+        grad_hidden, hidden, rows, width, per, partial_bias_grads);
   return finish_launch();
 }

@@ -187,6 +187,10 @@ _SIGNATURES = {
     "wdb_mlp_policy_forward_tiles": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _ll, _vp, _vp, _vp]),
     "wdb_discounted_returns": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f]),
     "wdb_pg_loss_and_grads": (_i, [_vp, ctypes.POINTER(PgLoss)]),
+    "wdb_heads_softmax": (_i, [_vp, _vp, _ll, _i, _i, _i, _vp, _vp, _vp]),
+    "wdb_heads_softmax_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _vp]),
+    "wdb_relu_backward_bias_rows": (_i, [_ll]),
+    "wdb_relu_backward_bias": (_i, [_vp, _vp, _vp, _ll, _i, _vp]),
     "wdb_grad_sumsq": (_i, [_vp, _vp, _ll, _vp]),
     "wdb_adam_step": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _i, _f, _vp]),
     "wdb_single_agent_rollout_supported": (_i, [_i, ctypes.POINTER(_i)]),

@@ -65,6 +65,8 @@ class FullyConnected(nn.Module):
                 [nn.Linear(self.fc_dims[-1], h) for h in heads])
         self.vf_head = nn.Linear(self.fc_dims[-1], 1)
         self.action_mask = None
+        # training-time forward as one fused autograd node (models/fused_mlp_train.py)
+        self.use_fused_train_forward = bool(model_config.get("fused_train_forward", True))
         name = f"{_PROCESSED_OBSERVATIONS}_batch_{policy}"
         self.batch_size = env.cuda_data_manager.get_shape(name=name)[0]
 
@@ -123,6 +125,12 @@ class FullyConnected(nn.Module):
 
     # ---- forward (fully_connected.py:51-89)
     def forward(self, obs=None, action=None):
+        if self.use_fused_train_forward and torch.is_grad_enabled() and obs.is_cuda:
+            # the update: one autograd node, bias / ReLU / softmax fused around cuBLAS GEMMs
+            from warp_drive_b200.training.models import fused_mlp_train
+
+            if fused_mlp_train.supported(self, obs):
+                return fused_mlp_train.fused_train_forward(self, obs)
         x = obs
         for i in range(len(self.fc)):
             x = self.fc[str(i)](x)
