@@ -2,7 +2,7 @@
 # Round-2 closing pass on one B200: full GPU suite, every bench configuration, ncu captures of
 # the driver's bench configuration, launch list.  Outputs under gpurun_out/final_r2_*.
 mkdir -p gpurun_out
-O=gpurun_out/final_r2
+O=gpurun_out/${FINAL_TAG:-final_r2}
 timeout 1500 python -m pytest tests -m gpu -q --tb=short 2>&1 | tail -8 | tee ${O}_gpu_suite.log
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | grep "smoke ok" | tee ${O}_smoke.log
 timeout 600 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > ${O}_ref_arm.json 2> ${O}_ref_arm.err
@@ -16,14 +16,14 @@ python - <<'PY'
 import json
 for f in ("ref_arm", "bench_driver", "bench_default", "bench_config3", "bench_config4_bpe2", "bench_config4_bpe1", "bench_train"):
     try:
-        d = json.loads(open(f"gpurun_out/final_r2_{f}.json").read().strip().splitlines()[-1])
+        d = json.loads(open(f"gpurun_out/" + __import__("os").environ.get("FINAL_TAG","final_r2") + f"_{f}.json").read().strip().splitlines()[-1])
         r = d.get("roofline") or {}
         print(f, "value", round(d["value"] / 1e6, 2), "M/s ms/step", round(d["ms_per_step"], 5),
               "kernel_ms", r.get("kernel_ms"), "frac", r.get("frac"), "e2e", round(d["e2e"]["value"] / 1e6, 1) if "e2e" in d else None,
               "launches", d.get("gpu_launches"))
         if "train" in d: print("   train", json.dumps(d["train"])[:400])
     except Exception as e:
-        print(f, "failed", e); print(open(f"gpurun_out/final_r2_{f}.err").read()[-1500:])
+        print(f, "failed", e); print(open(f"gpurun_out/" + __import__("os").environ.get("FINAL_TAG","final_r2") + f"_{f}.err").read()[-1500:])
 PY
 # ncu: the driver's bench configuration (--steps 20 --warmup 5), dominant kernel + MLP, then a launch list
 timeout 400 ncu --set full --import-source on --clock-control none -k regex:tag_continuous_kernel -s 30 -c 1 \

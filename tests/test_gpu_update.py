@@ -164,7 +164,7 @@ def test_cartpole_learns_with_the_fused_rollout_and_update(tmp_path):
     assert best > 1.5 * first, (first, best, [round(m, 1) for m in means[::10]])
 
 
-@pytest.mark.parametrize("heads", [(21, 21), (3,)])
+@pytest.mark.parametrize("heads", [(21, 21), (3,), (40, 30)])
 @pytest.mark.parametrize("rows_shape", [(7, 13, 5), (1000,)])
 def test_fused_train_forward_matches_module_autograd(heads, rows_shape):
     """models/fused_mlp_train.py (bias + ReLU in the GEMM epilogue, one GEMM for all heads,

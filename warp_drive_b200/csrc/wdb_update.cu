@@ -32,76 +32,120 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// Row blocks through shared memory: the 32 rows a warp works on are ONE contiguous block of
+// global memory (rows of 21 / 43 floats: 84 / 172-byte pitches, neither a multiple of the
+// sector size), so the warp copies the block with unit-stride accesses into a padded per-warp
+// tile (odd pitch: lane r walks row r without bank conflicts) and back.
+__device__ __forceinline__ void warp_block_load(float *tile, int pitch, const float *g, int width,
+                                                int n_rows, int lane) {
+  const int total = n_rows * width;
+  const int drow = 32 / width, dcol = 32 - drow * width;
+  int row = lane / width, col = lane - row * width;
+  for (int e = lane; e < total; e += 32) {
+    tile[row * pitch + col] = g[e];
+    row += drow; col += dcol;
+    if (col >= width) { col -= width; row++; }
+  }
+}
+__device__ __forceinline__ void warp_block_store(float *g, const float *tile, int pitch, int width,
+                                                 int n_rows, int lane) {
+  const int total = n_rows * width;
+  const int drow = 32 / width, dcol = 32 - drow * width;
+  int row = lane / width, col = lane - row * width;
+  for (int e = lane; e < total; e += 32) {
+    g[e] = tile[row * pitch + col];
+    row += drow; col += dcol;
+    if (col >= width) { col -= width; row++; }
+  }
+}
+
 // sums[0] = sum(-logp * adv), sums[1] = sum((V - R)^2), sums[2] = sum over heads of entropy,
 // sums[3] = sum(adv)  (PPO's surrogate at ratio == 1 is -mean(adv))
+// Dynamic shared memory: one tile of 32 x (max A | 1) floats per warp.
 __global__ void __launch_bounds__(kPgThreads)
-pg_loss_kernel(const __grid_constant__ wdb_pg_loss L) {
+pg_loss_kernel(const __grid_constant__ wdb_pg_loss L, int tile_pitch) {
+  extern __shared__ float pg_tiles[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float *tile = pg_tiles + (size_t)warp * 32 * tile_pitch;
   const long long per_t = (long long)L.n_envs * L.n_agents;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i0 = i - lane;                          // first index of this warp
   const bool live = i < per_t;
+  const int n_rows = (int)max(0ll, min(32ll, per_t - i0));   // rows of this warp that exist
   const int env = live ? (int)(i / L.n_agents) : 0;
   const double inv_m = 1.0 / ((double)L.T * (double)per_t);
   const float inv_mf = (float)inv_m;
   double s_pol = 0.0, s_vf = 0.0, s_ent = 0.0, s_adv = 0.0;
-  if (live) {
+  if (n_rows > 0) {
     float ret = 0.0f;
     for (int t = L.T - 1; t >= 0; t--) {
       const long long idx = (long long)t * per_t + i;
-      const int d = L.done[(long long)t * L.n_envs + env] > 0;
-      const float v = L.values[idx];
-      // a2c.py:80-93: returns[T-1] = done ? r : V ;  returns[t] = r + (done ? 0 : gamma * next)
-      if (t == L.T - 1) ret = d ? L.rewards[idx] : v;
-      else ret = L.rewards[idx] + (d ? 0.0f : L.gamma * ret);
-      if (L.returns) L.returns[idx] = ret;
-      const float adv = ret - v;
-      const float dv = v - ret;
-      s_vf += (double)dv * (double)dv;
-      s_adv += (double)adv;
-      if (L.grad_values) L.grad_values[idx] = 2.0f * L.vf_coeff * dv * inv_mf;
+      float adv = 0.0f;
+      if (live) {
+        const int d = L.done[(long long)t * L.n_envs + env] > 0;
+        const float v = L.values[idx];
+        // a2c.py:80-93: returns[T-1] = done ? r : V ;  returns[t] = r + (done ? 0 : gamma * next)
+        if (t == L.T - 1) ret = d ? L.rewards[idx] : v;
+        else ret = L.rewards[idx] + (d ? 0.0f : L.gamma * ret);
+        if (L.returns) L.returns[idx] = ret;
+        adv = ret - v;
+        const float dv = v - ret;
+        s_vf += (double)dv * (double)dv;
+        s_adv += (double)adv;
+        if (L.grad_values) L.grad_values[idx] = 2.0f * L.vf_coeff * dv * inv_mf;
+      }
       float logp = 0.0f;
       for (int k = 0; k < L.n_heads; k++) {
         const int A = L.n_actions[k];
-        const float *p = L.probs[k] + idx * A;
-        float *g = L.grad_probs[k] ? L.grad_probs[k] + idx * A : nullptr;
-        const int a = L.actions[idx * L.n_heads + k];
-        // torch.distributions.Categorical(probs=p): probs / sum, logits = log(clamp(probs,
-        // eps, 1 - eps)); log_prob = logits[a]; entropy = -sum(logits * probs)
-        float z = 0.0f;
-        for (int j = 0; j < A; j++) z += p[j];
-        const float inv_z = 1.0f / z;
-        // pass 1: entropy, log-prob and S = sum_i (dL/dq_i) q_i  (q = p / z)
-        float ent = 0.0f, S = 0.0f;
-        for (int j = 0; j < A; j++) {
-          const float q = p[j] * inv_z;
-          const bool inside = q > kProbEps && q < 1.0f - kProbEps;
-          const float lq = logf(fminf(fmaxf(q, kProbEps), 1.0f - kProbEps));
-          ent -= lq * q;
-          float gq = L.entropy_coeff * (lq + (inside ? 1.0f : 0.0f));   // -c_ent * dH/dq_j
-          if (j == a) {
-            logp += lq;
-            if (inside) gq -= adv / q;                                   // -adv * dlogp/dq_a
-          }
-          S += gq * q;
-        }
-        // pass 2: dL/dp_j = (dL/dq_j - S) / z, scaled by 1 / M
-        if (g) {
+        const long long blk = ((long long)t * per_t + i0) * A;   // the warp's 32 x A block
+        __syncwarp();
+        warp_block_load(tile, tile_pitch, L.probs[k] + blk, A, n_rows, lane);
+        __syncwarp();
+        if (live) {
+          float *p = tile + lane * tile_pitch;                 // this lane's row, overwritten by
+          const int a = L.actions[idx * L.n_heads + k];        // its gradient in pass 2
+          // torch.distributions.Categorical(probs=p): probs / sum, logits = log(clamp(probs,
+          // eps, 1 - eps)); log_prob = logits[a]; entropy = -sum(logits * probs)
+          float z = 0.0f;
+          for (int j = 0; j < A; j++) z += p[j];
+          const float inv_z = 1.0f / z;
+          // pass 1: entropy, log-prob and S = sum_i (dL/dq_i) q_i  (q = p / z)
+          float ent = 0.0f, S = 0.0f;
           for (int j = 0; j < A; j++) {
             const float q = p[j] * inv_z;
             const bool inside = q > kProbEps && q < 1.0f - kProbEps;
             const float lq = logf(fminf(fmaxf(q, kProbEps), 1.0f - kProbEps));
-            float gq = L.entropy_coeff * (lq + (inside ? 1.0f : 0.0f));
-            if (j == a && inside) gq -= adv / q;
-            g[j] = (gq - S) * inv_mf * inv_z;
+            ent -= lq * q;
+            float gq = L.entropy_coeff * (lq + (inside ? 1.0f : 0.0f));   // -c_ent * dH/dq_j
+            if (j == a) {
+              logp += lq;
+              if (inside) gq -= adv / q;                                   // -adv * dlogp/dq_a
+            }
+            S += gq * q;
           }
+          // pass 2: dL/dp_j = (dL/dq_j - S) / z, scaled by 1 / M
+          if (L.grad_probs[k]) {
+            for (int j = 0; j < A; j++) {
+              const float q = p[j] * inv_z;
+              const bool inside = q > kProbEps && q < 1.0f - kProbEps;
+              const float lq = logf(fminf(fmaxf(q, kProbEps), 1.0f - kProbEps));
+              float gq = L.entropy_coeff * (lq + (inside ? 1.0f : 0.0f));
+              if (j == a && inside) gq -= adv / q;
+              p[j] = (gq - S) * inv_mf * inv_z;
+            }
+          }
+          s_ent += (double)ent;
         }
-        s_ent += (double)ent;
+        if (L.grad_probs[k]) {
+          __syncwarp();
+          warp_block_store(L.grad_probs[k] + blk, tile, tile_pitch, A, n_rows, lane);
+        }
       }
-      s_pol += (double)(-logp * adv);
+      if (live) s_pol += (double)(-logp * adv);
     }
   }
   // block reduction -> 4 double atomics per CTA
   __shared__ double red[4][kPgThreads / 32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   s_pol = warp_sum(s_pol); s_vf = warp_sum(s_vf); s_ent = warp_sum(s_ent); s_adv = warp_sum(s_adv);
   if (lane == 0) { red[0][warp] = s_pol; red[1][warp] = s_vf; red[2][warp] = s_ent; red[3][warp] = s_adv; }
   __syncthreads();
@@ -159,56 +203,87 @@ adam_kernel(float *__restrict__ p, float *__restrict__ g, float *__restrict__ m,
 
 // ---- elementwise pieces of the MLP's training forward / backward (the GEMMs stay on cuBLAS;
 // these replace the separate torch kernels -- and tensor passes -- between them) ------------
-// logits [M, A0 + A1 + 1] (two action heads and the value column of ONE GEMM) -> softmax per
-// head into dense probs0 / probs1, value column into values.  One thread per row: the 32 rows of
-// a warp are one contiguous block, every sector is fetched once and re-used from L1.
-__global__ void __launch_bounds__(256)
+// logits [M, pitch] (two action heads and the value column of ONE GEMM) -> softmax per head
+// into dense probs0 / probs1, value column into values.  A warp stages its 32 rows through a
+// padded shared-memory tile (warp_block_load / _store): unit-stride global accesses.
+constexpr int kRowThreads = 128;
+__global__ void __launch_bounds__(kRowThreads)
 heads_softmax_kernel(const float *__restrict__ z, long long M, int A0, int A1, int ld,
-                     float *__restrict__ p0, float *__restrict__ p1, float *__restrict__ values) {
+                     float *__restrict__ p0, float *__restrict__ p1, float *__restrict__ values,
+                     int tile_pitch) {
+  extern __shared__ float row_tiles[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float *tile = row_tiles + (size_t)warp * 32 * tile_pitch;
   const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= M) return;
-  const float *row = z + r * ld;
-  for (int h = 0; h < 2; h++) {
-    const int n = h ? A1 : A0;
-    if (n == 0) continue;
-    const float *x = row + (h ? A0 : 0);
-    float *o = (h ? p1 : p0) + r * n;
-    float mx = x[0];
-    for (int j = 1; j < n; j++) mx = fmaxf(mx, x[j]);
-    float sum = 0.0f;
-    for (int j = 0; j < n; j++) sum += expf(x[j] - mx);
-    const float inv = 1.0f / sum;
-    for (int j = 0; j < n; j++) o[j] = expf(x[j] - mx) * inv;
+  const long long r0 = r - lane;
+  const int n_rows = (int)max(0ll, min(32ll, M - r0));
+  if (n_rows == 0) return;
+  const bool live = r < M;
+  warp_block_load(tile, tile_pitch, z + r0 * ld, ld, n_rows, lane);
+  __syncwarp();
+  float *row = tile + lane * tile_pitch;
+  if (live) {
+    for (int h = 0; h < 2; h++) {
+      const int n = h ? A1 : A0;
+      float *x = row + (h ? A0 : 0);
+      if (n == 0) continue;
+      float mx = x[0];
+      for (int j = 1; j < n; j++) mx = fmaxf(mx, x[j]);
+      float sum = 0.0f;
+      for (int j = 0; j < n; j++) { const float e = expf(x[j] - mx); x[j] = e; sum += e; }
+      const float inv = 1.0f / sum;
+      for (int j = 0; j < n; j++) x[j] *= inv;
+    }
+    values[r] = row[A0 + A1];
   }
-  values[r] = row[A0 + A1];
+  __syncwarp();
+  warp_block_store(p0 + r0 * A0, tile, tile_pitch, A0, n_rows, lane);
+  if (A1 > 0) warp_block_store(p1 + r0 * A1, tile + A0, tile_pitch, A1, n_rows, lane);
 }
 
-// d(logits) from d(probs): dz_j = p_j (g_j - sum_k g_k p_k) per head; value column = gv
-__global__ void __launch_bounds__(256)
+// d(logits) from d(probs): dz_j = p_j (g_j - sum_k g_k p_k) per head; value column = gv;
+// the padding columns of the pitch = 0
+__global__ void __launch_bounds__(kRowThreads)
 heads_softmax_backward_kernel(const float *__restrict__ p0, const float *__restrict__ p1,
                               const float *__restrict__ g0, const float *__restrict__ g1,
                               const float *__restrict__ gv, long long M, int A0, int A1,
-                              int ld, float *__restrict__ dz) {
+                              int ld, float *__restrict__ dz, int tile_pitch) {
+  extern __shared__ float row_tiles[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // two tiles per warp: probabilities (becomes dz, full pitch) and incoming gradients
+  float *tp = row_tiles + (size_t)warp * 64 * tile_pitch;
+  float *tg = tp + 32 * tile_pitch;
   const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= M) return;
-  float *row = dz + r * ld;
-  for (int h = 0; h < 2; h++) {
-    const int n = h ? A1 : A0;
-    if (n == 0) continue;
-    const float *p = (h ? p1 : p0) + r * n;
-    const float *g = h ? g1 : g0;
-    float *o = row + (h ? A0 : 0);
-    if (!g) {                                   // this head received no gradient
-      for (int j = 0; j < n; j++) o[j] = 0.0f;
-      continue;
+  const long long r0 = r - lane;
+  const int n_rows = (int)max(0ll, min(32ll, M - r0));
+  if (n_rows == 0) return;
+  const bool live = r < M;
+  warp_block_load(tp, tile_pitch, p0 + r0 * A0, A0, n_rows, lane);
+  if (A1 > 0) warp_block_load(tp + A0, tile_pitch, p1 + r0 * A1, A1, n_rows, lane);
+  if (g0) warp_block_load(tg, tile_pitch, g0 + r0 * A0, A0, n_rows, lane);
+  if (g1 && A1 > 0) warp_block_load(tg + A0, tile_pitch, g1 + r0 * A1, A1, n_rows, lane);
+  __syncwarp();
+  if (live) {
+    float *prow = tp + lane * tile_pitch;
+    const float *grow = tg + lane * tile_pitch;
+    for (int h = 0; h < 2; h++) {
+      const int n = h ? A1 : A0;
+      if (n == 0) continue;
+      float *p = prow + (h ? A0 : 0);
+      const float *g = grow + (h ? A0 : 0);
+      if (!(h ? g1 : g0)) {                       // this head received no gradient
+        for (int j = 0; j < n; j++) p[j] = 0.0f;
+        continue;
+      }
+      float dot = 0.0f;
+      for (int j = 0; j < n; j++) dot += g[j] * p[j];
+      for (int j = 0; j < n; j++) p[j] = p[j] * (g[j] - dot);
     }
-    g += r * n;
-    float dot = 0.0f;
-    for (int j = 0; j < n; j++) dot += g[j] * p[j];
-    for (int j = 0; j < n; j++) o[j] = p[j] * (g[j] - dot);
+    prow[A0 + A1] = gv ? gv[r] : 0.0f;
+    for (int j = A0 + A1 + 1; j < ld; j++) prow[j] = 0.0f;
   }
-  row[A0 + A1] = gv ? gv[r] : 0.0f;
-  for (int j = A0 + A1 + 1; j < ld; j++) row[j] = 0.0f;    // alignment padding of the pitch
+  __syncwarp();
+  warp_block_store(dz + r0 * ld, tp, tile_pitch, ld, n_rows, lane);
 }
 
 // ReLU backward in place + the bias gradient of the layer: dh[r, c] = h[r, c] > 0 ? dh[r, c] : 0,
@@ -299,7 +374,19 @@ WDB_API int wdb_pg_loss_and_grads(void *stream, const wdb_pg_loss *l) {
     if (!l->probs[k] || l->n_actions[k] < 1) return (int)cudaErrorInvalidValue;
   const long long n = (long long)l->n_envs * l->n_agents;
   const int grid = (int)((n + kPgThreads - 1) / kPgThreads);
-  pg_loss_kernel<<<grid, kPgThreads, 0, as_stream(stream)>>>(*l);
+  int amax = 1;
+  for (int k = 0; k < l->n_heads; k++) amax = l->n_actions[k] > amax ? l->n_actions[k] : amax;
+  const int pitch = amax | 1;                                   // odd: no bank conflicts
+  const size_t smem = (size_t)(kPgThreads / 32) * 32 * pitch * sizeof(float);
+  if (smem > 200 * 1024) return (int)cudaErrorInvalidValue;
+  static size_t configured = 48 * 1024;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(pg_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = smem;
+  }
+  pg_loss_kernel<<<grid, kPgThreads, smem, as_stream(stream)>>>(*l, pitch);
   return finish_launch();
 }
 
@@ -331,8 +418,21 @@ WDB_API int wdb_heads_softmax(void *stream, const float *logits, long long rows,
   if (!logits || !probs0 || !values || rows < 1 || A0 < 1 || A1 < 0 || (A1 > 0 && !probs1) ||
       pitch < A0 + A1 + 1)
     return (int)cudaErrorInvalidValue;
-  heads_softmax_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, as_stream(stream)>>>(
-      logits, rows, A0, A1, pitch, probs0, probs1, values);
+  const int tp = pitch | 1;
+  const size_t smem = (size_t)(kRowThreads / 32) * 32 * tp * sizeof(float);
+  if (smem > 200 * 1024) return (int)cudaErrorInvalidValue;
+  {
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+      cudaError_t e = cudaFuncSetAttribute(heads_softmax_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      configured = smem;
+    }
+  }
+  heads_softmax_kernel<<<(unsigned)((rows + kRowThreads - 1) / kRowThreads), kRowThreads, smem,
+                         as_stream(stream)>>>(logits, rows, A0, A1, pitch, probs0, probs1, values,
+                                              tp);
   return finish_launch();
 }
 
@@ -343,8 +443,21 @@ WDB_API int wdb_heads_softmax_backward(void *stream, const float *probs0, const 
   if (!probs0 || !grad_logits || rows < 1 || A0 < 1 || A1 < 0 || (A1 > 0 && !probs1) ||
       pitch < A0 + A1 + 1)
     return (int)cudaErrorInvalidValue;
-  heads_softmax_backward_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, as_stream(stream)>>>(
-      probs0, probs1, grad_probs0, grad_probs1, grad_values, rows, A0, A1, pitch, grad_logits);
+  const int tp = pitch | 1;
+  const size_t smem = (size_t)(kRowThreads / 32) * 64 * tp * sizeof(float);
+  if (smem > 200 * 1024) return (int)cudaErrorInvalidValue;
+  {
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+      cudaError_t e = cudaFuncSetAttribute(heads_softmax_backward_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      configured = smem;
+    }
+  }
+  heads_softmax_backward_kernel<<<(unsigned)((rows + kRowThreads - 1) / kRowThreads), kRowThreads,
+                                  smem, as_stream(stream)>>>(
+      probs0, probs1, grad_probs0, grad_probs1, grad_values, rows, A0, A1, pitch, grad_logits, tp);
   return finish_launch();
 }
 
