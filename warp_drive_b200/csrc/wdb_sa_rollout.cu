@@ -61,7 +61,14 @@ __device__ __forceinline__ int sa_search(const float *cdf, float p, int r) {
 // dependent chain per timestep is ~1/7 of a one-thread-per-env layout and eight times as many
 // warps are in flight.  All control flow is warp-uniform (groups past n_envs compute on
 // clamped indices and skip their stores).
-__global__ void __launch_bounds__(kSaThreads)
+// Residency: the kernel loops over ALL timesteps, so a grid that does not fit the GPU in ONE
+// wave pays the whole rollout twice.  At 128 registers 8 CTAs of 64 threads fit an SM: 1184
+// slots for BASELINE config 3's 1250 CTAs (10 000 envs) -- 1.06 waves, the last 5 % of the envs
+// doubled the time.  Capped at 96 registers (a few bytes of spills) 10 CTAs fit: 1480 slots.
+// (16-byte weight / activation loads in the forward, 5 loads per 16 FMAs instead of 20, were
+// measured neutral: 6.66 vs 6.55 us per timestep -- the step is bound by lane 0's serial
+// softmax / sample / physics chain, not by the forward's load count.)
+__global__ void __launch_bounds__(kSaThreads, 9)
 sa_rollout_kernel(const __grid_constant__ wdb_sa_rollout R) {
   extern __shared__ float s_w[];               // per layer: [Wt (in x out) | b (out)]
   __shared__ int s_dims[8];                    // layer widths (dynamic indexing of the kernel
