@@ -14,13 +14,14 @@ PHASES_V2 = [(0, 60, "sample_row_regs (register CDF + mask search)"), (60, 232, 
              (530, 560, "kk / ids store + bookkeeping loads"), (560, 600, "rewards"),
              (600, 650, "finalize rewards / done / pushes"), (650, 700, "feature chunks"),
              (700, 770, "chunk copy-out"), (770, 100000, "reset")]
-PHASES = [(0, 560, "inlined helpers (scan, sort network, division, CDF)"),
-          (560, 650, "prologue loads"), (650, 722, "sampling + kinematics"),
-          (722, 790, "obs setup / bookkeeping loads"),
-          (790, 900, "history scan + extract + sort"),
-          (900, 1010, "verification / exact / network paths"), (1010, 1106, "features"),
-          (1106, 1156, "barrier + TMA store issue"), (1156, 1200, "rewards"),
-          (1200, 1300, "barrier + push / bookkeeping"), (1300, 100000, "reset")]
+PHASES = [(0, 53, "file-level helpers"), (53, 176, "setup + probability TMA requests"),
+          (176, 290, "prologue loads (state, ids, tables)"),
+          (290, 365, "sampling + kinematics"),
+          (365, 427, "obs setup / key planes"),
+          (427, 546, "history scan + extract + sort (+ network fallback)"),
+          (546, 660, "verification / exact path"), (660, 760, "features"),
+          (760, 810, "barrier + TMA store issue + bookkeeping loads"), (810, 852, "rewards"),
+          (852, 948, "barrier + push / bookkeeping"), (948, 100000, "reset")]
 
 
 def main():
