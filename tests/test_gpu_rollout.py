@@ -392,3 +392,33 @@ def test_generic_path_native_moves_equal_torch_indexing():
     for p in pm:
         a, b = float(ea.episodic_reward_sum[p]), float(eb.episodic_reward_sum[p])
         assert abs(a - b) <= 1e-4 * max(1.0, abs(b)), (p, a, b)
+
+
+def test_bookkeep_treats_any_nonzero_done_flag_as_done():
+    """MountainCar writes done == 2 at the goal: the batch keeps the raw flag (neg / pos env
+    sampling tests for == 2) while the episodic sums count the env ONCE and the running sums
+    are cleared, not sign-flipped."""
+    E, T = 6, 2
+    w, e, pm = _engine(E, T, False, False)
+    dm = w.cuda_data_manager
+    done = dm.data_on_device_via_torch("_done_")
+    done.copy_(torch.tensor([0, 1, 2, 0, 2, 0], dtype=done.dtype, device="cuda"))
+    rewards = dm.data_on_device_via_torch("rewards")
+    rewards.copy_(torch.arange(rewards.numel(), device="cuda").view_as(rewards).float() * 0.25)
+    for p in pm:
+        e.reward_running_sum[p].fill_(1.0)
+    e.step_running_sum.fill_(4)
+    before = {p: e.reward_running_sum[p].clone() for p in pm}
+    e.bookkeep(1)
+    torch.cuda.synchronize()
+    assert dm.data_on_device_via_torch("done_flags_batch")[1].tolist() == [0, 1, 2, 0, 2, 0]
+    is_done = torch.tensor([False, True, True, False, True, False], device="cuda")
+    assert e.step_running_sum.tolist() == [5, 0, 0, 5, 0, 5]
+    assert int(e.num_completed_episodes) == 3 and int(e.episodic_step_sum) == 15
+    for p, ids in pm.items():
+        r_p = rewards[:, ids]
+        assert torch.equal(dm.data_on_device_via_torch(f"rewards_batch_{p}")[1], r_p)
+        run = before[p] + r_p
+        assert torch.equal(e.reward_running_sum[p], torch.where(is_done[:, None], 0.0 * run, run))
+        want = float(run[is_done].sum())
+        assert abs(float(e.episodic_reward_sum[p]) - want) <= 1e-4 * max(1.0, abs(want))
