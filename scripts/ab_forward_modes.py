@@ -1,8 +1,10 @@
 #!/usr/bin/env python
 """Interleaved A/B of the rollout-step launch modes at BASELINE config 2, in ONE process:
-  pair+pdl   both policies' forwards in one launch, programmatic dependent launches
-  pair       one launch, plain stream order
-  fork       one launch per policy on two streams (fork / join by events)
+  fork       one forward launch per policy on two streams (fork / join by events): the default
+  fork+tail  the same, env kernel with the last partial wave as one-env CTAs (tc_tail_split)
+  pair       both policies' forwards in one launch, plain stream order
+  pair+pdl   ... plus programmatic dependent launches
+(AB_MODES=a,b restricts the set.)
 Each mode gets its own engine (same seed) and CUDA graph of T steps; the modes are timed
 round-robin (CUDA events around `reps` replays) so clock / thermal drift hits all alike.
 Prints one JSON object: per mode the per-round ms per step and the median."""
@@ -24,16 +26,26 @@ def main():
     rounds = int(os.environ.get("AB_ROUNDS", 7))
     reps = int(os.environ.get("AB_REPS", 10))
     L = wlib.load()
-    modes = {"pair+pdl": (True, 1), "pair": (True, 0), "fork": (False, 0)}
+    # name -> (both policies in one launch?, library options while this engine's graph is captured)
+    modes = {"fork+tail": (False, {"pdl": 0, "tc_tail_split": 1}),
+             "fork": (False, {"pdl": 0, "tc_tail_split": 0}),
+             "pair": (True, {"pdl": 0, "tc_tail_split": 0}),
+             "pair+pdl": (True, {"pdl": 1, "tc_tail_split": 0})}
+    only = os.environ.get("AB_MODES")
+    if only:
+        modes = {k: v for k, v in modes.items() if k in only.split(",")}
+    defaults = {"pdl": 0, "tc_tail_split": 0}
     engines = {}
-    for name, (pair, pdl) in modes.items():
-        assert L.wdb_set_option(b"pdl", pdl) == 0
+    for name, (pair, opts) in modes.items():
+        for k, v in opts.items():
+            assert L.wdb_set_option(k.encode(), v) == 0
         _w, eng, _s, _pm = bench.build_engine(E, seed=1234, graph_steps=T, pair_forward=pair)
-        for _ in range(3):          # capture (with this mode's pdl setting) + warm replays
+        for _ in range(3):          # capture (with this mode's options) + warm replays
             eng.rollout()
         torch.cuda.synchronize()
         engines[name] = (eng, _w)
-    L.wdb_set_option(b"pdl", 0)
+    for k, v in defaults.items():
+        L.wdb_set_option(k.encode(), v)
     out = {k: [] for k in modes}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     for _ in range(rounds):

@@ -557,3 +557,20 @@ def test_tag_continuous_large_agent_counts_vs_reference_cuda(wdb_lib, N, n_tagge
         b_st["num_runners"].copy_(a_st["num_runners"])
         b_st["_done_"].copy_(a_st["_done_"])
 
+
+
+@pytest.mark.parametrize("shape", [(4, 23), (8, 105)])
+def test_tail_split_ctas_bit_exact_vs_reference_cuda(wdb_lib, shape, tc_history):
+    """`tc_tail_split`: the envs of a partly filled last wave go out as ONE-env CTAs (config 2:
+    592 three-env CTAs + 224 one-env CTAs).  Option value 2 forces half of the CTAs into that
+    shape at any size: same bits as the reference kernel, step-only and through the fused
+    rollout step."""
+    import test_gpu_rollout as roll
+
+    assert wdb_lib.wdb_set_option(b"tc_tail_split", 2) == 0
+    try:
+        test_tag_continuous_bit_exact_vs_reference_cuda(wdb_lib, shape, False, tc_history)
+        roll.test_fused_step_equals_separate_calls(False)
+        roll.test_engine_cuda_graph_matches_eager(True)
+    finally:
+        assert wdb_lib.wdb_set_option(b"tc_tail_split", 0) == 0

@@ -35,6 +35,8 @@ struct TcParams {
   int use_full_obs, runner_exits, stage_obs, scratch_in_smem, id_bits;
   int use_history, scr_warp_bytes;   // per-warp scratch: history candidate list / exact path
   int force_exact;                   // A/B switch: every agent takes the exact (reference-literal) path
+  int full_ctas;                     // CTAs [0, full_ctas) carry epb envs each, the rest ONE env each
+                                     // (the tail of the last wave as small CTAs); >= grid: all full
   float *loc_x, *loc_y, *speed, *direction, *acceleration;
   const int *agent_types;
   float *edge_pen;
