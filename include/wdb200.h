@@ -435,6 +435,8 @@ int wdb_heads_softmax_backward(void *stream, const float *probs0, const float *p
                                const float *grad_probs0, const float *grad_probs1,
                                const float *grad_values, long long rows, int A0, int A1,
                                int pitch, float *grad_logits);
+int wdb_pad_rows(void *stream, const float *src, long long rows, int width, int pitch,
+                 float *dst /* [rows, pitch], columns >= width zero-filled */);
 int wdb_relu_backward_bias_rows(long long rows);
 int wdb_relu_backward_bias(void *stream, float *grad_hidden, const float *hidden,
                            long long rows, int width, float *partial_bias_grads);

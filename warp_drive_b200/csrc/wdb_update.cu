@@ -363,6 +363,21 @@ relu_backward_bias_scalar_kernel(float *__restrict__ dh, const float *__restrict
   }
 }
 
+
+// rows of `width` floats -> rows of `pitch` >= width floats, zero-filled (the 16-byte-aligned
+// copy of the observations the first-layer GEMMs read); one thread per output element
+__global__ void __launch_bounds__(256)
+pad_rows_kernel(const float *__restrict__ src, long long rows, int width, int pitch,
+                float *__restrict__ dst) {
+  const long long n = rows * pitch;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / pitch;
+    const int c = (int)(i - r * pitch);
+    dst[i] = c < width ? src[r * width + c] : 0.0f;
+  }
+}
+
 }  // namespace
 
 WDB_API int wdb_pg_loss_and_grads(void *stream, const wdb_pg_loss *l) {
@@ -483,5 +498,14 @@ WDB_API int wdb_relu_backward_bias(void *stream, float *grad_hidden, const float
   else
     relu_backward_bias_scalar_kernel<<<(unsigned)ctas, 256, 0, as_stream(stream)>>>(
         grad_hidden, hidden, rows, width, per, partial_bias_grads);
+  return finish_launch();
+}
+
+WDB_API int wdb_pad_rows(void *stream, const float *src, long long rows, int width, int pitch,
+                         float *dst) {
+  if (!src || !dst || rows < 1 || width < 1 || pitch < width) return (int)cudaErrorInvalidValue;
+  long long blocks = (rows * pitch + 255) / 256;
+  if (blocks > 32ll * kNumSMs) blocks = 32ll * kNumSMs;
+  pad_rows_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(src, rows, width, pitch, dst);
   return finish_launch();
 }

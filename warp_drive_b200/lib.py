@@ -189,6 +189,7 @@ _SIGNATURES = {
     "wdb_pg_loss_and_grads": (_i, [_vp, ctypes.POINTER(PgLoss)]),
     "wdb_heads_softmax": (_i, [_vp, _vp, _ll, _i, _i, _i, _vp, _vp, _vp]),
     "wdb_heads_softmax_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _vp]),
+    "wdb_pad_rows": (_i, [_vp, _vp, _ll, _i, _i, _vp]),
     "wdb_relu_backward_bias_rows": (_i, [_ll]),
     "wdb_relu_backward_bias": (_i, [_vp, _vp, _vp, _ll, _i, _vp]),
     "wdb_grad_sumsq": (_i, [_vp, _vp, _ll, _vp]),
