@@ -181,7 +181,7 @@ class Trainer:
 
         total = sum(FlatAdam.numel(self.models[p].parameters()) for p in self.policies)
         dev = next(self.models[self.policies[0]].parameters()).device
-        self._arena_params = torch.empty(total, dtype=torch.float32, device=dev)
+        self._arena_params = torch.zeros(total, dtype=torch.float32, device=dev)
         self._arena_grads = torch.zeros(total, dtype=torch.float32, device=dev)
         self._arena_off = 0
         for policy in self.policies:

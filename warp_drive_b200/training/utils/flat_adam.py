@@ -12,20 +12,27 @@ import torch
 from warp_drive_b200 import lib as _lib
 
 
+def _slot(k):
+    """Arena elements reserved for a tensor of k elements: every tensor starts on a 16-byte
+    boundary (cuBLASLt's fused epilogues and 16-byte loads need aligned weight / bias
+    pointers); the padding holds zeros, receives zero gradients and never moves."""
+    return (k + 3) // 4 * 4
+
+
 class FlatAdam:
     @staticmethod
     def numel(parameters):
-        return sum(p.numel() for p in parameters if p.requires_grad)
+        return sum(_slot(p.numel()) for p in parameters if p.requires_grad)
 
     def __init__(self, parameters, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, arena=None):
         """arena: optional (params, grads) flat float32 tensors of exactly numel(parameters)
-        elements (slices of a larger arena shared by several policies, so that ONE
+        elements (numel() counts every tensor rounded up to 4 elements) (slices of a larger arena shared by several policies, so that ONE
         all-reduce covers all of them)."""
         self.param_list = [p for p in parameters if p.requires_grad]
         assert self.param_list, "no trainable parameters"
         dev = self.param_list[0].device
         assert dev.type == "cuda", "FlatAdam runs on the GPU (no CPU fallback)"
-        n = sum(p.numel() for p in self.param_list)
+        n = sum(_slot(p.numel()) for p in self.param_list)
         self.n = n
         if arena is not None:
             self.params, self.grads = arena
@@ -33,7 +40,7 @@ class FlatAdam:
             assert self.params.is_contiguous() and self.grads.is_contiguous()
             self.grads.zero_()
         else:
-            self.params = torch.empty(n, dtype=torch.float32, device=dev)
+            self.params = torch.zeros(n, dtype=torch.float32, device=dev)
             self.grads = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
@@ -44,7 +51,7 @@ class FlatAdam:
             self.params[off:off + k].copy_(p.data.reshape(-1))
             p.data = self.params[off:off + k].view_as(p)
             p.grad = self.grads[off:off + k].view_as(p)
-            off += k
+            off += _slot(k)
         self.lr, self.betas, self.eps = float(lr), betas, float(eps)
         self.step_count = 0
         # torch.optim-style handle so that schedulers / callers can set group["lr"]
@@ -59,7 +66,7 @@ class FlatAdam:
             k = p.numel()
             if p.grad is None or p.grad.data_ptr() != self.grads[off:off + k].data_ptr():
                 p.grad = self.grads[off:off + k].view_as(p)
-            off += k
+            off += _slot(k)
 
     def grad_norm(self):
         """Device tensor holding the 2-norm of the (unclipped) flat gradient."""
