@@ -72,3 +72,41 @@ def test_wide_kernel_shared_memory_budget_formula():
     env2.reset()
     env2.get_data_dictionary()
     assert env2.allocate_reference_scratch              # K + 2 > 16: the packed kernel's exact path
+
+
+def test_weight_gradient_chunking_equals_plain_product():
+    """fused_mlp_train._wgrad: a^T b as a batched GEMM over row chunks + a sum of the partials
+    (the layout that streams at the HBM peak on the GPU) -- same result as the plain product,
+    and the plain product when the row count does not split."""
+    import torch
+
+    from warp_drive_b200.training.models.fused_mlp_train import _wgrad
+
+    g = torch.Generator().manual_seed(0)
+    for rows in (16 * 8192, 2 * 8192 + 2, 1000):
+        a = torch.randn(rows, 12, generator=g, dtype=torch.float64)
+        b = torch.randn(rows, 7, generator=g, dtype=torch.float64)
+        assert torch.allclose(_wgrad(a, b), a.t() @ b, rtol=1e-12, atol=1e-9), rows
+
+
+def test_fused_train_forward_is_not_taken_off_the_gpu():
+    """The fused training node needs CUDA float32 tensors: on CPU tensors the model keeps the
+    plain module path (and still differentiates)."""
+    import torch
+
+    from warp_drive_b200.training.models import fused_mlp_train
+
+    class M(torch.nn.Module):
+        is_deterministic = False
+        action_mask = None
+        output_dims = [3]
+
+        def __init__(self):
+            super().__init__()
+            self.fc = torch.nn.ModuleDict({
+                "0": torch.nn.Sequential(torch.nn.Linear(5, 8), torch.nn.ReLU()),
+                "1": torch.nn.Sequential(torch.nn.Linear(8, 8), torch.nn.ReLU())})
+            self.policy_head = torch.nn.ModuleList([torch.nn.Linear(8, 3)])
+            self.vf_head = torch.nn.Linear(8, 1)
+
+    assert not fused_mlp_train.supported(M(), torch.randn(4, 5))
