@@ -2,6 +2,7 @@
 """Interleaved A/B of the rollout-step launch modes at BASELINE config 2, in ONE process:
   fork       one forward launch per policy on two streams (fork / join by events): the default
   fork+tail  the same, env kernel with the last partial wave as one-env CTAs (tc_tail_split)
+  fork+pdlenv  the same, env step launched programmatically dependent on the runner forward
   pair       both policies' forwards in one launch, plain stream order
   pair+pdl   ... plus programmatic dependent launches
 (AB_MODES=a,b restricts the set.)
@@ -27,7 +28,8 @@ def main():
     reps = int(os.environ.get("AB_REPS", 10))
     L = wlib.load()
     # name -> (both policies in one launch?, library options while this engine's graph is captured)
-    modes = {"fork+tail": (False, {"pdl": 0, "tc_tail_split": 1}),
+    modes = {"fork+pdlenv": (False, {"pdl": 1, "tc_tail_split": 0}),
+             "fork+tail": (False, {"pdl": 0, "tc_tail_split": 1}),
              "fork": (False, {"pdl": 0, "tc_tail_split": 0}),
              "pair": (True, {"pdl": 0, "tc_tail_split": 0}),
              "pair+pdl": (True, {"pdl": 1, "tc_tail_split": 0})}
@@ -40,6 +42,7 @@ def main():
         for k, v in opts.items():
             assert L.wdb_set_option(k.encode(), v) == 0
         _w, eng, _s, _pm = bench.build_engine(E, seed=1234, graph_steps=T, pair_forward=pair)
+        eng.pdl_after_fork = name == "fork+pdlenv"
         for _ in range(3):          # capture (with this mode's options) + warm replays
             eng.rollout()
         torch.cuda.synchronize()

@@ -29,6 +29,9 @@ class RolloutEngine:
                  use_fused_forward=True, use_obs_tiles=False, use_pair_forward=False):
         self.env_wrapper = env_wrapper
         self.use_pair_forward = bool(use_pair_forward)
+        # A/B switch: with one forward launch per policy, launch the env step programmatically
+        # dependent on the main-stream forward (option "pdl" must be on as well)
+        self.pdl_after_fork = False
         self.dm = env_wrapper.cuda_data_manager
         self.models = models
         self.policy_map = policy_tag_to_agent_id_map
@@ -242,7 +245,7 @@ class RolloutEngine:
         self._one_forward(p, obs_in, probs, share[p])
         for ev in joins:
             cur.wait_event(ev)
-        return False
+        return self.pdl_after_fork
 
     def _one_forward(self, p, obs_in, probs, max_ctas=0):
         if self.obs_tiles:
