@@ -1,0 +1,15 @@
+#!/bin/bash
+mkdir -p gpurun_out
+O=gpurun_out/r2ae
+timeout 600 python -m pytest tests/test_gpu_update.py tests/test_gpu_training.py -m gpu -q --tb=short 2>&1 | tail -4 | tee ${O}_tests.log
+timeout 300 python bench.py --mode train --steps 40 --warmup 10 > ${O}_train.json 2> ${O}_train.err
+python - <<'PY'
+import json
+try:
+    d = json.loads(open("gpurun_out/r2ae_train.json").read().strip().splitlines()[-1])
+    t = d.get("train") or {}
+    print("train value", round(d["value"]/1e6,2), "M/s iteration_ms", t.get("iteration_ms"), "rollout", t.get("rollout_ms"), "update", t.get("update_ms"))
+except Exception as e:
+    print("failed", e); print(open("gpurun_out/r2ae_train.err").read()[-2000:])
+PY
+exit 0

@@ -41,11 +41,21 @@ __device__ __forceinline__ void warp_block_load(float *tile, int pitch, const fl
   const int total = n_rows * width;
   const int drow = 32 / width, dcol = 32 - drow * width;
   int row = lane / width, col = lane - row * width;
-  for (int e = lane; e < total; e += 32) {
-    tile[row * pitch + col] = g[e];
-    row += drow; col += dcol;
+  int e = lane;
+  // four loads in flight per lane before the first shared-memory store waits for one of them
+  for (; e + 96 < total; e += 128) {
+    const float v0 = g[e], v1 = g[e + 32], v2 = g[e + 64], v3 = g[e + 96];
+#define WDB_PUT(V)                                   \
+    tile[row * pitch + col] = V;                     \
+    row += drow; col += dcol;                        \
     if (col >= width) { col -= width; row++; }
+    WDB_PUT(v0) WDB_PUT(v1) WDB_PUT(v2) WDB_PUT(v3)
   }
+  for (; e < total; e += 32) {
+    const float v = g[e];
+    WDB_PUT(v)
+  }
+#undef WDB_PUT
 }
 __device__ __forceinline__ void warp_block_store(float *g, const float *tile, int pitch, int width,
                                                  int n_rows, int lane) {
